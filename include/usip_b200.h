@@ -1,0 +1,184 @@
+/* usip_b200.h -- C ABI of libusip_b200.so: the B200 (sm_100a) drop-in for the USIP detector /
+ * descriptor hot path.  Plain pointers and sizes only: no torch types, no C++ in the signatures.
+ *
+ * Conventions (all functions):
+ *   - every pointer is a DEVICE pointer unless the name says `host`; tensors are dense, row-major;
+ *   - the caller owns and pre-allocates every buffer; the library keeps no global state;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, nothing synchronises;
+ *   - the return value is 0 on success, otherwise a cudaError_t (or -1 for invalid arguments);
+ *   - "(B,C,N)" etc. are the REFERENCE layouts (channel-major), "[P,C]" are this library's internal
+ *     row-major point-major activations (row = one point / one group sample, C contiguous).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to lijx10/USIP).
+ */
+#ifndef USIP_B200_H_
+#define USIP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USIP_B200_ABI_VERSION 1
+int usip_abi_version(void);
+/* name of the last failing check/launch for the calling thread ("" if none); host pointer */
+const char* usip_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Reference operator modules (plugin API B-1)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* index_max.forward_cuda_shared_mem / forward_cuda          models/index_max_ext/index_max.cpp:132-148,
+ * kernels models/index_max_ext/index_max_cuda.cu:9-25,29-61.
+ * data (B,C,N) f32, index (B,N) i32 in [0,K) -> out_idx (B,C,K) i32: smallest n attaining
+ * max{data[b,c,n] : index[b,n]==k, data > -1000}, else 0.  No B*K shared-memory cap.
+ * scratch: B*C*K u64 (packed running max), may not alias anything. */
+int usip_index_max_f32(const float* data, const int32_t* index, int32_t* out_idx,
+                       unsigned long long* scratch, int B, int C, int N, int K, void* stream);
+
+/* ball_query.forward_cuda_shared_mem                        models/ball_query_ext/ball_query.cpp:33-39,
+ * kernel models/ball_query_ext/ball_query_cuda.cu:10-49.
+ * dist (B,M,N) f32 -> out_idx (B,M,K) i32: first K n (ascending) with dist<=radius; 0 hits -> 0;
+ * u<K hits -> out[u+i] = out[i % u]. */
+int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
+                             int B, int M, int N, int K, void* stream);
+
+/* Fused replacement of models/networks.py:355-373 (distance matrix + ball_query + gather + decenter):
+ * xyz (B,3,N), feat (B,S,N) (S may be 0), centers (B,3,M) ->
+ *   out_idx (B,M,K) i32      (bit-identical to ball_query on torch.norm(centers-xyz))
+ *   out_group (B,3+S,M,K) f32 = x_aug gathered, xyz channels minus the centre  (`x_features`)
+ * scratch_i32: B*(N + 2*cells+2) + ... see usip_ball_group_scratch_bytes(). */
+int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
+                        int32_t* out_idx, float* out_group, void* scratch, int64_t scratch_bytes,
+                        int B, int S, int N, int M, int K, void* stream);
+int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
+
+/* operations.knn_gather_by_indexing                         models/operations.py:271-287
+ * src (B,C,N), idx (B,M,K) i32 -> out (B,C,M,K): out[b,c,m,k] = src[b,c,idx[b,m,k]]. */
+int usip_knn_gather_f32(const float* src, const int32_t* idx, float* out,
+                        int B, int C, int N, int M, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Grouping front-end of RPN_Detector.forward            models/networks.py:85-108, util/som.py:17-54
+ * ---------------------------------------------------------------------------------------------- */
+
+/* som.query_topk(k=1): nearest node per point, fp32 (dx*dx+dy*dy)+dz*dz, ties -> smallest m.
+ * xyz (B,3,N), node (B,3,M) -> min_idx (B,N) i32, count (B,M) i32 (must be zeroed by the caller). */
+int usip_som_assign_f32(const float* xyz, const float* node, int32_t* min_idx, int32_t* count,
+                        int B, int N, int M, void* stream);
+
+/* Stable counting sort of the points of every cloud by node id.
+ *   seg_off (B,M+1) i32 : rows [seg_off[m], seg_off[m+1]) of cloud b belong to node m
+ *   perm    (B,N)   i32 : sorted position -> original point index n (ascending n inside a node)
+ *   row_seg (B,N)   i32 : b*M + node id of each sorted row
+ * scratch: B * ceil(N/256) * M i32. */
+int usip_cluster_sort(const int32_t* min_idx, int32_t* seg_off, int32_t* perm, int32_t* row_seg,
+                      int32_t* scratch, int B, int N, int M, void* stream);
+
+/* networks.py:87-108: cluster mean (sum/(count+1e-5), empty -> 0), decentre, concat sn.
+ *   cluster_mean (B,3,M) f32 ; x_aug [B*N, ldx] (sorted rows; cols 0..2 = x - mean[node], 3..3+S-1 = sn,
+ *   remaining cols up to ldx zero). */
+int usip_cluster_mean_decenter(const float* xyz, const float* feat, const int32_t* seg_off,
+                               const int32_t* perm, float* cluster_mean, float* x_aug, int ldx,
+                               int B, int S, int N, int M, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Shared-MLP stack: conv1x1 (+bias) with fused BN/ReLU prologue and BN-stat / group-max epilogue
+ *    models/layers.py:248-303 (EquivariantLayer), 172-216 (MyConv2d), 23-121 (MyBatchNorm*)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct usip_layer_desc {
+  const float* X;  int32_t ldx;        /* [P,Cin] input (pre-activation of the previous layer)       */
+  int32_t P, Cin, Cout;
+  const float* W;  int32_t ldw;        /* [Cout,Cin] weight rows, row stride ldw (conv weight layout)  */
+  const float* bias;                   /* [Cout] or NULL                                              */
+  const float* in_scale;               /* [Cin] or NULL: a = x*in_scale+in_shift (folded BatchNorm)   */
+  const float* in_shift;
+  int32_t in_relu;                     /* apply ReLU after the affine                                 */
+  const float* addend; int32_t ld_add; /* optional [G,Cout] term added per row group                  */
+  const int32_t* add_index;            /* row -> g  (NULL: g = row / add_group)                       */
+  int32_t add_group;
+  float* Y; int32_t ldy;               /* [P,Cout] output (NULL: not written)                         */
+  float* stat_partial;                 /* [ntiles,2,Cout] per-tile (sum, sumsq) or NULL               */
+  float* gmax; float* gmin;            /* [P/group,Cout] per-group max / min of Y, or NULL            */
+  int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
+  int32_t group;
+  int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0)   */
+} usip_layer_desc;
+
+int usip_layer_fwd(const usip_layer_desc* d, void* stream);
+/* rows per stat tile (ntiles = ceil(P / usip_layer_tile_rows())) */
+int usip_layer_tile_rows(void);
+
+/* Training-mode BatchNorm finalisation (F.batch_norm, layers.py:69-71): reduce the per-tile partials,
+ * produce the folded affine scale = gamma/sqrt(var+eps), shift = beta - mean*scale, update running stats
+ * (momentum, unbiased var) and save mean / invstd for the backward pass. */
+int usip_bn_finalize(const float* stat_partial, int ntiles, int64_t count, int C,
+                     const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, float* scale, float* shift,
+                     float* save_mean, float* save_invstd, void* stream);
+/* Eval-mode: scale/shift from the running statistics. */
+int usip_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, int C, float* scale, float* shift, void* stream);
+
+/* Segmented max over the sorted rows of every node (index_max + gather of networks.py:117-120,130-133):
+ * X [B*N, ldx] -> pooled [B*M, ldp] (empty node -> 0), arg [B*M, C] i32 = global sorted row (or -1). */
+int usip_segmax(const float* X, int ldx, const int32_t* seg_off, const int32_t* perm,
+                float* pooled, int ldp, int32_t* arg, int B, int N, int M, int C, void* stream);
+
+/* Node kNN, layers.py:417-421: ascending sqrt-distance, ties by index.  pts (B,3,M) -> knn (B,M,K) i32. */
+int usip_knn_nodes(const float* pts, int32_t* knn_idx, int B, int M, int K, void* stream);
+
+/* First kNN-fusion layer without materialising the (B,3+C,M,K) group tensor (layers.py:422-432):
+ * Y[(b,m,k),:] = Z[b*M+knn[b,m,k],:] + Wxyz * (pts[b,:,knn]-pts[b,:,m]) + bias ; + BN stat partials. */
+int usip_knn_combine(const float* Z, int ldz, const float* pts, const int32_t* knn_idx,
+                     const float* W, int ldw, const float* bias, float* Y, int ldy, float* stat_partial,
+                     int B, int M, int K, int Cout, void* stream);
+
+/* out[q, c] = relu(scale[c]*(scale[c]>=0 ? gmax : gmin)[q,c] + shift[c])  == max_k relu(bn(y_k)) */
+int usip_group_select(const float* gmax, const float* gmin, const float* scale, const float* shift,
+                      float* out, int ldo, int Q, int C, void* stream);
+
+/* networks.py:151-154: keypoints (B,3,M) = out[:, :3] + cluster_mean ; sigmas (B,M) = softplus(out[:,3]) + lb */
+int usip_head_finalize(const float* out4, int ld, const float* cluster_mean, float sigma_lower_bound,
+                       float* keypoints, float* sigmas, int B, int M, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Losses                                                  models/losses.py:44-143
+ * ---------------------------------------------------------------------------------------------- */
+/* min_j ||a_i - b_j||_2 and argmin (first index on exact ties).  a (B,3,Ma), b (B,3,Nb) ->
+ * min_d (B,Ma) f32, arg (B,Ma) i32.  packed: B*Ma u64 scratch. */
+int usip_pairwise_min_f32(const float* a, const float* b, float* min_d, int32_t* arg,
+                          unsigned long long* packed, int B, int Ma, int Nb, void* stream);
+
+/* ChamferLoss_Brute sigma branch (losses.py:79-97) from the two pairwise-min results:
+ * out[0]=loss, out[1]=chamfer_pure, out[2]=chamfer_weighted. */
+int usip_chamfer_prob_reduce(const float* d_sd, const int32_t* i_sd, const float* d_ds, const int32_t* i_ds,
+                             const float* sig_src, const float* sig_dst, float* out3, int B, int M, int N,
+                             void* stream);
+
+/* keypoint_detector.py:182-184: out = R @ kp * scale + shift   (kp (B,3,M), R (B,3,3), scale (B), shift (B,3)) */
+int usip_transform_points(const float* kp, const float* R, const float* scale, const float* shift,
+                          float* out, int B, int M, void* stream);
+
+/* mean over (B,M) of d times alpha -> out[0]  (keypoint_detector.py:193-197) */
+int usip_mean_scale(const float* d, int64_t n, float alpha, float* out, void* stream);
+
+
+/* ---- backward of the loss kernels (autograd of models/losses.py / keypoint_detector.py:182-184) ---- */
+/* grad of sum_i g_i*gscale*min_d_i: grad_a (B,3,Ma) overwritten, grad_b (B,3,Nb) ACCUMULATED (pre-zero) or NULL */
+int usip_pairwise_min_bwd(const float* a, const float* b, const float* min_d, const int32_t* arg,
+                          const float* g, float gscale, float* grad_a, float* grad_b,
+                          int B, int Ma, int Nb, void* stream);
+/* all four grads ACCUMULATE into pre-zeroed buffers; gout = d loss_total / d chamfer_loss (device scalar) */
+int usip_chamfer_prob_bwd(const float* src, const float* dst, const float* sig_src, const float* sig_dst,
+                          const float* d_sd, const int32_t* i_sd, const float* d_ds, const int32_t* i_ds,
+                          const float* gout, float* g_src, float* g_dst, float* g_sig_src, float* g_sig_dst,
+                          int B, int M, int N, void* stream);
+int usip_transform_points_bwd(const float* g_out, const float* R, const float* scale, float* g_kp,
+                              int B, int M, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USIP_B200_H_ */

@@ -1,0 +1,264 @@
+// loss.cu -- tiled pairwise-L2 arg-min and the probabilistic chamfer reduction.
+// Reference: models/losses.py:50-99 (ChamferLoss_Brute), :125-143 (SingleSideChamferLoss_Brute),
+// models/keypoint_detector.py:182-197.
+#include "common.cuh"
+
+namespace usip {
+
+constexpr int PM_THREADS = 256;
+constexpr int PM_TILE = 1024;   // database points staged per CTA (float4 each -> 16 KB)
+
+__global__ void pm_init_kernel(unsigned long long* packed, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[i] = ~0ull;
+}
+
+// grid (ceil(Nb/PM_TILE), ceil(Ma/PM_THREADS), B): each thread owns one query a_i and scans one
+// shared-memory tile of b; partial results merge through a 64-bit atomicMin on (d2 bits << 32 | j),
+// which yields the first index among exact ties (d2 >= 0 so float bits order like uints).
+__global__ void __launch_bounds__(PM_THREADS)
+pairwise_min_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                    unsigned long long* __restrict__ packed, int Ma, int Nb) {
+  __shared__ float4 sb[PM_TILE];
+  const int bb = blockIdx.z;
+  const int i = blockIdx.y * PM_THREADS + threadIdx.x;
+  const int j0 = blockIdx.x * PM_TILE;
+  const int jc = min(PM_TILE, Nb - j0);
+  const float* pb = b + (size_t)bb * 3 * Nb;
+  for (int t = threadIdx.x; t < jc; t += PM_THREADS)
+    sb[t] = make_float4(pb[j0 + t], pb[Nb + j0 + t], pb[2 * Nb + j0 + t], 0.f);
+  __syncthreads();
+  if (i >= Ma) return;
+  const float* pa = a + (size_t)bb * 3 * Ma;
+  const float ax = pa[i], ay = pa[Ma + i], az = pa[2 * Ma + i];
+  float best = INFINITY; int bj = 0;
+#pragma unroll 4
+  for (int t = 0; t < jc; ++t) {
+    float4 q = sb[t];
+    float d = sqdist_rn(ax, ay, az, q.x, q.y, q.z);
+    if (d < best) { best = d; bj = t; }
+  }
+  if (best == best && best < INFINITY) {
+    unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(j0 + bj);
+    atomicMin(&packed[(size_t)bb * Ma + i], key);
+  }
+}
+
+__global__ void pm_finish_kernel(const unsigned long long* __restrict__ packed, float* __restrict__ min_d,
+                                 int32_t* __restrict__ arg, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = packed[i];
+  bool none = (k == ~0ull);
+  float d2 = __uint_as_float((unsigned)(k >> 32));
+  if (min_d) min_d[i] = none ? INFINITY : __fsqrt_rn(d2);     // torch.norm = sqrt of the fp32 sum
+  if (arg) arg[i] = none ? 0 : (int32_t)(k & 0xffffffffull);
+}
+
+// block-wide deterministic double sum
+__device__ double block_sum(double v, double* sh) {
+  v = warp_sum_d(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  return r;   // valid on thread 0
+}
+
+// losses.py:79-97.  Single CTA (sizes are B*M ~ 1e4).
+__global__ void __launch_bounds__(1024)
+chamfer_prob_reduce_kernel(const float* __restrict__ d_sd, const int32_t* __restrict__ i_sd,
+                           const float* __restrict__ d_ds, const int32_t* __restrict__ i_ds,
+                           const float* __restrict__ sig_src, const float* __restrict__ sig_dst,
+                           float* __restrict__ out3, int B, int M, int N) {
+  __shared__ double sh[32];
+  double f_loss = 0, f_d = 0, f_inv = 0, f_wd = 0;
+  for (int t = threadIdx.x; t < B * M; t += blockDim.x) {
+    int b = t / M;
+    double s = 0.5 * ((double)sig_src[t] + (double)sig_dst[(size_t)b * N + i_sd[t]]);
+    double d = d_sd[t];
+    f_loss += log(s) + d / s; f_d += d; f_inv += 1.0 / s; f_wd += d / s;
+  }
+  double b_loss = 0, b_d = 0, b_inv = 0, b_wd = 0;
+  for (int t = threadIdx.x; t < B * N; t += blockDim.x) {
+    int b = t / N;
+    double s = 0.5 * ((double)sig_dst[t] + (double)sig_src[(size_t)b * M + i_ds[t]]);
+    double d = d_ds[t];
+    b_loss += log(s) + d / s; b_d += d; b_inv += 1.0 / s; b_wd += d / s;
+  }
+  double r[8] = {f_loss, f_d, f_inv, f_wd, b_loss, b_d, b_inv, b_wd};
+  for (int q = 0; q < 8; ++q) r[q] = block_sum(r[q], sh);
+  if (threadIdx.x == 0) {
+    double nf = (double)B * M, nb = (double)B * N;
+    out3[0] = (float)(r[0] / nf + r[4] / nb);
+    out3[1] = (float)(r[1] / nf + r[5] / nb);
+    // mean(w*d), w = (1/s)/mean(1/s)  ==  mean(d/s) / mean(1/s)
+    out3[2] = (float)((r[3] / nf) / (r[2] / nf) + (r[7] / nb) / (r[6] / nb));
+  }
+}
+
+__global__ void transform_points_kernel(const float* __restrict__ kp, const float* __restrict__ R,
+                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                        float* __restrict__ out, int B, int M) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * M) return;
+  int b = t / M, m = t - b * M;
+  const float* p = kp + (size_t)b * 3 * M;
+  const float x = p[m], y = p[M + m], z = p[2 * M + m];
+  const float* r = R + (size_t)b * 9;
+  const float s = scale[b];
+  for (int c = 0; c < 3; ++c) {
+    float v = r[c * 3 + 0] * x + r[c * 3 + 1] * y + r[c * 3 + 2] * z;   // torch.matmul(R, kp)
+    out[(size_t)b * 3 * M + (size_t)c * M + m] = v * s + shift[b * 3 + c];
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+mean_scale_kernel(const float* __restrict__ d, int64_t n, float alpha, float* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0;
+  for (int64_t t = threadIdx.x; t < n; t += blockDim.x) s += d[t];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = (float)(s / (double)n) * alpha;
+}
+
+
+// ---- backward kernels -------------------------------------------------------------------------
+// d/da_i ||a_i - b_j*|| = (a_i - b_j*)/d  (0 at d == 0, torch.norm's sub-gradient; losses.py:65)
+__global__ void pairwise_min_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                        const float* __restrict__ min_d, const int32_t* __restrict__ arg,
+                                        const float* __restrict__ g, float gscale, float* __restrict__ ga,
+                                        float* __restrict__ gb, int B, int Ma, int Nb) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * Ma) return;
+  int bb = t / Ma, i = t - bb * Ma;
+  int j = arg[t];
+  float d = min_d[t];
+  float gi = (g ? g[t] : 1.f) * gscale;
+  float inv = d > 0.f ? gi / d : 0.f;
+  const float* pa = a + (size_t)bb * 3 * Ma; const float* pb = b + (size_t)bb * 3 * Nb;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float diff = pa[(size_t)c * Ma + i] - pb[(size_t)c * Nb + j];
+    float v = diff * inv;
+    if (ga) ga[(size_t)bb * 3 * Ma + (size_t)c * Ma + i] = v;
+    if (gb) atomicAdd(&gb[(size_t)bb * 3 * Nb + (size_t)c * Nb + j], -v);
+  }
+}
+
+// backward of ChamferLoss_Brute's sigma branch (losses.py:79-90); all grads accumulate atomically into
+// pre-zeroed buffers.  dir 0: src->dst terms, dir 1: dst->src terms.
+__global__ void chamfer_prob_bwd_kernel(const float* __restrict__ src, const float* __restrict__ dst,
+                                        const float* __restrict__ sig_src, const float* __restrict__ sig_dst,
+                                        const float* __restrict__ d_sd, const int32_t* __restrict__ i_sd,
+                                        const float* __restrict__ d_ds, const int32_t* __restrict__ i_ds,
+                                        const float* __restrict__ gout, float* __restrict__ g_src,
+                                        float* __restrict__ g_dst, float* __restrict__ g_ss, float* __restrict__ g_sd,
+                                        int B, int M, int N) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nf = B * M, nb = B * N;
+  if (t >= nf + nb) return;
+  const float go = gout[0];
+  const bool fwd = t < nf;
+  const int u = fwd ? t : t - nf;
+  const int La = fwd ? M : N, Lb = fwd ? N : M;            // a = own set, b = other set
+  const int bb = u / La, i = u - bb * La;
+  const float* A = fwd ? src : dst; const float* Bm = fwd ? dst : src;
+  const float* sa = fwd ? sig_src : sig_dst; const float* sb = fwd ? sig_dst : sig_src;
+  float* gA = fwd ? g_src : g_dst; float* gB = fwd ? g_dst : g_src;
+  float* gsa = fwd ? g_ss : g_sd; float* gsb = fwd ? g_sd : g_ss;
+  const int j = fwd ? i_sd[u] : i_ds[u];
+  const float d = fwd ? d_sd[u] : d_ds[u];
+  const float s = 0.5f * (sa[(size_t)bb * La + i] + sb[(size_t)bb * Lb + j]);
+  const float w = go / (float)(fwd ? nf : nb);
+  const float gd = w / s;                                   // d loss / d d
+  const float gs = w * (1.f / s - d / (s * s)) * 0.5f;      // d loss / d sigma (each of the two)
+  atomicAdd(&gsa[(size_t)bb * La + i], gs);
+  atomicAdd(&gsb[(size_t)bb * Lb + j], gs);
+  const float inv = d > 0.f ? gd / d : 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float diff = A[(size_t)bb * 3 * La + (size_t)c * La + i] - Bm[(size_t)bb * 3 * Lb + (size_t)c * Lb + j];
+    atomicAdd(&gA[(size_t)bb * 3 * La + (size_t)c * La + i], diff * inv);
+    atomicAdd(&gB[(size_t)bb * 3 * Lb + (size_t)c * Lb + j], -diff * inv);
+  }
+}
+
+// g_kp = scale * R^T g_out   (keypoint_detector.py:182-184)
+__global__ void transform_points_bwd_kernel(const float* __restrict__ g, const float* __restrict__ R,
+                                            const float* __restrict__ scale, float* __restrict__ gk, int B, int M) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * M) return;
+  int b = t / M, m = t - b * M;
+  const float* r = R + (size_t)b * 9;
+  const float s = scale[b];
+  const float gx = g[(size_t)b * 3 * M + m] * s, gy = g[(size_t)b * 3 * M + M + m] * s, gz = g[(size_t)b * 3 * M + 2 * M + m] * s;
+  for (int c = 0; c < 3; ++c) gk[(size_t)b * 3 * M + (size_t)c * M + m] = r[0 * 3 + c] * gx + r[1 * 3 + c] * gy + r[2 * 3 + c] * gz;
+}
+
+}  // namespace usip
+
+using namespace usip;
+
+extern "C" int usip_pairwise_min_f32(const float* a, const float* b, float* min_d, int32_t* arg,
+                                     unsigned long long* packed, int B, int Ma, int Nb, void* stream) {
+  USIP_REQUIRE(a && b && packed && B > 0 && Ma > 0 && Nb > 0, "pairwise_min: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)B * Ma;
+  pm_init_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(packed, n);
+  dim3 grid(cdiv(Nb, PM_TILE), cdiv(Ma, PM_THREADS), B);
+  pairwise_min_kernel<<<grid, PM_THREADS, 0, st>>>(a, b, packed, Ma, Nb);
+  pm_finish_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(packed, min_d, arg, n);
+  return check_launch("pairwise_min");
+}
+
+extern "C" int usip_chamfer_prob_reduce(const float* d_sd, const int32_t* i_sd, const float* d_ds,
+                                        const int32_t* i_ds, const float* sig_src, const float* sig_dst,
+                                        float* out3, int B, int M, int N, void* stream) {
+  USIP_REQUIRE(d_sd && i_sd && d_ds && i_ds && sig_src && sig_dst && out3, "chamfer_prob_reduce: bad args");
+  chamfer_prob_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst, out3,
+                                                                  B, M, N);
+  return check_launch("chamfer_prob_reduce_kernel");
+}
+
+extern "C" int usip_transform_points(const float* kp, const float* R, const float* scale, const float* shift,
+                                     float* out, int B, int M, void* stream) {
+  USIP_REQUIRE(kp && R && scale && shift && out, "transform_points: bad args");
+  transform_points_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(kp, R, scale, shift, out, B, M);
+  return check_launch("transform_points_kernel");
+}
+
+extern "C" int usip_mean_scale(const float* d, int64_t n, float alpha, float* out, void* stream) {
+  USIP_REQUIRE(d && out && n > 0, "mean_scale: bad args");
+  mean_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d, n, alpha, out);
+  return check_launch("mean_scale_kernel");
+}
+
+extern "C" int usip_pairwise_min_bwd(const float* a, const float* b, const float* min_d, const int32_t* arg,
+                                     const float* g, float gscale, float* grad_a, float* grad_b, int B, int Ma,
+                                     int Nb, void* stream) {
+  USIP_REQUIRE(a && b && min_d && arg, "pairwise_min_bwd: bad args");
+  pairwise_min_bwd_kernel<<<cdiv(B * Ma, 256), 256, 0, (cudaStream_t)stream>>>(a, b, min_d, arg, g, gscale, grad_a,
+                                                                             grad_b, B, Ma, Nb);
+  return check_launch("pairwise_min_bwd_kernel");
+}
+
+extern "C" int usip_chamfer_prob_bwd(const float* src, const float* dst, const float* sig_src, const float* sig_dst,
+                                     const float* d_sd, const int32_t* i_sd, const float* d_ds, const int32_t* i_ds,
+                                     const float* gout, float* g_src, float* g_dst, float* g_sig_src,
+                                     float* g_sig_dst, int B, int M, int N, void* stream) {
+  USIP_REQUIRE(src && dst && sig_src && sig_dst && gout && g_src && g_dst && g_sig_src && g_sig_dst,
+               "chamfer_prob_bwd: bad args");
+  chamfer_prob_bwd_kernel<<<cdiv(B * (M + N), 256), 256, 0, (cudaStream_t)stream>>>(
+      src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds, gout, g_src, g_dst, g_sig_src, g_sig_dst, B, M, N);
+  return check_launch("chamfer_prob_bwd_kernel");
+}
+
+extern "C" int usip_transform_points_bwd(const float* g_out, const float* R, const float* scale, float* g_kp,
+                                         int B, int M, void* stream) {
+  USIP_REQUIRE(g_out && R && scale && g_kp, "transform_points_bwd: bad args");
+  transform_points_bwd_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(g_out, R, scale, g_kp, B, M);
+  return check_launch("transform_points_bwd_kernel");
+}

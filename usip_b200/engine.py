@@ -1,0 +1,224 @@
+"""Fused B200 execution plan of the USIP detector / descriptor networks.
+
+This is NOT a layer-by-layer translation of models/networks.py: the (B,C,N) activations of the reference
+are replaced by point-major [rows, C] buffers over points SORTED BY NODE, so that
+  * index_max + gather + mask (networks.py:117-120,130-133) is a contiguous segmented max,
+  * the un-pool gather (networks.py:123-126) and the concat that follows become a per-node GEMM whose
+    result is added in the consuming layer's epilogue (W [a;b] = Wa a + Wb b),
+  * the kNN group tensor (B,3+C,M,K) of layers.py:422-429 is never built: W_feat @ feat is computed once
+    per node and gathered; the broadcast-max half of layers.py:435 likewise,
+  * train-mode BatchNorm (layers.py:69-71) is "epilogue emits statistics -> finalize -> next layer's
+    prologue normalises": every pre-BN activation is written once and read once,
+  * max_k relu(bn(y_k)) (layers.py:433,438) comes from per-group max/min of the raw GEMM output.
+All arithmetic happens in libusip_b200.so; torch only owns memory / streams / autograd plumbing.
+"""
+import torch
+
+from . import ops
+
+f32 = torch.float32
+i32 = torch.int32
+EPS = 1e-5
+
+
+def _w2d(w):
+    return w.detach().reshape(w.shape[0], -1)
+
+
+class BNState:
+    """Folded affine of one BatchNorm for the current step (+ what backward needs)."""
+    __slots__ = ("scale", "shift", "mean", "invstd", "count")
+
+
+def _precision_for(P, Cin, Cout, use_tc):
+    return 1 if (use_tc and Cin % 32 == 0 and Cout % 64 == 0 and P >= 1024) else 0
+
+
+class LayerRunner:
+    """Runs conv1x1(+BN) layers of one nn.Module tree through usip_layer_fwd / usip_bn_finalize."""
+
+    def __init__(self, net, training, use_tc, dev):
+        self.net = net
+        self.training = training
+        self.use_tc = use_tc
+        self.dev = dev
+        self.tile = ops.tile_rows()
+
+    def bn_state(self, norm, part, ntiles, count, momentum):
+        C = norm.weight.numel()
+        st = BNState()
+        st.scale = torch.empty(C, dtype=f32, device=self.dev)
+        st.shift = torch.empty(C, dtype=f32, device=self.dev)
+        st.count = count
+        if self.training:
+            st.mean = torch.empty(C, dtype=f32, device=self.dev)
+            st.invstd = torch.empty(C, dtype=f32, device=self.dev)
+            ops.bn_finalize(part, ntiles, count, C, norm.weight.detach(), norm.bias.detach(), EPS, momentum,
+                            norm.running_mean, norm.running_var, st.scale, st.shift, st.mean, st.invstd)
+        else:
+            st.mean = st.invstd = None
+            ops.bn_eval_affine(norm.weight.detach(), norm.bias.detach(), norm.running_mean, norm.running_var, EPS,
+                               st.scale, st.shift)
+        return st
+
+    def partials(self, P, Cout):
+        ntiles = (P + self.tile - 1) // self.tile
+        if not self.training:
+            return None, ntiles
+        return torch.empty((ntiles, 2, Cout), dtype=f32, device=self.dev), ntiles
+
+    def run(self, X, P, W, bias, norm=None, momentum=0.1, prev=None, relu_in=None, Y=None, write_y=True,
+            addend=None, add_index=None, add_group=0, group=0, want_group=False, want_arg=False, count=None):
+        """Y = act(X) W^T + bias (+addend); returns (Y, BNState or None, group dict or None)."""
+        Cout, Cin = W.shape
+        if Y is None and write_y:
+            Y = torch.empty((P, Cout), dtype=f32, device=self.dev)
+        part, ntiles = self.partials(P, Cout) if norm is not None else (None, 0)
+        grp = None
+        if want_group:
+            Q = P // group
+            grp = dict(gmax=torch.empty((Q, Cout), dtype=f32, device=self.dev),
+                       gmin=torch.empty((Q, Cout), dtype=f32, device=self.dev))
+            if want_arg:
+                grp["amax"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
+                grp["amin"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
+        ops.layer_fwd(X, W, bias, P, Cin, Cout,
+                      in_scale=None if prev is None else prev.scale, in_shift=None if prev is None else prev.shift,
+                      in_relu=(prev is not None) if relu_in is None else relu_in,
+                      addend=addend, add_index=add_index, add_group=add_group, Y=Y if write_y else None,
+                      stat_partial=part,
+                      gmax=None if grp is None else grp["gmax"], gmin=None if grp is None else grp["gmin"],
+                      garg_max=None if grp is None else grp.get("amax"),
+                      garg_min=None if grp is None else grp.get("amin"),
+                      group=group, precision=_precision_for(P, Cin, Cout, self.use_tc))
+        st = None
+        if norm is not None:
+            st = self.bn_state(norm, part, ntiles, P if count is None else count, momentum)
+        return Y, st, grp
+
+
+def _bn_mom(norm, epoch):
+    """layers.py:62-66 -- side effect on norm.momentum kept, like the reference."""
+    if (epoch is not None) and (epoch >= 1) and (norm.momentum_decay_step is not None) and (norm.momentum_decay_step > 0):
+        norm.momentum = norm.momentum_original * (norm.momentum_decay ** (epoch // norm.momentum_decay_step))
+        if norm.momentum < 0.01:
+            norm.momentum = 0.01
+    return norm.momentum
+
+
+def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
+    """RPN_Detector.forward (models/networks.py:75-162) on the fused plan.
+
+    x (B,3,N), sn (B,S,N), node (B,3,M) CUDA f32 contiguous.  Returns
+    (cluster_mean (B,3,M), keypoints (B,3,M), sigmas (B,M), ctx) -- ctx holds everything backward needs when
+    keep=True."""
+    opt = net.opt
+    assert opt.k == 1, "only k=1 is supported (every shipped config; networks.py:91-92)"
+    dev = x.device
+    Bp, _, N = x.shape
+    M = node.shape[2]
+    S = opt.surface_normal_len if opt.surface_normal_len >= 1 else 0
+    Kn = opt.node_knn_k_1
+    P, Q = Bp * N, Bp * M
+    G = Q * Kn
+    training = net.training
+    R = LayerRunner(net, training, use_tc, dev)
+    x = x.detach().contiguous(); node = node.detach().contiguous()
+    snc = sn.detach().contiguous() if S else None
+
+    # ---- grouping (som.query_topk + networks.py:87-108)
+    min_idx, count = ops.som_assign(x, node)
+    seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
+    cmean, X0 = ops.cluster_mean_decenter(x, snc, seg_off, perm, M, ldx=8)
+
+    # ---- first PointNet (3+S -> C1/2 -> C1/2 -> C1/2), networks.py:111-114
+    fp = net.first_pointnet.layers
+    H = fp[0].conv.weight.shape[0]
+    Y0, bn0, _ = R.run(X0, P, _w2d(fp[0].conv.weight), fp[0].conv.bias.detach(), fp[0].norm, _bn_mom(fp[0].norm, epoch))
+    Y1, bn1, _ = R.run(Y0, P, _w2d(fp[1].conv.weight), fp[1].conv.bias.detach(), fp[1].norm, _bn_mom(fp[1].norm, epoch), prev=bn0)
+    F1, _, _ = R.run(Y1, P, _w2d(fp[2].conv.weight), fp[2].conv.bias.detach(), prev=bn1)
+    # ---- pool 1 (index_max + gather * mask, networks.py:117-120)
+    pool1, arg1 = ops.segmax(F1, H, seg_off, perm, Bp, N, M, want_arg=keep)
+    # ---- second PointNet on cat(first, scattered max) (networks.py:123-127): W [f; s] = Wa f + Wb s
+    sp = net.second_pointnet.layers
+    C1 = sp[0].conv.weight.shape[0]
+    W3 = _w2d(sp[0].conv.weight)
+    V, _, _ = R.run(pool1, Q, W3[:, H:], None, relu_in=False)
+    Y3, bn3, _ = R.run(F1, P, W3[:, :H], sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
+                       relu_in=False, addend=V, add_index=row_seg)
+    F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3)
+    # ---- pool 2 -> first C1 columns of the head input (networks.py:130-133,143)
+    kb = net.knnlayer_1.layers_before
+    ka = net.knnlayer_1.layers_after
+    C2 = ka[-1].conv.weight.shape[0]
+    AGG = torch.empty((Q, C1 + C2), dtype=f32, device=dev)
+    pool2 = AGG[:, :C1]
+    _, arg2 = ops.segmax(F2, C1, seg_off, perm, Bp, N, M, out=pool2, want_arg=keep)
+
+    # ---- GeneralKNNFusionModule (layers.py:401-440)
+    knn_i = ops.knn_nodes(cmean, Kn)
+    W5 = _w2d(kb[0].conv.weight)
+    Cb = W5.shape[0]
+    Z, _, _ = R.run(pool2, Q, W5[:, 3:], None, relu_in=False)
+    Y5 = torch.empty((G, Cb), dtype=f32, device=dev)
+    part5, nt5 = R.partials(G, Cb)
+    ops.knn_combine(Z, cmean, knn_i, W5, W5.stride(0), kb[0].conv.bias.detach(), Y5, part5, Bp, M, Kn, Cb)
+    bn5 = R.bn_state(kb[0].norm, part5, nt5, G, _bn_mom(kb[0].norm, epoch))
+    prev, Yprev = bn5, Y5
+    saved_before = [(Y5, bn5)]
+    grp_b = None
+    for li in range(1, len(kb)):
+        last = li == len(kb) - 1
+        Yn, bnn, grp = R.run(Yprev, G, _w2d(kb[li].conv.weight), kb[li].conv.bias.detach(), kb[li].norm,
+                             _bn_mom(kb[li].norm, epoch), prev=prev, group=Kn, want_group=last, want_arg=last and keep)
+        prev, Yprev = bnn, Yn
+        saved_before.append((Yn, bnn))
+        grp_b = grp if last else grp_b
+    # max over K of the activated features (layers.py:433): from group max/min of the raw output
+    amax = torch.empty((Q, Cb), dtype=f32, device=dev)
+    ops.group_select(grp_b["gmax"], grp_b["gmin"], prev.scale, prev.shift, amax, Q, Cb)
+    W8 = _w2d(ka[0].conv.weight)
+    U, _, _ = R.run(amax, Q, W8[:, :Cb], None, relu_in=False)                                    # max half (layers.py:435)
+    Y8, bn8, _ = R.run(Yprev, G, W8[:, Cb:], ka[0].conv.bias.detach(), ka[0].norm, _bn_mom(ka[0].norm, epoch),
+                       prev=prev, addend=U, add_group=Kn)
+    saved_after = [(Y8, bn8)]
+    prevA, YA = bn8, Y8
+    grp_a = None
+    for li in range(1, len(ka)):
+        last = li == len(ka) - 1
+        Yn, bnn, grp = R.run(YA, G, _w2d(ka[li].conv.weight), ka[li].conv.bias.detach(), ka[li].norm,
+                             _bn_mom(ka[li].norm, epoch), prev=prevA, group=Kn, want_group=last, want_arg=last and keep,
+                             write_y=not last)
+        prevA, YA = bnn, Yn
+        saved_after.append((Yn, bnn))
+        grp_a = grp if last else grp_a
+    ops.group_select(grp_a["gmax"], grp_a["gmin"], prevA.scale, prevA.shift, AGG[:, C1:], Q, C2)   # layers.py:438
+
+    # ---- head (networks.py:143-154); mlp1/mlp2 are called WITHOUT epoch in the reference
+    Y10, bn10, _ = R.run(AGG, Q, _w2d(net.mlp1.conv.weight), net.mlp1.conv.bias.detach(), net.mlp1.norm,
+                         net.mlp1.norm.momentum, relu_in=False)
+    Y11, bn11, _ = R.run(Y10, Q, _w2d(net.mlp2.conv.weight), net.mlp2.conv.bias.detach(), net.mlp2.norm,
+                         net.mlp2.norm.momentum, prev=bn10)
+    OUT, _, _ = R.run(Y11, Q, _w2d(net.mlp3.conv.weight), net.mlp3.conv.bias.detach(), prev=bn11)
+    keypoints, sigmas = ops.head_finalize(OUT, cmean, opt.loss_sigma_lower_bound, Bp, M)
+
+    ctx = None
+    if keep:
+        ctx = dict(Bp=Bp, N=N, M=M, S=S, Kn=Kn, H=H, C1=C1, C2=C2, Cb=Cb,
+                   seg_off=seg_off, perm=perm, row_seg=row_seg, min_idx=min_idx, count=count, cmean=cmean,
+                   X0=X0, Y0=Y0, bn0=bn0, Y1=Y1, bn1=bn1, F1=F1, pool1=pool1, arg1=arg1, V=V,
+                   Y3=Y3, bn3=bn3, F2=F2, arg2=arg2, AGG=AGG, knn_i=knn_i, Z=Z,
+                   before=saved_before, grp_b=grp_b, amax=amax, U=U, after=saved_after, grp_a=grp_a,
+                   Y10=Y10, bn10=bn10, Y11=Y11, bn11=bn11, OUT=OUT, use_tc=use_tc)
+    aux = dict(min_idx=min_idx, count=count, perm=perm, seg_off=seg_off, knn_i=knn_i)
+    return cmean, keypoints, sigmas, ctx, aux
+
+
+# ----------------------------------------------------------------------------- losses (forward)
+def chamfer_prob_forward(src, dst, sig_src, sig_dst):
+    """ChamferLoss_Brute sigma branch (losses.py:79-97).  Returns (out3, saved)."""
+    src = src.contiguous(); dst = dst.contiguous()
+    d_sd, i_sd = ops.pairwise_min(src, dst)
+    d_ds, i_ds = ops.pairwise_min(dst, src)
+    out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src.contiguous(), sig_dst.contiguous())
+    return out3, (d_sd, i_sd, d_ds, i_ds)

@@ -1,0 +1,26 @@
+"""Drop-in for the reference's `index_max` extension module (models/index_max_ext/index_max.cpp:154-159).
+
+    forward_cuda_shared_mem(data, index, K) / forward_cuda(data, index, K) -> int32 (B,C,K)
+
+Both names run the same sm_100a kernel (usip_index_max_f32): the reference's two variants only differ in
+where the running max lives, and its shared-memory variant silently returns zeros once B*K > 12288
+(index_max_cuda.cu:92-96, no cudaFuncSetAttribute) -- that limit does not exist here.
+The CPU entry points are deliberately not provided: this build has no CPU path."""
+from . import ops as _ops
+
+
+def forward_cuda_shared_mem(data, index, K):
+    return _ops.index_max(data, index, K)
+
+
+def forward_cuda(data, index, K):
+    return _ops.index_max(data, index, K)
+
+
+def forward_cpu(data, index, K):
+    raise NotImplementedError("usip_b200.index_max is GPU-only (no CPU fallback); the CPU restatement of "
+                              "index_max.cpp:73-112 lives in oracle/ as test infrastructure")
+
+
+def forward_multi_thread_cpu(data, index, K, thread_num):
+    raise NotImplementedError("usip_b200.index_max is GPU-only (no CPU fallback)")

@@ -1,0 +1,222 @@
+"""`ModelDetector` -- same API surface as models/keypoint_detector.py:15-365 (constructor on `opt`,
+set_input / forward / forward_siamese / optimize / test_model / freeze_model / run_model /
+run_model_siamese / get_current_errors / save_network / update_learning_rate and the public attributes
+callers read), on top of the fused B200 plan.
+
+Multi-GPU: the reference wraps the detector in nn.DataParallel (keypoint_detector.py:35-37).  Here the unit is
+one process per GPU (torch.distributed, NCCL): every rank runs the same step on its own pairs, BatchNorm
+statistics stay per rank (the per-replica semantics DataParallel already has) and the only exchange is one
+all-reduce of a flat fp32 gradient buffer (`enable_data_parallel()`), launched by `optimize()`.
+"""
+import os
+import random
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import losses, networks
+
+
+class ModelDetector():
+    def __init__(self, opt):
+        self.opt = opt
+        if opt.scene == 'indoor':
+            self.detector = networks.RPN_DetectorLite(opt)      # keypoint_detector.py:19-22
+        else:
+            self.detector = networks.RPN_Detector(opt)
+        self.chamfer_criteria = losses.ChamferLoss_Brute(opt)
+        self.keypoint_on_pc_criteria = losses.KeypointOnPCLoss(opt)
+
+        if opt.gpu_ids[0] < 0:
+            raise RuntimeError("usip_b200.ModelDetector needs a CUDA device (opt.gpu_ids[0] >= 0): there is no CPU path")
+        self.detector = self.detector.to(self.opt.device)
+
+        self.old_lr_detector = self.opt.lr
+        self.optimizer_detector = torch.optim.Adam(self.detector.parameters(), lr=self.old_lr_detector,
+                                                   betas=(0.9, 0.999), weight_decay=0)
+        self._dp_group = None
+        self._flat_grad = None
+
+        dev = self.opt.device
+        B, N, M = self.opt.batch_size, self.opt.input_pc_num, self.opt.node_num
+        # place holders, same names as the reference (keypoint_detector.py:51-97)
+        self.src_pc = torch.empty(B, 3, N, device=dev).uniform_()
+        self.src_sn = torch.empty(B, 3, N, device=dev).uniform_()
+        self.src_label = torch.ones(B, dtype=torch.long, device=dev)
+        self.src_node = torch.empty(B, 3, M, device=dev)
+        self.dst_pc = torch.empty(B, 3, N, device=dev).uniform_()
+        self.dst_sn = torch.empty(B, 3, N, device=dev).uniform_()
+        self.dst_label = torch.ones(B, dtype=torch.long, device=dev)
+        self.dst_node = torch.empty(B, 3, M, device=dev)
+        self.src_R_dst = torch.zeros((B, 3, 3), dtype=torch.float32, device=dev)
+        self.src_scale_dst = torch.zeros((B, 1), dtype=torch.float32, device=dev)
+        self.src_shift_dst = torch.zeros((B, 3, 1), dtype=torch.float32, device=dev)
+        z = lambda: torch.tensor([0], dtype=torch.float32, requires_grad=False, device=dev)
+        self.test_chamfer_average = z(); self.test_loss_average = z(); self.test_keypoint_on_pc_average = z()
+        self.chamfer_pure = z(); self.test_chamfer_pure_average = z()
+        self.chamfer_weighted = z(); self.test_chamfer_weighted_average = z()
+
+    # ------------------------------------------------------------------ data parallel (one process / GPU)
+    def enable_data_parallel(self, process_group=None):
+        """Switch on the gradient all-reduce.  Call after torch.distributed.init_process_group."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        params = [p for p in self.detector.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        # parameters' .grad become views into one flat buffer: one collective, no packing copies
+        off = 0
+        for p in params:
+            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # identical initial weights on every rank
+        for t in list(self.detector.parameters()) + list(self.detector.buffers()):
+            dist.broadcast(t.data, src=0, group=self._dp_group)
+
+    def _allreduce_grads(self):
+        if self._dp_group is None:
+            return
+        import torch.distributed as dist
+        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self._dp_group)
+        self._flat_grad.mul_(1.0 / dist.get_world_size(self._dp_group))
+
+    # ------------------------------------------------------------------ reference API
+    def set_input(self, src_pc, src_sn, src_node, dst_pc, dst_sn, dst_node, src_R_dst, src_scale_dst, src_shift_dst):
+        dev = self.opt.device
+        nb = True
+        self.src_pc = src_pc.float().to(dev, non_blocking=nb).detach()
+        self.src_sn = src_sn.float().to(dev, non_blocking=nb).detach()
+        self.src_node = src_node.float().to(dev, non_blocking=nb).detach()
+        self.dst_pc = dst_pc.float().to(dev, non_blocking=nb).detach()
+        self.dst_sn = dst_sn.float().to(dev, non_blocking=nb).detach()
+        self.dst_node = dst_node.float().to(dev, non_blocking=nb).detach()
+        self.src_R_dst = src_R_dst.float().to(dev, non_blocking=nb).detach()
+        self.src_scale_dst = src_scale_dst.float().to(dev, non_blocking=nb).detach()
+        self.src_shift_dst = src_shift_dst.float().to(dev, non_blocking=nb).detach()
+        torch.cuda.synchronize()                                  # keypoint_detector.py:134
+
+    def forward(self, pc, sn, node, is_train=False, epoch=None):
+        with torch.cuda.device(pc.get_device()):
+            return self.detector(pc, sn, node, is_train, epoch)
+
+    def forward_siamese(self, pc_tuple, sn_tuple, node_tuple, is_train=False, epoch=None):
+        size_of_single_chunk = pc_tuple[0].size()[0]
+        node_recomputed, keypoints, sigmas, descriptors = self.detector(torch.cat(pc_tuple, dim=0),
+                                                                        torch.cat(sn_tuple, dim=0),
+                                                                        torch.cat(node_tuple, dim=0), is_train, epoch)
+        node_recomputed_tuple = torch.split(node_recomputed, split_size_or_sections=size_of_single_chunk, dim=0)
+        keypoints_tuple = torch.split(keypoints, split_size_or_sections=size_of_single_chunk, dim=0)
+        sigmas_tuple = torch.split(sigmas, split_size_or_sections=size_of_single_chunk, dim=0)
+        descriptors_tuple = (None, None)
+        return node_recomputed_tuple, keypoints_tuple, sigmas_tuple, descriptors_tuple
+
+    def _losses(self):
+        # keypoint_detector.py:182-204 (and :219-241)
+        self.src_keypoints_transformed = losses.transform_keypoints(self.src_keypoints, self.src_R_dst,
+                                                                    self.src_scale_dst, self.src_shift_dst)
+        self.loss_chamfer, self.chamfer_pure, self.chamfer_weighted = self.chamfer_criteria(
+            self.src_keypoints_transformed, self.dst_keypoints, self.src_sigmas, self.dst_sigmas)
+        if self.opt.keypoint_on_pc_type == 'point_to_point':
+            self.loss_keypoint_on_pc_src = losses.mean_scale(
+                self.keypoint_on_pc_criteria(self.src_keypoints, self.src_pc, None), self.opt.keypoint_on_pc_alpha)
+            self.loss_keypoint_on_pc_dst = losses.mean_scale(
+                self.keypoint_on_pc_criteria(self.dst_keypoints, self.dst_pc, None), self.opt.keypoint_on_pc_alpha)
+        else:
+            raise NotImplementedError("keypoint_on_pc_type=%r: only 'point_to_point' is on the B200 hot path"
+                                      % self.opt.keypoint_on_pc_type)
+        self.loss = self.loss_chamfer + self.loss_keypoint_on_pc_src + self.loss_keypoint_on_pc_dst
+
+    def _run_siamese(self, is_train, epoch):
+        (self.src_node_recomputed, self.dst_node_recomputed), \
+        (self.src_keypoints, self.dst_keypoints), \
+        (self.src_sigmas, self.dst_sigmas), \
+        (self.src_descriptors, self.dst_descriptors) = self.forward_siamese((self.src_pc, self.dst_pc),
+                                                                            (self.src_sn, self.dst_sn),
+                                                                            (self.src_node, self.dst_node),
+                                                                            is_train=is_train, epoch=epoch)
+
+    def optimize(self, epoch=None):
+        with torch.cuda.device(self.src_pc.get_device()):
+            if self.opt.random_pc_dropout_lower_limit < 0.99:      # keypoint_detector.py:161-169, same RNG streams
+                dropout_keep_ratio = random.uniform(self.opt.random_pc_dropout_lower_limit, 1.0)
+                resulting_pc_num = round(dropout_keep_ratio * self.opt.input_pc_num)
+                chosen_indices = np.random.choice(self.opt.input_pc_num, resulting_pc_num, replace=False)
+                chosen_indices_tensor = torch.from_numpy(chosen_indices).to(self.opt.device)
+                self.src_pc = torch.index_select(self.src_pc, dim=2, index=chosen_indices_tensor)
+                self.src_sn = torch.index_select(self.src_sn, dim=2, index=chosen_indices_tensor)
+                self.dst_pc = torch.index_select(self.dst_pc, dim=2, index=chosen_indices_tensor)
+                self.dst_sn = torch.index_select(self.dst_sn, dim=2, index=chosen_indices_tensor)
+            self.detector.train()
+            self._run_siamese(is_train=True, epoch=epoch)
+            if self._flat_grad is not None:
+                self._flat_grad.zero_()
+            else:
+                self.detector.zero_grad()
+            self._losses()
+            self.loss.backward()
+            self._allreduce_grads()
+            self.optimizer_detector.step()
+
+    def test_model(self):
+        self.detector.eval()
+        with torch.no_grad():
+            self._run_siamese(is_train=False, epoch=None)
+            self._losses()
+
+    def forward_loss(self, epoch=None, train_bn=True):
+        """fwd+loss only (the BASELINE metric): train-mode BatchNorm statistics, no backward."""
+        self.detector.train(train_bn)
+        with torch.no_grad():
+            self._run_siamese(is_train=train_bn, epoch=epoch)
+            self._losses()
+        return self.loss
+
+    def freeze_model(self):
+        for p in self.detector.parameters():
+            p.requires_grad = False
+
+    def run_model(self, pc, sn, node):
+        self.detector.eval()
+        with torch.no_grad():
+            _, keypoints, sigmas, _ = self.forward(pc, sn, node, is_train=False, epoch=None)
+        return keypoints, sigmas
+
+    def run_model_siamese(self, pc_tuple, sn_tuple, node_tuple):
+        self.detector.eval()
+        with torch.no_grad():
+            _, keypoints_tuple, sigmas_tuple, _ = self.forward_siamese(pc_tuple, sn_tuple, node_tuple,
+                                                                       is_train=False, epoch=None)
+        return keypoints_tuple, sigmas_tuple
+
+    def get_current_visuals(self):
+        raise NotImplementedError("visdom payloads (keypoint_detector.py:259-334) are outside the hot path")
+
+    def get_current_errors(self):
+        return OrderedDict([
+            ('O_loss', self.loss.item()),
+            ('O_chamfer', self.loss_chamfer.item()),
+            ('O_key_on_pc', self.loss_keypoint_on_pc_src.item() + self.loss_keypoint_on_pc_dst.item()),
+            ('E_loss', self.test_loss_average.item()),
+            ('E_chamfer', self.test_chamfer_average.item()),
+            ('E_key_on_pc', self.test_keypoint_on_pc_average.item()),
+            ('E_cham_pure', self.test_chamfer_pure_average.item()),
+            ('E_cham_weig', self.test_chamfer_weighted_average.item())
+        ])
+
+    def save_network(self, network, network_label, epoch_label, gpu_id):
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_path = os.path.join(self.opt.checkpoints_dir, save_filename)
+        torch.save(network.state_dict(), save_path)
+
+    def update_learning_rate(self, ratio):
+        lr_clip = 0.00001
+        lr_detector = self.old_lr_detector * ratio
+        if lr_detector < lr_clip:
+            lr_detector = lr_clip
+        for param_group in self.optimizer_detector.param_groups:
+            param_group['lr'] = lr_detector
+        print('update detector learning rate: %f -> %f' % (self.old_lr_detector, lr_detector))
+        self.old_lr_detector = lr_detector

@@ -1,0 +1,148 @@
+"""Host-side mirror of the hot-path losses of models/losses.py (same class names / signatures / returns):
+
+  ChamferLoss_Brute            losses.py:44-99    probabilistic chamfer (sigma branch) + plain branch
+  KeypointOnPCLoss             losses.py:102-116  (point_to_point -> SingleSideChamferLoss_Brute)
+  SingleSideChamferLoss_Brute  losses.py:119-143
+
+The (B,3,M,N) / (B,M,N) temporaries of the reference are never built: one tiled pairwise-L2 arg-min kernel
+(usip_pairwise_min_f32) serves all three, the reductions and the backward passes are small fused kernels.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..ops import _p, _stream
+
+
+class _PairMinFn(torch.autograd.Function):
+    """min_j ||a_i - b_j|| (B,Ma); differentiable w.r.t. both point sets (sub-gradient 0 at d == 0)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a.contiguous(); b = b.contiguous()
+        d, arg = ops.pairwise_min(a, b)
+        ctx.save_for_backward(a, b, d, arg)
+        return d
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, d, arg = ctx.saved_tensors
+        B, _, Ma = a.shape
+        Nb = b.shape[2]
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.zeros_like(b) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.load().usip_pairwise_min_bwd(_p(a), _p(b), _p(d), _p(arg), _p(g.contiguous()), 1.0, _p(ga),
+                                                     _p(gb), B, Ma, Nb, _stream()), "usip_pairwise_min_bwd")
+        return ga, gb
+
+
+class _ChamferProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, dst, sig_src, sig_dst):
+        src = src.contiguous(); dst = dst.contiguous()
+        sig_src = sig_src.contiguous(); sig_dst = sig_dst.contiguous()
+        d_sd, i_sd = ops.pairwise_min(src, dst)
+        d_ds, i_ds = ops.pairwise_min(dst, src)
+        out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst)
+        ctx.save_for_backward(src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds)
+        loss, pure, weighted = out3[0], out3[1], out3[2]
+        ctx.mark_non_differentiable(pure, weighted)
+        return loss, pure, weighted
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pure, g_weighted):
+        src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds = ctx.saved_tensors
+        B, _, M = src.shape
+        N = dst.shape[2]
+        g_src = torch.zeros_like(src); g_dst = torch.zeros_like(dst)
+        g_ss = torch.zeros_like(sig_src); g_sd = torch.zeros_like(sig_dst)
+        gout = g_loss.reshape(1).to(torch.float32).contiguous()
+        _lib.check(_lib.load().usip_chamfer_prob_bwd(_p(src), _p(dst), _p(sig_src), _p(sig_dst), _p(d_sd), _p(i_sd),
+                                                     _p(d_ds), _p(i_ds), _p(gout), _p(g_src), _p(g_dst), _p(g_ss),
+                                                     _p(g_sd), B, M, N, _stream()), "usip_chamfer_prob_bwd")
+        return g_src, g_dst, g_ss, g_sd
+
+
+class _TransformFn(torch.autograd.Function):
+    """R @ kp * scale + shift (keypoint_detector.py:182-184); gradient only w.r.t. kp."""
+
+    @staticmethod
+    def forward(ctx, kp, R, scale, shift):
+        kp = kp.contiguous(); R = R.contiguous()
+        scale = scale.reshape(-1).contiguous(); shift = shift.reshape(shift.shape[0], 3).contiguous()
+        ctx.save_for_backward(R, scale)
+        return ops.transform_points(kp, R, scale, shift)
+
+    @staticmethod
+    def backward(ctx, g):
+        R, scale = ctx.saved_tensors
+        g = g.contiguous()
+        B, _, M = g.shape
+        gk = torch.empty_like(g)
+        _lib.check(_lib.load().usip_transform_points_bwd(_p(g), _p(R), _p(scale), _p(gk), B, M, _stream()),
+                   "usip_transform_points_bwd")
+        return gk, None, None, None
+
+
+class _MeanScaleFn(torch.autograd.Function):
+    """mean(d) * alpha (keypoint_detector.py:193-197)."""
+
+    @staticmethod
+    def forward(ctx, d, alpha):
+        ctx.alpha = alpha; ctx.n = d.numel(); ctx.shape = d.shape
+        return ops.mean_scale(d.contiguous(), alpha)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g * (ctx.alpha / ctx.n)).expand(ctx.shape), None
+
+
+def transform_keypoints(kp, R, scale, shift):
+    return _TransformFn.apply(kp, R, scale, shift)
+
+
+def mean_scale(d, alpha):
+    return _MeanScaleFn.apply(d, float(alpha))
+
+
+class ChamferLoss_Brute(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.dimension = 3
+
+    def forward(self, pc_src_input, pc_dst_input, sigma_src=None, sigma_dst=None):
+        """pc_src (B,3,M), pc_dst (B,3,N), sigma (B,M)/(B,N) -> (loss, chamfer_pure, chamfer_weighted);
+        without sigmas: un-reduced (B,M) tensors (losses.py:68-78)."""
+        if sigma_src is None or sigma_dst is None:
+            forward_loss = _PairMinFn.apply(pc_src_input, pc_dst_input)
+            backward_loss = _PairMinFn.apply(pc_dst_input, pc_src_input)
+            chamfer_pure = forward_loss + backward_loss
+            return forward_loss + backward_loss, chamfer_pure, chamfer_pure
+        return _ChamferProbFn.apply(pc_src_input, pc_dst_input, sigma_src, sigma_dst)
+
+
+class SingleSideChamferLoss_Brute(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.dimension = 3
+
+    def forward(self, pc_src_input, pc_dst_input):
+        """(B,3,M), (B,3,N) -> (B,M) min distances (losses.py:125-143)."""
+        return _PairMinFn.apply(pc_src_input, pc_dst_input)
+
+
+class KeypointOnPCLoss(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.single_side_chamfer = SingleSideChamferLoss_Brute(opt)
+
+    def forward(self, keypoint, pc, sn=None):
+        if sn is not None:
+            raise NotImplementedError("point_to_plane (PointOnSurfaceLoss, losses.py:146-183) is a non-default "
+                                      "option outside the B200 hot path; use keypoint_on_pc_type='point_to_point'")
+        return self.single_side_chamfer(keypoint, pc)
