@@ -104,11 +104,16 @@ typedef struct usip_layer_desc {
   int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
   int32_t group;
   int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0)   */
+  void* tc_workspace;                  /* precision 1: >= usip_layer_tc_workspace_bytes(Cin,Cout) bytes */
+  int64_t tc_workspace_bytes;
+  int32_t tc_weights_packed;           /* 1: tc_workspace already holds the packed weights of this W  */
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);
 /* rows per stat tile (ntiles = ceil(P / usip_layer_tile_rows())) */
 int usip_layer_tile_rows(void);
+/* bytes of tc_workspace (hi/lo TF32 split of W, pre-swizzled into tcgen05 operand tiles) */
+int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout);
 
 /* Training-mode BatchNorm finalisation (F.batch_norm, layers.py:69-71): reduce the per-tile partials,
  * produce the folded affine scale = gamma/sqrt(var+eps), shift = beta - mean*scale, update running stats

@@ -1,0 +1,89 @@
+"""-m gpu parity of the fused detector plan (ModelDetector API) against the reference goldens (small shapes,
+outputs of the real reference) and against the numpy oracle at larger shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import usip_oracle as orc
+from tests.util_gpu import cu, dev, golden, load_params, make_opt, rel_err
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def _setup(fname, use_tc):
+    from usip_b200.models.keypoint_detector import ModelDetector
+    g = golden(fname)
+    B, N, M, S, Kn, seed = [int(v) for v in g["cfg"]]
+    kind, scene = str(g["kind"]), str(g["scene"])
+    d = orc.synth_pair(B, N, M, S, kind=kind, seed=seed)
+    C1, C2 = (64, 256) if scene == "indoor" else (128, 512)
+    P = orc.init_detector_params(S=S, seed=seed, C1=C1, C2=C2, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn, scene=scene,
+                   loss_sigma_lower_bound=float(g["lb"]), keypoint_on_pc_alpha=float(g["alpha"]), use_tensor_cores=use_tc)
+    md = ModelDetector(opt)
+    load_params(md.detector, P)
+    md.set_input(*[torch.from_numpy(d[k]) for k in ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node",
+                                                    "R", "scale", "shift")])
+    return g, d, P, md
+
+
+def _loss_vec(md):
+    return np.array([md.loss.item(), md.loss_chamfer.item(), md.chamfer_pure.item(), md.chamfer_weighted.item(),
+                     md.loss_keypoint_on_pc_src.item(), md.loss_keypoint_on_pc_dst.item()], np.float32)
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("fname", ["detector_kitti_small.npz", "detector_modelnet_small.npz", "detector_lite_small.npz"])
+def test_detector_eval_and_train_forward_vs_reference_golden(fname, use_tc):
+    g, d, P, md = _setup(fname, use_tc)
+    md.test_model()                                                       # eval-mode BN (running stats)
+    kp = torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy()
+    sig = torch.cat([md.src_sigmas, md.dst_sigmas]).cpu().numpy()
+    node = torch.cat([md.src_node_recomputed, md.dst_node_recomputed]).cpu().numpy()
+    assert rel_err(node, g["eval_node"]) < 1e-5
+    assert rel_err(kp, g["eval_kp"]) < REL, rel_err(kp, g["eval_kp"])
+    assert rel_err(sig, g["eval_sig"]) < REL, rel_err(sig, g["eval_sig"])
+    lv = _loss_vec(md)
+    assert np.all(np.abs(lv - g["eval_loss"]) <= REL * np.abs(g["eval_loss"]) + 1e-6), (lv, g["eval_loss"])
+
+    md.forward_loss(epoch=0, train_bn=True)                               # train-mode BN forward + loss
+    kp = torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy()
+    sig = torch.cat([md.src_sigmas, md.dst_sigmas]).cpu().numpy()
+    assert rel_err(kp, g["train_kp"]) < REL, rel_err(kp, g["train_kp"])
+    assert rel_err(sig, g["train_sig"]) < REL, rel_err(sig, g["train_sig"])
+    lv = _loss_vec(md)
+    assert np.all(np.abs(lv - g["train_loss"]) <= REL * np.abs(g["train_loss"]) + 1e-6), (lv, g["train_loss"])
+    # running statistics were updated exactly once (momentum 0.1, unbiased variance)
+    sd = md.detector.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            flat = sd[k].cpu().numpy().reshape(-1)
+            ref = g["after/" + k]
+            assert np.allclose(flat[:24], ref[3:3 + min(24, flat.size)], rtol=2e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_detector_vs_oracle_medium(use_tc):
+    """B'=4 clouds, N=8192, M=256, Kn=16: fused CUDA plan vs the numpy oracle (fp32), train-mode BN."""
+    from usip_b200.models.keypoint_detector import ModelDetector
+    B, N, M, S, Kn = 2, 8192, 256, 4, 16
+    d = orc.synth_pair(B, N, M, S, kind="lidar", seed=77)
+    P = orc.init_detector_params(S=S, seed=5, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn, use_tensor_cores=use_tc)
+    md = ModelDetector(opt)
+    load_params(md.detector, P)
+    md.set_input(*[torch.from_numpy(d[k]) for k in ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node",
+                                                    "R", "scale", "shift")])
+    md.forward_loss(train_bn=True)
+    r = orc.detector_fwd_loss(P, d["src_pc"], d["src_sn"], d["src_node"], d["dst_pc"], d["dst_sn"], d["dst_node"],
+                              d["R"], d["scale"], d["shift"], node_knn_k=Kn, sigma_lower_bound=opt.loss_sigma_lower_bound,
+                              alpha=opt.keypoint_on_pc_alpha, training=True)
+    kp = torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy()
+    sig = torch.cat([md.src_sigmas, md.dst_sigmas]).cpu().numpy()
+    assert rel_err(kp, np.concatenate([r["src_keypoints"], r["dst_keypoints"]])) < REL
+    assert rel_err(sig, np.concatenate([r["src_sigmas"], r["dst_sigmas"]])) < REL
+    assert abs(md.loss.item() - r["loss"]) <= REL * abs(r["loss"])
+    assert abs(md.loss_chamfer.item() - r["loss_chamfer"]) <= REL * abs(r["loss_chamfer"])

@@ -1,0 +1,298 @@
+"""-m gpu parity tests of the individual C-ABI kernels against oracle/ (bit-exact for index / integer work,
+1e-4 relative for fp) and, where it travelled, against the reference's own CUDA extensions (oracle/_ref)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import usip_oracle as orc
+from tests.util_gpu import cu, dev, golden, ref_ext, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+# ------------------------------------------------------------------------------------------ index_max
+def test_index_max_golden_cases():
+    from usip_b200 import index_max
+    g = golden("index_max.npz")
+    for c in "abcd":
+        out = index_max.forward_cuda_shared_mem(cu(g["data_" + c]), cu(g["index_" + c]), int(g["K_" + c]))
+        assert out.dtype == torch.int32
+        assert np.array_equal(out.cpu().numpy(), g["out_" + c]), c
+        out2 = index_max.forward_cuda(cu(g["data_" + c]), cu(g["index_" + c]), int(g["K_" + c]))
+        assert np.array_equal(out2.cpu().numpy(), g["out_" + c]), c
+
+
+@pytest.mark.parametrize("B,C,N,K", [(3, 64, 5000, 512), (2, 128, 16384, 512), (1, 5, 1001, 7), (2, 16, 4096, 3000),
+                                     (1, 2, 2048, 20000)])
+def test_index_max_vs_oracle(B, C, N, K):
+    from usip_b200 import index_max
+    rng = np.random.default_rng(B * 1000 + C)
+    data = rng.normal(size=(B, C, N)).astype(np.float32)
+    data[:, 0] = np.maximum(data[:, 0], 0)            # post-ReLU like: many exact zeros / ties
+    data[0, -1, ::5] = -0.0
+    index = rng.integers(0, K, size=(B, N)).astype(np.int32)
+    out = index_max.forward_cuda_shared_mem(cu(data), cu(index), K).cpu().numpy()
+    assert np.array_equal(out, orc.index_max(data, index, K))
+
+
+def test_index_max_vs_reference_cuda_full_size():
+    """KITTI shape (B'=16, C=128, N=16384, K=512) against the reference's own kernel (global-mem variant, no cap)."""
+    from usip_b200 import index_max
+    ref = ref_ext("index_max")
+    if ref is None:
+        pytest.skip("oracle/_ref/index_max not built")
+    torch.manual_seed(0)
+    data = torch.randn(16, 128, 16384, device=dev())
+    index = torch.randint(0, 512, (16, 16384), device=dev(), dtype=torch.int32)
+    ours = index_max.forward_cuda_shared_mem(data, index, 512)
+    theirs = ref.forward_cuda(data, index, 512)
+    torch.cuda.synchronize()
+    assert torch.equal(ours, theirs)
+
+
+def test_index_max_errors():
+    from usip_b200 import index_max
+    d = torch.randn(1, 2, 8); i = torch.zeros(1, 8, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        index_max.forward_cuda_shared_mem(d, i, 2)                      # CPU tensor
+    with pytest.raises(RuntimeError):
+        index_max.forward_cuda_shared_mem(d.to(dev()).transpose(1, 2), i.to(dev()), 2)   # non-contiguous
+    with pytest.raises(NotImplementedError):
+        index_max.forward_cpu(d, i, 2)
+
+
+# ------------------------------------------------------------------------------------------ ball query
+@pytest.mark.parametrize("B,M,N,K,r", [(2, 33, 1000, 16, 0.9), (1, 8, 257, 64, 2.5), (2, 16, 4096, 64, 0.2)])
+def test_ball_query_dist_vs_oracle(B, M, N, K, r):
+    from usip_b200 import ball_query
+    rng = np.random.default_rng(5)
+    dist = np.abs(rng.normal(size=(B, M, N))).astype(np.float32)
+    dist[0, 0] = 100.0                 # zero hits
+    dist[0, 1, :3] = 0.0               # very few hits
+    dist[0, 2] = 0.0                   # everything hits
+    out = ball_query.forward_cuda_shared_mem(cu(dist), r, K).cpu().numpy()
+    assert np.array_equal(out, orc.ball_query_dist(dist, r, K))
+
+
+def test_ball_query_vs_reference_cuda():
+    from usip_b200 import ball_query
+    ref = ref_ext("ball_query")
+    if ref is None:
+        pytest.skip("oracle/_ref/ball_query not built")
+    torch.manual_seed(1)
+    pc = torch.rand(8, 3, 4096, device=dev()) * 8
+    kp = pc[:, :, :256] + 0.05 * torch.randn(8, 3, 256, device=dev())
+    dist = torch.norm(kp.unsqueeze(3) - pc.unsqueeze(2), dim=1).contiguous()
+    ours = ball_query.forward_cuda_shared_mem(dist, 1.0, 64)
+    theirs = ref.forward_cuda_shared_mem(dist, 1.0, 64)
+    torch.cuda.synchronize()
+    assert torch.equal(ours, theirs)
+    fused, _ = ball_query.forward_fused(pc.contiguous(), None, kp.contiguous(), 1.0, 64, want_group=False)
+    assert torch.equal(fused, theirs)
+
+
+@pytest.mark.parametrize("S", [0, 4])
+def test_ball_group_fused_vs_oracle(S):
+    from usip_b200 import ball_query
+    rng = np.random.default_rng(9)
+    B, N, M, K = 2, 3000, 40, 32
+    pc = (rng.uniform(-4, 4, (B, 3, N))).astype(np.float32)
+    sn = rng.normal(size=(B, S, N)).astype(np.float32)
+    kp = pc[:, :, :M] + rng.normal(0, 0.1, (B, 3, M)).astype(np.float32)
+    kp[:, :, 0] = 99.0
+    idx, grp = ball_query.forward_fused(cu(pc), cu(sn) if S else None, cu(kp), 1.0, K)
+    ref_idx = orc.ball_query_xyz(pc, kp, 1.0, K)
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    x_aug = np.concatenate([pc, sn], 1) if S else pc
+    gi = np.broadcast_to(ref_idx.astype(np.int64).reshape(B, 1, M * K), (B, 3 + S, M * K))
+    ball = np.take_along_axis(x_aug, gi, axis=2).reshape(B, 3 + S, M, K).copy()
+    ball[:, :3] -= kp[:, :, :, None]
+    assert np.array_equal(grp.cpu().numpy(), ball)
+
+
+# ------------------------------------------------------------------------------------------ grouping
+def test_som_assign_sort_mean_segmax():
+    from usip_b200 import ops
+    B, N, M, S = 3, 5000, 96, 4
+    d = orc.synth_pair(B, N, M, S, kind="lidar", seed=3)
+    x, sn, node = d["src_pc"], d["src_sn"], d["src_node"].copy()
+    node[:, :, 7] = 1000.0             # empty cluster
+    min_idx, count = ops.som_assign(cu(x), cu(node))
+    ref_idx = orc.som_assign(x, node)
+    assert np.array_equal(min_idx.cpu().numpy(), ref_idx)
+    cnt = np.stack([np.bincount(ref_idx[b], minlength=M) for b in range(B)])
+    assert np.array_equal(count.cpu().numpy(), cnt)
+    seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
+    so, pm, rs = seg_off.cpu().numpy(), perm.cpu().numpy(), row_seg.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(so[b], np.concatenate([[0], np.cumsum(cnt[b])]))
+        assert np.array_equal(pm[b], np.argsort(ref_idx[b], kind="stable"))          # stable: ascending n per node
+        assert np.array_equal(rs[b], b * M + ref_idx[b][pm[b]])
+    cmean, x_aug = ops.cluster_mean_decenter(cu(x), cu(sn), seg_off, perm, M, ldx=8)
+    cm = cmean.cpu().numpy(); xa = x_aug.cpu().numpy().reshape(B, N, 8)
+    for b in range(B):
+        for m in range(M):
+            pts = x[b][:, ref_idx[b] == m]
+            ref_mean = pts.sum(1) / (pts.shape[1] + 1e-5) if pts.shape[1] else np.zeros(3)
+            assert np.allclose(cm[b, :, m], ref_mean, rtol=1e-5, atol=1e-5)
+        exp = np.concatenate([x[b][:, pm[b]] - cm[b][:, ref_idx[b][pm[b]]], sn[b][:, pm[b]]], 0).T
+        assert np.allclose(xa[b, :, :7], exp, rtol=0, atol=1e-6)
+        assert np.all(xa[b, :, 7] == 0)
+    # segmented max of a random feature map over the sorted rows
+    C = 64
+    F = torch.randn(B * N, C, device=dev())
+    pooled, arg = ops.segmax(F, C, seg_off, perm, B, N, M)
+    Fh = F.cpu().numpy().reshape(B, N, C)
+    pl, ag = pooled.cpu().numpy().reshape(B, M, C), arg.cpu().numpy().reshape(B, M, C)
+    for b in range(B):
+        # express in the reference's (B,C,N) layout / original point order and use the index_max oracle
+        orig = np.zeros((C, N), np.float32); orig[:, pm[b]] = Fh[b].T
+        idx = orc.index_max(orig[None], ref_idx[b][None], M)[0]                       # (C,M) original n
+        exp = np.take_along_axis(orig, idx.astype(np.int64), 1).T * (cnt[b] > 0)[:, None]
+        assert np.array_equal(pl[b], exp)
+        got_n = pm[b][np.clip(ag[b] - b * N, 0, N - 1)]
+        assert np.array_equal(np.where(cnt[b][:, None] > 0, got_n, 0), np.where(cnt[b][:, None] > 0, idx.T, 0))
+
+
+def test_knn_nodes_vs_oracle():
+    from usip_b200 import ops
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-10, 10, (4, 3, 200)).astype(np.float32)
+    pts[0, :, 50] = pts[0, :, 20]          # duplicate point -> exact ties
+    for K in (16, 32):
+        out = ops.knn_nodes(cu(pts), K).cpu().numpy()
+        ref, _ = orc.knn(pts, pts, K)
+        assert np.array_equal(out, ref)
+
+
+def test_query_topk_api():
+    from usip_b200.util import som
+    g = golden("query_topk.npz")
+    d = orc.synth_pair(2, 2048, 64, 4, kind="lidar", seed=int(g["seed_lidar"]))
+    mask, row_max, min_idx = som.query_topk(cu(g["node_lidar"]), cu(d["src_pc"]), 64, 1)
+    assert np.array_equal(min_idx.cpu().numpy().astype(np.int32), g["min_idx_lidar"])
+    assert np.array_equal(row_max.cpu().numpy(), g["row_max_lidar"])
+    assert mask.shape == (2, 2048, 64) and int(mask.sum()) == 2 * 2048
+
+
+# ------------------------------------------------------------------------------------------ shared-MLP layer
+def _layer_ref(X, W, b, scale, shift, relu, addend, add_idx):
+    A = X.astype(np.float64)
+    if scale is not None:
+        A = A * scale + shift
+    if relu:
+        A = np.maximum(A, 0)
+    Y = A @ W.astype(np.float64).T
+    if b is not None:
+        Y = Y + b
+    if addend is not None:
+        Y = Y + addend[add_idx]
+    return Y
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("P,Cin,Cout,group", [(1000, 7, 64, 0), (4096, 64, 64, 16), (2048, 128, 128, 32),
+                                              (1536, 256, 256, 16), (1024, 512, 512, 64), (700, 640, 512, 0),
+                                              (512, 256, 4, 0), (640, 131, 256, 0)])
+def test_layer_fwd(P, Cin, Cout, group, precision):
+    from usip_b200 import ops
+    if precision == 1 and not (Cin % 32 == 0 and Cout % 64 == 0):
+        pytest.skip("tensor-core path needs Cin%32==0 and Cout%64==0")
+    rng = np.random.default_rng(P + Cin)
+    ldx = Cin + (8 - Cin % 8) % 8
+    X = rng.normal(size=(P, ldx)).astype(np.float32)
+    W = (rng.normal(size=(Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    b = rng.normal(size=Cout).astype(np.float32)
+    scale = rng.normal(size=Cin).astype(np.float32); shift = rng.normal(size=Cin).astype(np.float32)
+    G = 37
+    addend = rng.normal(size=(G, Cout)).astype(np.float32)
+    add_idx = rng.integers(0, G, size=P).astype(np.int32)
+    Xd = cu(X)
+    Y = torch.empty((P, Cout), device=dev())
+    tile = ops.tile_rows(); nt = (P + tile - 1) // tile
+    part = torch.zeros((nt, 2, Cout), device=dev())
+    kw = {}
+    if group and P % group == 0:
+        Q = P // group
+        kw = dict(gmax=torch.empty((Q, Cout), device=dev()), gmin=torch.empty((Q, Cout), device=dev()),
+                  garg_max=torch.empty((Q, Cout), dtype=torch.int32, device=dev()),
+                  garg_min=torch.empty((Q, Cout), dtype=torch.int32, device=dev()), group=group)
+    ops.layer_fwd(Xd, cu(W), cu(b), P, Cin, Cout, ldx=ldx, in_scale=cu(scale), in_shift=cu(shift), in_relu=True,
+                  addend=cu(addend), add_index=cu(add_idx), Y=Y, stat_partial=part, precision=precision, **kw)
+    torch.cuda.synchronize()
+    ref = _layer_ref(X[:, :Cin], W, b, scale, shift, True, addend, add_idx)
+    e = rel_err(Y.cpu().numpy(), ref)
+    assert e < 2e-5, e
+    st = part.cpu().numpy().astype(np.float64).sum(0)
+    assert rel_err(st[0], ref.sum(0)) < 1e-4 and rel_err(st[1], (ref ** 2).sum(0)) < 1e-4
+    if kw:
+        Yh = Y.cpu().numpy().reshape(P // group, group, Cout)
+        assert np.array_equal(kw["gmax"].cpu().numpy(), Yh.max(1)) and np.array_equal(kw["gmin"].cpu().numpy(), Yh.min(1))
+        assert np.array_equal(kw["garg_max"].cpu().numpy(), Yh.argmax(1)) and np.array_equal(kw["garg_min"].cpu().numpy(), Yh.argmin(1))
+    # plain variant: no prologue / addend / stats, strided output
+    Ybig = torch.zeros((P, Cout + 16), device=dev())
+    ops.layer_fwd(Xd, cu(W), None, P, Cin, Cout, ldx=ldx, Y=Ybig[:, 8:8 + Cout], precision=precision)
+    assert rel_err(Ybig[:, 8:8 + Cout].cpu().numpy(), _layer_ref(X[:, :Cin], W, None, None, None, False, None, None)) < 2e-5
+    assert float(Ybig[:, :8].abs().max()) == 0 and float(Ybig[:, 8 + Cout:].abs().max()) == 0
+
+
+def test_bn_finalize_matches_batch_norm():
+    from usip_b200 import ops
+    P, C = 3000, 96
+    torch.manual_seed(0)
+    Y = torch.randn(P, C, device=dev()) * 3 + 1.5
+    W = torch.eye(C, device=dev())
+    tile = ops.tile_rows(); nt = (P + tile - 1) // tile
+    part = torch.zeros((nt, 2, C), device=dev())
+    out = torch.empty_like(Y)
+    ops.layer_fwd(Y, W, None, P, C, C, Y=out, stat_partial=part)
+    gamma = torch.rand(C, device=dev()) + 0.5; beta = torch.randn(C, device=dev())
+    rm = torch.randn(C, device=dev()); rv = torch.rand(C, device=dev()) + 0.5
+    rm2, rv2 = rm.clone(), rv.clone()
+    scale = torch.empty(C, device=dev()); shift = torch.empty(C, device=dev())
+    ops.bn_finalize(part, nt, P, C, gamma, beta, 1e-5, 0.1, rm2, rv2, scale, shift)
+    ref = torch.nn.functional.batch_norm(Y, rm, rv, gamma, beta, True, 0.1, 1e-5)
+    assert rel_err((Y * scale + shift).cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    assert rel_err(rm2.cpu().numpy(), rm.cpu().numpy()) < 1e-5 and rel_err(rv2.cpu().numpy(), rv.cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ losses
+def test_losses_vs_golden_and_grads():
+    from usip_b200.models import losses
+    from tests.util_gpu import make_opt
+    g = golden("losses.npz")
+    opt = make_opt()
+    crit = losses.ChamferLoss_Brute(opt)
+    src = cu(g["src"]).requires_grad_(True); dst = cu(g["dst"]).requires_grad_(True)
+    ss = cu(g["sig_src"]).requires_grad_(True); sd = cu(g["sig_dst"]).requires_grad_(True)
+    loss, pure, weighted = crit(src, dst, ss, sd)
+    assert rel_err(loss.item(), g["loss"]) < 1e-5 and rel_err(pure.item(), g["pure"]) < 1e-5
+    assert rel_err(weighted.item(), g["weighted"]) < 1e-5
+    loss.backward()
+    for got, name in ((src.grad, "g_src"), (dst.grad, "g_dst"), (ss.grad, "g_sig_src"), (sd.grad, "g_sig_dst")):
+        assert rel_err(got.cpu().numpy(), g[name]) < 1e-4, name
+    kp = cu(g["kp"]).requires_grad_(True)
+    d = losses.SingleSideChamferLoss_Brute(opt)(kp, cu(g["pc"]))
+    assert np.array_equal(d.detach().cpu().numpy(), g["single"])          # sqrt of the same fp32 sum: bit exact
+    d.mean().backward()
+    assert rel_err(kp.grad.cpu().numpy(), g["g_kp"]) < 1e-5
+    l2, _, _ = crit(cu(g["src"]), cu(g["dst"]))
+    assert rel_err(l2.cpu().numpy(), g["nosigma"]) < 1e-6
+
+
+def test_pairwise_min_full_size_properties():
+    """KITTI size (16 x 512 keypoints vs 16384 points): bit-exact vs the oracle on a slice + sortedness property."""
+    from usip_b200 import ops
+    rng = np.random.default_rng(0)
+    pc = rng.uniform(-40, 40, (16, 3, 16384)).astype(np.float32)
+    kp = pc[:, :, :512] + rng.normal(0, 0.3, (16, 3, 512)).astype(np.float32)
+    d, arg = ops.pairwise_min(cu(kp), cu(pc))
+    dh, ah = d.cpu().numpy(), arg.cpu().numpy()
+    rd, ra = orc.pairwise_min(kp[:2], pc[:2])
+    assert np.array_equal(dh[:2], rd) and np.array_equal(ah[:2], ra)
+    # property: the reported neighbour really is at the reported distance, and no sampled point is closer
+    sel = np.take_along_axis(pc, np.broadcast_to(ah[:, None, :].astype(np.int64), (16, 3, 512)), 2)
+    assert np.allclose(np.sqrt(((kp - sel) ** 2).sum(1)), dh, rtol=1e-6)
+    samp = pc[:, :, ::64]
+    dd = np.sqrt(((kp[:, :, :, None] - samp[:, :, None, :]) ** 2).sum(1)).min(2)
+    assert np.all(dh <= dd * (1 + 1e-6))

@@ -30,6 +30,9 @@ class LayerDesc(ctypes.Structure):
         ("garg_max", c_ptr), ("garg_min", c_ptr),
         ("group", ctypes.c_int32),
         ("precision", ctypes.c_int32),
+        ("tc_workspace", c_ptr),
+        ("tc_workspace_bytes", ctypes.c_int64),
+        ("tc_weights_packed", ctypes.c_int32),
     ]
 
 
@@ -50,6 +53,7 @@ SIGNATURES = {
                                            c_int, c_int, c_int, c_int, c_ptr]),
     "usip_layer_fwd": (c_int, [ctypes.POINTER(LayerDesc), c_ptr]),
     "usip_layer_tile_rows": (c_int, []),
+    "usip_layer_tc_workspace_bytes": (c_i64, [c_int, c_int]),
     "usip_bn_finalize": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr,
                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "usip_bn_eval_affine": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_int, c_ptr, c_ptr, c_ptr]),

@@ -398,6 +398,7 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st);   // mlp_tc.cu
 using namespace usip;
 
 extern "C" int usip_layer_tile_rows(void) { return L_BM; }
+extern "C" int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout) { return (int64_t)2 * Cin * Cout * 4; }
 
 extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
   USIP_REQUIRE(dp, "layer_fwd: null desc");

@@ -1,5 +1,500 @@
-// mlp_tc.cu -- tcgen05 (3xTF32) path of usip_layer_fwd.  PLACEHOLDER until the kernel lands.
+// mlp_tc.cu -- tcgen05 / TMEM path of usip_layer_fwd (precision == 1): 3xTF32 error-compensated GEMM
+//
+//     Y[P,Cout] = act(X)[P,Cin] * W[Cout,Cin]^T (+bias, +addend),     act = folded BN affine + ReLU
+//
+// with  a = a_hi + a_lo (a_hi = rna_tf32(a), a_lo = rna_tf32(a - a_hi)) and likewise for W:
+//     D += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi        (dropped term a_lo*w_lo ~ 2^-22 relative)
+// which keeps fp32-level accuracy (the 1e-4 parity bar) at 1/3 of the TF32 tensor rate.
+//
+// Persistent, warp-specialised CTA (one per SM), 13 warps:
+//   warps 0-3  : epilogue  (TMEM lanes 32*(w%4)..+31): tcgen05.ld -> bias/addend -> Y, BN statistic
+//                partials and per-group max/min (+arg) of the raw output
+//   warp  4    : TMEM allocation, mbarrier init, single-thread tcgen05.mma issue
+//   warps 5-12 : A-operand producers, two groups of four warps on alternating K chunks: coalesced
+//                float4 loads of X, BN/ReLU prologue, hi/lo split, 128B-swizzled st.shared;
+//                one elected thread per chunk also issues the bulk-TMA (cp.async.bulk) copies of the
+//                pre-split, pre-swizzled weight tiles.
+// Pipelines: smem full/empty ring (STAGES deep) between producers and MMA, TMEM full/empty (2
+// accumulators) between MMA and epilogue, static round-robin tile scheduler.
+//
+// Operand tiles are K-major, SWIZZLE_128B: row r (128 B = 32 tf32) at r*128, 16-byte chunk c stored at
+// chunk (c ^ (r & 7)); 8-row groups 1024 B apart (SBO).  One K chunk = 32 floats = 4 MMA k-steps of 8.
 #include "common.cuh"
+
 namespace usip {
-int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) { (void)d; (void)st; return fail("layer_fwd_tc: not built"); }
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                  // floats per K chunk (= one 128-byte swizzle row)
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_MMA_WARP = 4;
+constexpr int TC_PROD_WARP0 = 5;
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_PROD_WARP0 + TC_PROD_WARPS) * 32;   // 416
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M=128, N from idesc, K=8
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 (1024 B) |
+//  [46,48) version=1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32(1)@4, a=TF32(2)@7, b=TF32(2)@10,
+// a/b K-major (0), N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk): [hi | lo] blocks of BN x 128 B,
+// already 128B-swizzled, so a tile is one contiguous bulk copy.
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int Cout, int Cin, int BN,
+                                       uint32_t* __restrict__ out) {
+  const int KC = Cin / TC_BK;
+  const int total = Cout * (Cin / 4);                 // one thread per 16-byte chunk
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int n = t / (Cin / 4), k4 = t - n * (Cin / 4);
+  const int kc = k4 / 8, c = k4 & 7;                  // chunk c of K chunk kc
+  const int nt = n / BN, r = n - nt * BN;
+  const float* src = W + (size_t)n * ldw + k4 * 4;
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_tf32(src[j], hi[j], lo[j]);
+  const size_t blk = ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;     // in 32-bit words
+  const size_t off = (size_t)r * TC_BK + (size_t)((c ^ (r & 7)) * 4);
+  *reinterpret_cast<uint4*>(out + blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(out + blk + (size_t)BN * TC_BK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_STAGE = 2 * TC_BM * 128;                 // hi + lo
+  static constexpr int B_STAGE = 2 * BN * 128;
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int TRANS = TC_EPI_WARPS * 32 * 33 * 4;       // per-warp 32x33 transpose tile
+  static constexpr int COMB = (BN <= 128 ? 6 : 2) * TC_EPI_WARPS * BN * 4;   // sum, sumsq (+ max, min, args for group > 32)
+  static constexpr int BARS = 256;
+  static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + BARS + 1024;   // +1024 alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack) {
+  using SM = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
+  uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  // carve
+  const uint32_t stage_base = smem_base;
+  float* trans = reinterpret_cast<float*>(smem + STAGES * SM::STAGE);
+  float* comb = reinterpret_cast<float*>(smem + STAGES * SM::STAGE + SM::TRANS);
+  const uint32_t bar_base = smem_base + STAGES * SM::STAGE + SM::TRANS + SM::COMB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * SM::STAGE + SM::TRANS + SM::COMB + 192);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = d.P, Cin = d.Cin, Cout = d.Cout;
+  const int KC = Cin / TC_BK;
+  const int m_tiles = (P + TC_BM - 1) / TC_BM, n_tiles = Cout / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+
+  if (warp == TC_MMA_WARP) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= TC_PROD_WARP0) {
+    // =============================== A producers (+ weight bulk copies) ===========================
+    const int pw = warp - TC_PROD_WARP0;            // 0..7
+    const int grp = pw >> 2;                        // K chunks with (it & 1) == grp
+    const int pt = (pw & 3) * 32 + lane;            // 0..127 inside the group
+    const int c = pt & 7;                           // 16-byte chunk (4 floats) of the 128-byte row
+    const int r0 = pt >> 3;                         // rows r0 + 16*j
+    const bool has_aff = d.in_scale != nullptr;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int row0 = mt * TC_BM;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        if ((int)(it & 1) != grp) continue;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t a_hi = stage_base + s * SM::STAGE;
+        const uint32_t a_lo = a_hi + TC_BM * 128;
+        const uint32_t b_hi = a_hi + SM::A_STAGE;
+        if (pt == 0) {
+          mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
+          const uint32_t* src = wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;
+          bulk_g2s(b_hi, src, SM::B_STAGE, full_bar(s));          // [hi | lo] contiguous
+        }
+        const int k = kc * TC_BK + c * 4;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_aff) {
+          sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + k));
+          sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + k));
+        }
+        float4 x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = row0 + r0 + 16 * j;
+          x[j] = row < P ? __ldg(reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r0 + 16 * j;
+          float v[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+          if (has_aff) {
+            v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
+            v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+          }
+          if (d.in_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+          if (row0 + r >= P) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_tf32(v[q], hi[q], lo[q]);
+          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+        fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(s));
+      }
+    }
+  } else if (warp == TC_MMA_WARP) {
+    // =============================== MMA issuer (one thread) =====================================
+    constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int kc = 0; kc < KC; ++kc, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(full_bar(s), (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = stage_base + s * SM::STAGE;
+          const uint32_t a_lo = a_hi + TC_BM * 128;
+          const uint32_t b_hi = a_hi + SM::A_STAGE;
+          const uint32_t b_lo = b_hi + BN * 128;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = make_kmajor_sw128_desc(a_hi + ks * 32), dal = make_kmajor_sw128_desc(a_lo + ks * 32);
+            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ks * 32), dbl = make_kmajor_sw128_desc(b_lo + ks * 32);
+            umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
+          if (kc == KC - 1) umma_commit(tfull_bar(buf));   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================== epilogue warps 0..3 ========================================
+    const int q = warp;                               // TMEM lane quarter
+    float* tw = trans + q * (32 * 33);
+    const int g = d.group;
+    const bool want_stats = d.stat_partial != nullptr;
+    const bool want_grp = (d.gmax != nullptr) || (d.gmin != nullptr);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int row0 = mt * TC_BM, n0 = nt * BN;
+      const uint32_t buf = tcount & 1;
+      const int wrow0 = row0 + q * 32;                // first row of this warp
+      const int row = wrow0 + lane;
+      const bool rok = row < P;
+      const int nvalid = min(32, max(0, P - wrow0));  // valid rows of this warp
+      const float* addp = nullptr;
+      if (d.addend && rok) {
+        const int gi = d.add_index ? __ldg(d.add_index + row) : row / d.add_group;
+        addp = d.addend + (size_t)gi * d.ld_add + n0;
+      }
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(taddr + ch * 32, v);
+        const int cb = n0 + ch * 32;
+        if (d.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + cb + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+        if (addp) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + ch * 32 + j));
+            v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+          }
+        }
+        if (d.Y && rok) {
+          float* yp = d.Y + (size_t)row * d.ldy + cb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (want_stats || want_grp) {
+          // transpose through shared memory: afterwards lane j owns column cb + j of this warp's 32 rows
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tw[lane * 33 + j] = v[j];
+          __syncwarp();
+          float s = 0.f, ss = 0.f;
+          float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
+          int ax0 = 0, an0 = 0, ax1 = 0, an1 = 0;
+          const int half = (g == 16) ? 16 : 32;       // rows per in-warp group segment
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float x = tw[r * 33 + lane];
+            const bool ok = r < nvalid;
+            if (ok) { s += x; ss = fmaf(x, x, ss); }
+            if (r < half) {
+              if (ok && x > mx0) { mx0 = x; ax0 = r; }
+              if (ok && x < mn0) { mn0 = x; an0 = r; }
+            } else {
+              if (ok && x > mx1) { mx1 = x; ax1 = r; }
+              if (ok && x < mn1) { mn1 = x; an1 = r; }
+            }
+          }
+          __syncwarp();
+          const int cl = ch * 32 + lane;              // column inside the tile
+          if (want_stats) { comb[(0 * 4 + q) * BN + cl] = s; comb[(1 * 4 + q) * BN + cl] = ss; }
+          if (want_grp) {
+            if (g == 16) {
+              const int grow = wrow0 / 16;
+              if (nvalid > 0) {
+                if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
+                if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
+                if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
+                if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
+              }
+              if (nvalid > 16) {
+                if (d.gmax) d.gmax[(size_t)(grow + 1) * Cout + cb + lane] = mx1;
+                if (d.gmin) d.gmin[(size_t)(grow + 1) * Cout + cb + lane] = mn1;
+                if (d.garg_max) d.garg_max[(size_t)(grow + 1) * Cout + cb + lane] = ax1 - 16;
+                if (d.garg_min) d.garg_min[(size_t)(grow + 1) * Cout + cb + lane] = an1 - 16;
+              }
+            } else if (g == 32) {
+              if (nvalid > 0) {
+                const int grow = wrow0 / 32;
+                if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
+                if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
+                if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
+                if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
+              }
+            } else {                                    // 64 / 128: combine across warps below
+              comb[(2 * 4 + q) * BN + cl] = mx0; comb[(3 * 4 + q) * BN + cl] = mn0;
+              reinterpret_cast<int*>(comb)[(4 * 4 + q) * BN + cl] = q * 32 + ax0;
+              reinterpret_cast<int*>(comb)[(5 * 4 + q) * BN + cl] = q * 32 + an0;
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (want_stats || (want_grp && g > 32)) {
+        named_bar_sync(1, TC_EPI_WARPS * 32);
+        const int t = threadIdx.x;                     // 0..127
+        for (int cl = t; cl < BN; cl += TC_EPI_WARPS * 32) {
+          if (want_stats) {
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { s += comb[(0 * 4 + w) * BN + cl]; ss += comb[(1 * 4 + w) * BN + cl]; }
+            d.stat_partial[((size_t)mt * 2 + 0) * Cout + n0 + cl] = s;
+            d.stat_partial[((size_t)mt * 2 + 1) * Cout + n0 + cl] = ss;
+          }
+          if (want_grp && g > 32) {
+            const int wpg = g / 32;                    // warps per group: 2 or 4
+            for (int gi = 0; gi < 4 / wpg; ++gi) {
+              const int grow = row0 / g + gi;
+              if ((size_t)grow * g >= (size_t)P) break;
+              float mx = -INFINITY, mn = INFINITY; int ax = 0, an = 0;
+              for (int w = gi * wpg; w < (gi + 1) * wpg; ++w) {
+                float a = comb[(2 * 4 + w) * BN + cl], b = comb[(3 * 4 + w) * BN + cl];
+                if (a > mx) { mx = a; ax = reinterpret_cast<int*>(comb)[(4 * 4 + w) * BN + cl]; }
+                if (b < mn) { mn = b; an = reinterpret_cast<int*>(comb)[(5 * 4 + w) * BN + cl]; }
+              }
+              if (d.gmax) d.gmax[(size_t)grow * Cout + n0 + cl] = mx;
+              if (d.gmin) d.gmin[(size_t)grow * Cout + n0 + cl] = mn;
+              if (d.garg_max) d.garg_max[(size_t)grow * Cout + n0 + cl] = ax - gi * g;
+              if (d.garg_min) d.garg_min[(size_t)grow * Cout + n0 + cl] = an - gi * g;
+            }
+          }
+        }
+        named_bar_sync(1, TC_EPI_WARPS * 32);          // comb is reused by the next tile
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
+  using SM = TcSmem<BN, STAGES>;
+  static_assert(SM::BYTES <= 232448, "shared memory budget");
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    if (e != cudaSuccess) { sm_count = 0; set_last_error("layer_fwd_tc smem attr"); return (int)e; }
+  }
+  const int m_tiles = cdiv(d.P, TC_BM), n_tiles = d.Cout / BN;
+  const int grid = min(sm_count, m_tiles * n_tiles);
+  layer_fwd_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
+  return check_launch("layer_fwd_tc_kernel");
+}
+
+int tc_tile_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
+
+int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
+  USIP_REQUIRE(d.Cin % TC_BK == 0 && d.Cout % 64 == 0, "layer_fwd_tc: needs Cin%32==0 and Cout%64==0");
+  USIP_REQUIRE((d.ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(d.X) % 16) == 0, "layer_fwd_tc: X must be 16B aligned");
+  USIP_REQUIRE(!d.Y || ((d.ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(d.Y) % 16) == 0), "layer_fwd_tc: Y must be 16B aligned");
+  USIP_REQUIRE(!d.addend || ((d.ld_add % 4) == 0 && (reinterpret_cast<uintptr_t>(d.addend) % 16) == 0), "layer_fwd_tc: addend alignment");
+  USIP_REQUIRE(!d.bias || (reinterpret_cast<uintptr_t>(d.bias) % 16) == 0, "layer_fwd_tc: bias alignment");
+  USIP_REQUIRE(!d.in_scale || ((reinterpret_cast<uintptr_t>(d.in_scale) % 16) == 0 && (reinterpret_cast<uintptr_t>(d.in_shift) % 16) == 0),
+               "layer_fwd_tc: scale/shift alignment");
+  USIP_REQUIRE(d.tc_workspace && d.tc_workspace_bytes >= (int64_t)2 * d.Cout * d.Cin * 4, "layer_fwd_tc: workspace too small");
+  if (d.gmax || d.gmin) USIP_REQUIRE(d.group == 16 || d.group == 32 || d.group == 64 || d.group == 128, "layer_fwd_tc: group must be 16/32/64/128");
+  int BN = tc_tile_n(d.Cout);
+  if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
+  uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
+  if (!d.tc_weights_packed) {
+    const int total = d.Cout * (d.Cin / 4);
+    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.Cout, d.Cin, BN, wpack);
+    int e = check_launch("tc_pack_weights_kernel");
+    if (e) return e;
+  }
+  if (BN == 256) return launch_tc<256, 2>(d, wpack, st);
+  if (BN == 128) return launch_tc<128, 3>(d, wpack, st);
+  return launch_tc<64, 4>(d, wpack, st);
+}
+
+}  // namespace usip

@@ -144,7 +144,7 @@ def knn_nodes(pts, K):
 # ----------------------------------------------------------------------------- shared-MLP stack
 def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_shift=None, in_relu=False,
               addend=None, add_index=None, add_group=0, Y=None, ldy=None, stat_partial=None,
-              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0):
+              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False):
     d = LayerDesc()
     d.X = X.data_ptr(); d.ldx = X.stride(0) if ldx is None else ldx
     d.P = P; d.Cin = Cin; d.Cout = Cout
@@ -166,6 +166,11 @@ def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_sh
     d.garg_min = None if garg_min is None else garg_min.data_ptr()
     d.group = group
     d.precision = precision
+    if precision == 1:
+        if tc_ws is None:
+            tc_ws = torch.empty((2 * Cin * Cout,), dtype=f32, device=X.device)
+        d.tc_workspace = tc_ws.data_ptr(); d.tc_workspace_bytes = tc_ws.numel() * 4
+        d.tc_weights_packed = 1 if tc_packed else 0
     check(_lib.load().usip_layer_fwd(ctypes.byref(d), _stream()), "usip_layer_fwd")
 
 
