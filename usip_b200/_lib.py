@@ -100,7 +100,13 @@ def load():
     return lib
 
 
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
+KERNELS_PER_CALL = {"usip_cluster_sort": 3, "usip_pairwise_min_f32": 3, "usip_layer_fwd_tc": 2}
+LAUNCHES = [0]
+
+
 def check(code, what):
+    LAUNCHES[0] += KERNELS_PER_CALL.get(what, 1)
     if code != 0:
         lib = load()
         msg = lib.usip_last_error().decode()

@@ -20,6 +20,41 @@ f32 = torch.float32
 i32 = torch.int32
 EPS = 1e-5
 
+# Optional per-op device timing (bench.py): set PROFILE = {} to record CUDA-event pairs around every op of the
+# plan on the launching stream; collect_profile() turns them into mean milliseconds per op name.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, name, flops=None, nbytes=None, precision=None):
+        self.on = PROFILE is not None
+        if self.on:
+            self.name, self.flops, self.nbytes, self.precision = name, flops, nbytes, precision
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            rec = PROFILE.setdefault(self.name, dict(ev=[], flops=self.flops, bytes=self.nbytes, precision=self.precision))
+            rec["ev"].append((self.e0, self.e1))
+        return False
+
+
+def collect_profile():
+    out = {}
+    if not PROFILE:
+        return out
+    torch.cuda.synchronize()
+    for k, rec in PROFILE.items():
+        ms = [a.elapsed_time(b) for a, b in rec["ev"]]
+        out[k] = dict(ms=sum(ms) / len(ms), n=len(ms), flops=rec["flops"], bytes=rec["bytes"], precision=rec["precision"])
+    return out
+
 
 def _w2d(w):
     return w.detach().reshape(w.shape[0], -1)
@@ -68,7 +103,7 @@ class LayerRunner:
         return torch.empty((ntiles, 2, Cout), dtype=f32, device=self.dev), ntiles
 
     def run(self, X, P, W, bias, norm=None, momentum=0.1, prev=None, relu_in=None, Y=None, write_y=True,
-            addend=None, add_index=None, add_group=0, group=0, want_group=False, want_arg=False, count=None):
+            addend=None, add_index=None, add_group=0, group=0, want_group=False, want_arg=False, count=None, name="layer"):
         """Y = act(X) W^T + bias (+addend); returns (Y, BNState or None, group dict or None)."""
         Cout, Cin = W.shape
         if Y is None and write_y:
@@ -82,18 +117,22 @@ class LayerRunner:
             if want_arg:
                 grp["amax"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
                 grp["amin"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
-        ops.layer_fwd(X, W, bias, P, Cin, Cout,
-                      in_scale=None if prev is None else prev.scale, in_shift=None if prev is None else prev.shift,
-                      in_relu=(prev is not None) if relu_in is None else relu_in,
-                      addend=addend, add_index=add_index, add_group=add_group, Y=Y if write_y else None,
-                      stat_partial=part,
-                      gmax=None if grp is None else grp["gmax"], gmin=None if grp is None else grp["gmin"],
-                      garg_max=None if grp is None else grp.get("amax"),
-                      garg_min=None if grp is None else grp.get("amin"),
-                      group=group, precision=_precision_for(P, Cin, Cout, self.use_tc))
+        prec = _precision_for(P, Cin, Cout, self.use_tc)
+        with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
+                   precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
+            ops.layer_fwd(X, W, bias, P, Cin, Cout,
+                          in_scale=None if prev is None else prev.scale, in_shift=None if prev is None else prev.shift,
+                          in_relu=(prev is not None) if relu_in is None else relu_in,
+                          addend=addend, add_index=add_index, add_group=add_group, Y=Y if write_y else None,
+                          stat_partial=part,
+                          gmax=None if grp is None else grp["gmax"], gmin=None if grp is None else grp["gmin"],
+                          garg_max=None if grp is None else grp.get("amax"),
+                          garg_min=None if grp is None else grp.get("amin"),
+                          group=group, precision=prec)
         st = None
         if norm is not None:
-            st = self.bn_state(norm, part, ntiles, P if count is None else count, momentum)
+            with _Prof("bn_finalize"):
+                st = self.bn_state(norm, part, ntiles, P if count is None else count, momentum)
         return Y, st, grp
 
 
@@ -127,42 +166,49 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     snc = sn.detach().contiguous() if S else None
 
     # ---- grouping (som.query_topk + networks.py:87-108)
-    min_idx, count = ops.som_assign(x, node)
-    seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
-    cmean, X0 = ops.cluster_mean_decenter(x, snc, seg_off, perm, M, ldx=8)
+    with _Prof("som_assign", nbytes=4.0 * Bp * (4 * N + 3 * M)):
+        min_idx, count = ops.som_assign(x, node)
+    with _Prof("cluster_sort"):
+        seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
+    with _Prof("cluster_mean_decenter", nbytes=4.0 * Bp * N * (3 + S + 8 + 1)):
+        cmean, X0 = ops.cluster_mean_decenter(x, snc, seg_off, perm, M, ldx=8)
 
     # ---- first PointNet (3+S -> C1/2 -> C1/2 -> C1/2), networks.py:111-114
     fp = net.first_pointnet.layers
     H = fp[0].conv.weight.shape[0]
-    Y0, bn0, _ = R.run(X0, P, _w2d(fp[0].conv.weight), fp[0].conv.bias.detach(), fp[0].norm, _bn_mom(fp[0].norm, epoch))
-    Y1, bn1, _ = R.run(Y0, P, _w2d(fp[1].conv.weight), fp[1].conv.bias.detach(), fp[1].norm, _bn_mom(fp[1].norm, epoch), prev=bn0)
-    F1, _, _ = R.run(Y1, P, _w2d(fp[2].conv.weight), fp[2].conv.bias.detach(), prev=bn1)
+    Y0, bn0, _ = R.run(X0, P, _w2d(fp[0].conv.weight), fp[0].conv.bias.detach(), fp[0].norm, _bn_mom(fp[0].norm, epoch), name="pn1.0")
+    Y1, bn1, _ = R.run(Y0, P, _w2d(fp[1].conv.weight), fp[1].conv.bias.detach(), fp[1].norm, _bn_mom(fp[1].norm, epoch), prev=bn0, name="pn1.1")
+    F1, _, _ = R.run(Y1, P, _w2d(fp[2].conv.weight), fp[2].conv.bias.detach(), prev=bn1, name="pn1.2")
     # ---- pool 1 (index_max + gather * mask, networks.py:117-120)
-    pool1, arg1 = ops.segmax(F1, H, seg_off, perm, Bp, N, M, want_arg=keep)
+    with _Prof("segmax1", nbytes=4.0 * P * H):
+        pool1, arg1 = ops.segmax(F1, H, seg_off, perm, Bp, N, M, want_arg=keep)
     # ---- second PointNet on cat(first, scattered max) (networks.py:123-127): W [f; s] = Wa f + Wb s
     sp = net.second_pointnet.layers
     C1 = sp[0].conv.weight.shape[0]
     W3 = _w2d(sp[0].conv.weight)
-    V, _, _ = R.run(pool1, Q, W3[:, H:], None, relu_in=False)
+    V, _, _ = R.run(pool1, Q, W3[:, H:], None, relu_in=False, name="pn2.0_node")
     Y3, bn3, _ = R.run(F1, P, W3[:, :H], sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
-                       relu_in=False, addend=V, add_index=row_seg)
-    F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3)
+                       relu_in=False, addend=V, add_index=row_seg, name="pn2.0")
+    F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3, name="pn2.1")
     # ---- pool 2 -> first C1 columns of the head input (networks.py:130-133,143)
     kb = net.knnlayer_1.layers_before
     ka = net.knnlayer_1.layers_after
     C2 = ka[-1].conv.weight.shape[0]
     AGG = torch.empty((Q, C1 + C2), dtype=f32, device=dev)
     pool2 = AGG[:, :C1]
-    _, arg2 = ops.segmax(F2, C1, seg_off, perm, Bp, N, M, out=pool2, want_arg=keep)
+    with _Prof("segmax2", nbytes=4.0 * P * C1):
+        _, arg2 = ops.segmax(F2, C1, seg_off, perm, Bp, N, M, out=pool2, want_arg=keep)
 
     # ---- GeneralKNNFusionModule (layers.py:401-440)
-    knn_i = ops.knn_nodes(cmean, Kn)
+    with _Prof("knn_nodes"):
+        knn_i = ops.knn_nodes(cmean, Kn)
     W5 = _w2d(kb[0].conv.weight)
     Cb = W5.shape[0]
-    Z, _, _ = R.run(pool2, Q, W5[:, 3:], None, relu_in=False)
+    Z, _, _ = R.run(pool2, Q, W5[:, 3:], None, relu_in=False, name="knn_b0_node")
     Y5 = torch.empty((G, Cb), dtype=f32, device=dev)
     part5, nt5 = R.partials(G, Cb)
-    ops.knn_combine(Z, cmean, knn_i, W5, W5.stride(0), kb[0].conv.bias.detach(), Y5, part5, Bp, M, Kn, Cb)
+    with _Prof("knn_combine", nbytes=8.0 * G * Cb):
+        ops.knn_combine(Z, cmean, knn_i, W5, W5.stride(0), kb[0].conv.bias.detach(), Y5, part5, Bp, M, Kn, Cb)
     bn5 = R.bn_state(kb[0].norm, part5, nt5, G, _bn_mom(kb[0].norm, epoch))
     prev, Yprev = bn5, Y5
     saved_before = [(Y5, bn5)]
@@ -170,17 +216,19 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     for li in range(1, len(kb)):
         last = li == len(kb) - 1
         Yn, bnn, grp = R.run(Yprev, G, _w2d(kb[li].conv.weight), kb[li].conv.bias.detach(), kb[li].norm,
-                             _bn_mom(kb[li].norm, epoch), prev=prev, group=Kn, want_group=last, want_arg=last and keep)
+                             _bn_mom(kb[li].norm, epoch), prev=prev, group=Kn, want_group=last, want_arg=last and keep,
+                             name="knn_b%d" % li)
         prev, Yprev = bnn, Yn
         saved_before.append((Yn, bnn))
         grp_b = grp if last else grp_b
     # max over K of the activated features (layers.py:433): from group max/min of the raw output
     amax = torch.empty((Q, Cb), dtype=f32, device=dev)
-    ops.group_select(grp_b["gmax"], grp_b["gmin"], prev.scale, prev.shift, amax, Q, Cb)
+    with _Prof("group_select"):
+        ops.group_select(grp_b["gmax"], grp_b["gmin"], prev.scale, prev.shift, amax, Q, Cb)
     W8 = _w2d(ka[0].conv.weight)
-    U, _, _ = R.run(amax, Q, W8[:, :Cb], None, relu_in=False)                                    # max half (layers.py:435)
+    U, _, _ = R.run(amax, Q, W8[:, :Cb], None, relu_in=False, name="knn_a0_node")                                    # max half (layers.py:435)
     Y8, bn8, _ = R.run(Yprev, G, W8[:, Cb:], ka[0].conv.bias.detach(), ka[0].norm, _bn_mom(ka[0].norm, epoch),
-                       prev=prev, addend=U, add_group=Kn)
+                       prev=prev, addend=U, add_group=Kn, name="knn_a0")
     saved_after = [(Y8, bn8)]
     prevA, YA = bn8, Y8
     grp_a = None
@@ -188,7 +236,7 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
         last = li == len(ka) - 1
         Yn, bnn, grp = R.run(YA, G, _w2d(ka[li].conv.weight), ka[li].conv.bias.detach(), ka[li].norm,
                              _bn_mom(ka[li].norm, epoch), prev=prevA, group=Kn, want_group=last, want_arg=last and keep,
-                             write_y=not last)
+                             write_y=not last, name="knn_a%d" % li)
         prevA, YA = bnn, Yn
         saved_after.append((Yn, bnn))
         grp_a = grp if last else grp_a
@@ -196,11 +244,12 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
 
     # ---- head (networks.py:143-154); mlp1/mlp2 are called WITHOUT epoch in the reference
     Y10, bn10, _ = R.run(AGG, Q, _w2d(net.mlp1.conv.weight), net.mlp1.conv.bias.detach(), net.mlp1.norm,
-                         net.mlp1.norm.momentum, relu_in=False)
+                         net.mlp1.norm.momentum, relu_in=False, name="mlp1")
     Y11, bn11, _ = R.run(Y10, Q, _w2d(net.mlp2.conv.weight), net.mlp2.conv.bias.detach(), net.mlp2.norm,
-                         net.mlp2.norm.momentum, prev=bn10)
-    OUT, _, _ = R.run(Y11, Q, _w2d(net.mlp3.conv.weight), net.mlp3.conv.bias.detach(), prev=bn11)
-    keypoints, sigmas = ops.head_finalize(OUT, cmean, opt.loss_sigma_lower_bound, Bp, M)
+                         net.mlp2.norm.momentum, prev=bn10, name="mlp2")
+    OUT, _, _ = R.run(Y11, Q, _w2d(net.mlp3.conv.weight), net.mlp3.conv.bias.detach(), prev=bn11, name="mlp3")
+    with _Prof("head_finalize"):
+        keypoints, sigmas = ops.head_finalize(OUT, cmean, opt.loss_sigma_lower_bound, Bp, M)
 
     ctx = None
     if keep:
@@ -222,3 +271,15 @@ def chamfer_prob_forward(src, dst, sig_src, sig_dst):
     d_ds, i_ds = ops.pairwise_min(dst, src)
     out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src.contiguous(), sig_dst.contiguous())
     return out3, (d_sd, i_sd, d_ds, i_ds)
+
+
+def detector_backward(net, ctx, g_kp, g_sig):
+    raise NotImplementedError("detector backward plan not built yet")
+
+
+def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):
+    raise NotImplementedError("descriptor plan not built yet")
+
+
+def descriptor_backward(net, ctx, g_desc):
+    raise NotImplementedError("descriptor backward plan not built yet")

@@ -22,7 +22,9 @@ class _PairMinFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         a = a.contiguous(); b = b.contiguous()
-        d, arg = ops.pairwise_min(a, b)
+        from .. import engine
+        with engine._Prof("pairwise_min[%dx%dx%d]" % (a.shape[0], a.shape[2], b.shape[2])):
+            d, arg = ops.pairwise_min(a, b)
         ctx.save_for_backward(a, b, d, arg)
         return d
 
@@ -43,9 +45,11 @@ class _ChamferProbFn(torch.autograd.Function):
     def forward(ctx, src, dst, sig_src, sig_dst):
         src = src.contiguous(); dst = dst.contiguous()
         sig_src = sig_src.contiguous(); sig_dst = sig_dst.contiguous()
-        d_sd, i_sd = ops.pairwise_min(src, dst)
-        d_ds, i_ds = ops.pairwise_min(dst, src)
-        out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst)
+        from .. import engine
+        with engine._Prof("chamfer_prob"):
+            d_sd, i_sd = ops.pairwise_min(src, dst)
+            d_ds, i_ds = ops.pairwise_min(dst, src)
+            out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst)
         ctx.save_for_backward(src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds)
         loss, pure, weighted = out3[0], out3[1], out3[2]
         ctx.mark_non_differentiable(pure, weighted)
