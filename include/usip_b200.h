@@ -91,6 +91,8 @@ typedef struct usip_layer_desc {
   const float* X;  int32_t ldx;        /* [P,Cin] input (pre-activation of the previous layer)       */
   int32_t P, Cin, Cout;
   const float* W;  int32_t ldw;        /* [Cout,Cin] weight rows, row stride ldw (conv weight layout)  */
+  int32_t w_transposed;                /* 1: W is stored [Cin,Cout] (row stride ldw) -- dgrad uses the
+                                          forward weight as-is: G_in = G_out * W                        */
   const float* bias;                   /* [Cout] or NULL                                              */
   const float* in_scale;               /* [Cin] or NULL: a = x*in_scale+in_shift (folded BatchNorm)   */
   const float* in_shift;
@@ -182,6 +184,45 @@ int usip_chamfer_prob_bwd(const float* src, const float* dst, const float* sig_s
                           int B, int M, int N, void* stream);
 int usip_transform_points_bwd(const float* g_out, const float* R, const float* scale, float* g_kp,
                               int B, int M, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 5. Backward pass of the fused plan (autograd of models/networks.py:75-162 / layers.py re-derived)
+ * ---------------------------------------------------------------------------------------------- */
+/* train-mode BatchNorm(+ReLU) backward: partial sums of g_z and g_z*xhat per 128-row tile ([ntiles,2,C]) */
+int usip_bn_bwd_reduce(const float* G, int ldg, const float* Y, int ldy, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, int relu, float* part, int P, int C, void* stream);
+/* -> g_gamma, g_beta (optionally accumulated) and the per-channel constants c1 = g_beta/n, c2 = g_gamma/n */
+int usip_bn_bwd_finalize(const float* part, int ntiles, int64_t count, int C, float* g_gamma, float* g_beta,
+                         float* c1, float* c2, int accumulate, void* stream);
+/* g_y = scale*(g*1[z>0] - c1 - xhat*c2); GY may alias G */
+int usip_bn_bwd_apply(const float* G, int ldg, const float* Y, int ldy, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
+                      float* GY, int ldo, int P, int C, void* stream);
+/* group-max layers (max_k relu(bn(y_k)), layers.py:433,438) */
+int usip_groupmax_bwd_select(const float* Gout, int ldg, const float* gmax, const float* gmin, const int32_t* amax,
+                             const int32_t* amin, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, float* gz, int32_t* argsel, float* part, int Q, int C, void* stream);
+int usip_groupmax_scatter_add(float* G, int ldg, const float* gsrc, const int32_t* argsel, int K, int Q, int C,
+                              void* stream);
+int usip_groupmax_bwd_apply(const float* Y, int ldy, const float* gz, const int32_t* argsel, const float* scale,
+                            const float* mean, const float* invstd, const float* c1, const float* c2, float* GY,
+                            int ldo, int K, int P, int C, void* stream);
+int usip_group_sum(const float* G, int ldg, float* out, int ldo, int K, int Q, int C, void* stream);
+int usip_seg_sum(const float* G, int ldg, const int32_t* seg_off, float* out, int ldo, int B, int N, int M, int C,
+                 void* stream);
+/* arg-max un-pooling (backward of usip_segmax): G[arg[q,c], c] (+)= gp[q,c] */
+int usip_unpool_scatter(float* G, int ldg, const float* gp, int ldp, const int32_t* arg, int Q, int C,
+                        int accumulate, void* stream);
+/* backward of usip_knn_combine: GZ (pre-zeroed) += scatter of GY by neighbour; gW[:,0:3] += GY^T delta_xyz */
+int usip_knn_combine_bwd(const float* GY, int ldg, const float* pts, const int32_t* knn_idx, float* GZ, int ldz,
+                         float* gW, int ldw, int B, int M, int K, int C, void* stream);
+/* out[c] += sum_r G[r,c] */
+int usip_colsum(const float* G, int ldg, float* out, int P, int C, void* stream);
+int usip_head_bwd(const float* g_kp, const float* g_sig, const float* out4, int ld, float* G, int B, int M,
+                  void* stream);
+/* gW[Cout,Cin] += GY[P,Cout]^T * act(X)[P,Cin], act = optional folded BN affine + ReLU (same prologue as forward) */
+int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale, const float* in_shift,
+               int in_relu, float* gW, int ldw, int P, int Cout, int Cin, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,3 +87,42 @@ def test_detector_vs_oracle_medium(use_tc):
     assert rel_err(sig, np.concatenate([r["src_sigmas"], r["dst_sigmas"]])) < REL
     assert abs(md.loss.item() - r["loss"]) <= REL * abs(r["loss"])
     assert abs(md.loss_chamfer.item() - r["loss_chamfer"]) <= REL * abs(r["loss_chamfer"])
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("fname", ["detector_kitti_small.npz", "detector_modelnet_small.npz", "detector_lite_small.npz"])
+def test_detector_train_step_vs_reference_golden(fname, use_tc):
+    """One full ModelDetector.optimize() (train-mode forward, loss, backward, Adam) against the reference's own
+    gradients and post-step parameters (tools/make_golden.py ran test_model() then optimize(epoch=0))."""
+    g, d, P, md = _setup(fname, use_tc)
+    md.test_model()
+    md.optimize(epoch=0)
+    torch.cuda.synchronize()
+    lv = _loss_vec(md)
+    assert np.all(np.abs(lv - g["train_loss"]) <= REL * np.abs(g["train_loss"]) + 1e-6), (lv, g["train_loss"])
+    worst = 0.0
+    for k, p in md.detector.named_parameters():
+        ref = g["grad/" + k]
+        gr = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        absmax, norm = float(ref[2]), float(ref[3])
+        if k.endswith("conv.bias") and norm < 1e-6:
+            assert np.linalg.norm(gr) < 1e-5, k          # bias in front of BN: true gradient is 0 (reference: fp noise)
+            continue
+        e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
+        e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
+        worst = max(worst, e_norm, e_el)
+        assert e_norm < 2e-3 and e_el < 2e-3, (k, e_norm, e_el)
+    # parameters after the Adam step: the first Adam update is lr*sign(g) (|g| >> eps), so agreement needs the same
+    # gradient sign; allow the few near-zero-gradient entries to differ by at most 2*lr
+    sd = md.detector.state_dict()
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked"):
+            continue
+        ref = g["after/" + k]
+        flat = v.cpu().numpy().reshape(-1)
+        n = min(24, flat.size)
+        diff = np.abs(flat[:n] - ref[3:3 + n])
+        tol = 1e-5 + 2e-4 * np.abs(ref[3:3 + n])
+        assert diff.max() <= 2.2e-3, (k, diff.max())
+        assert (diff <= tol).mean() >= 0.85 or k.endswith("conv.bias"), (k, diff, tol)
+    print("worst gradient rel err", worst)

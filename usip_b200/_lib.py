@@ -18,6 +18,7 @@ class LayerDesc(ctypes.Structure):
         ("X", c_ptr), ("ldx", ctypes.c_int32),
         ("P", ctypes.c_int32), ("Cin", ctypes.c_int32), ("Cout", ctypes.c_int32),
         ("W", c_ptr), ("ldw", ctypes.c_int32),
+        ("w_transposed", ctypes.c_int32),
         ("bias", c_ptr),
         ("in_scale", c_ptr), ("in_shift", c_ptr),
         ("in_relu", ctypes.c_int32),
@@ -70,6 +71,22 @@ SIGNATURES = {
     "usip_pairwise_min_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr]),
     "usip_chamfer_prob_bwd": (c_int, [c_ptr] * 13 + [c_int, c_int, c_int, c_ptr]),
     "usip_transform_points_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr]),
+    "usip_bn_bwd_reduce": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_ptr]),
+    "usip_bn_bwd_finalize": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr]),
+    "usip_bn_bwd_apply": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
+                                  c_int, c_int, c_int, c_ptr]),
+    "usip_groupmax_bwd_select": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr, c_int, c_int, c_ptr]),
+    "usip_groupmax_scatter_add": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr]),
+    "usip_groupmax_bwd_apply": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                        c_int, c_int, c_int, c_ptr]),
+    "usip_group_sum": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_ptr]),
+    "usip_seg_sum": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr]),
+    "usip_unpool_scatter": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_ptr]),
+    "usip_knn_combine_bwd": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr]),
+    "usip_colsum": (c_int, [c_ptr, c_int, c_ptr, c_int, c_int, c_ptr]),
+    "usip_head_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_ptr]),
+    "usip_wgrad": (c_int, [c_ptr, c_int, c_ptr, c_int, c_ptr, c_ptr, c_int, c_ptr, c_int, c_int, c_int, c_int, c_ptr]),
 }
 
 _lib = None

@@ -1,0 +1,501 @@
+// backward.cu -- backward pass of the fused detector / descriptor plan.
+//
+// Autograd of the reference graph (models/networks.py:75-162, models/layers.py) re-derived for the fused
+// forward plan: train-mode BatchNorm backward is "reduce (sum g, sum g*xhat) -> finalize -> apply", the dgrad
+// GEMMs reuse usip_layer_fwd with a transposed weight view, the wgrad GEMMs reduce over the row dimension
+// with the same register-tiled micro-kernel as the forward SIMT path, and every gather of the forward
+// (arg-max pooling, un-pooling, kNN grouping, group max) has its scatter here.
+#include "common.cuh"
+
+namespace usip {
+
+constexpr int BW_ROWS = 128;      // rows per reduction tile (same as the forward stat tile)
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm(+ReLU) backward, phase 1: per-tile partial sums of g_z and g_z * xhat,
+// g_z = g * 1[scale*y+shift > 0].  CTA = 128 rows x CW channels (CW = min(C,128)).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                     float* __restrict__ part, int P, int C) {
+  __shared__ float red[2][32][132];
+  const int CW = min(C, 128), c4n = CW / 4, rsn = 256 / c4n;
+  const int tile = blockIdx.x, cb = blockIdx.y * 128;
+  const int c4 = threadIdx.x % c4n, rs = threadIdx.x / c4n;
+  const int c = cb + c4 * 4;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  if (c < C) {
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+    const int rend = min(P, (tile + 1) * BW_ROWS);
+    for (int r = tile * BW_ROWS + rs; r < rend; r += rsn) {
+      const float4 g4 = *reinterpret_cast<const float4*>(G + (size_t)r * ldg + c);
+      const float4 y4 = *reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c);
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf(yv[j], scv[j], shv[j]);
+        const float gz = (!relu || z > 0.f) ? gv[j] : 0.f;
+        s1[j] += gz; s2[j] = fmaf(gz, (yv[j] - muv[j]) * isv[j], s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][rs][c4 * 4 + j] = s1[j]; red[1][rs][c4 * 4 + j] = s2[j]; }
+  __syncthreads();
+  if (threadIdx.x < CW && cb + threadIdx.x < C) {
+    float a = 0.f, b = 0.f;
+    for (int t = 0; t < rsn; ++t) { a += red[0][t][threadIdx.x]; b += red[1][t][threadIdx.x]; }
+    part[((size_t)tile * 2 + 0) * C + cb + threadIdx.x] = a;
+    part[((size_t)tile * 2 + 1) * C + cb + threadIdx.x] = b;
+  }
+}
+
+// phase 2: reduce partials (double, fixed order) -> g_gamma = sum g_z*xhat, g_beta = sum g_z, c1 = g_beta/n, c2 = g_gamma/n
+__global__ void __launch_bounds__(1024)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int C, float* __restrict__ g_gamma,
+                       float* __restrict__ g_beta, float* __restrict__ c1, float* __restrict__ c2, int accumulate) {
+  __shared__ double sh[2][32][33];
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C)
+    for (int t = sl; t < ntiles; t += 32) {
+      a += (double)part[((size_t)t * 2 + 0) * C + c];
+      b += (double)part[((size_t)t * 2 + 1) * C + c];
+    }
+  sh[0][sl][cl] = a; sh[1][sl][cl] = b;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    double A = 0.0, B = 0.0;
+    for (int t = 0; t < 32; ++t) { A += sh[0][t][cl]; B += sh[1][t][cl]; }
+    if (g_beta) g_beta[c] = (accumulate ? g_beta[c] : 0.f) + (float)A;
+    if (g_gamma) g_gamma[c] = (accumulate ? g_gamma[c] : 0.f) + (float)B;
+    c1[c] = (float)(A / count); c2[c] = (float)(B / count);
+  }
+}
+
+// phase 3: g_y = scale * (g_z - c1 - xhat*c2)            (scale = gamma*invstd)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
+                    int relu, float* __restrict__ GY, int ldo, int P, int C) {
+  const int c4n = C / 4;
+  const size_t total = (size_t)P * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i - (size_t)r * c4n) * 4;
+    const float4 g4 = *reinterpret_cast<const float4*>(G + (size_t)r * ldg + c);
+    const float4 y4 = *reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sc = scale[c + j];
+      const float z = fmaf(yv[j], sc, shift[c + j]);
+      const float gz = (!relu || z > 0.f) ? gv[j] : 0.f;
+      o[j] = sc * (gz - c1[c + j] - (yv[j] - mean[c + j]) * invstd[c + j] * c2[c + j]);
+    }
+    *reinterpret_cast<float4*>(GY + (size_t)r * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group-max layers: out[q,c] = relu(scale*ysel+shift), ysel = (scale>=0 ? gmax : gmin)[q,c] at row arg.
+//   select : gz[q,c] = g_out[q,c]*1[z>0], argsel[q,c]; partial sums of gz and gz*xhat(ysel) over q tiles
+//   scatter: G[(q*K+argsel), c] += gz_or_g[q,c]            (max path joins a dense gradient)
+//   apply  : g_y[(q,k),c] = scale*( (k==argsel)*gz - c1 - xhat*c2 )   (max is the ONLY consumer)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+groupmax_bwd_select_kernel(const float* __restrict__ Gout, int ldg, const float* __restrict__ gmax,
+                           const float* __restrict__ gmin, const int32_t* __restrict__ amax,
+                           const int32_t* __restrict__ amin, const float* __restrict__ scale,
+                           const float* __restrict__ shift, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, float* __restrict__ gz, int32_t* __restrict__ argsel,
+                           float* __restrict__ part, int Q, int C) {
+  // CTA = 128 q-rows x 128 channels, thread = (row slice, channel)
+  __shared__ float red[2][2][128];
+  const int tile = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), rs = threadIdx.x >> 7;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    const float sc = scale[c], sh = shift[c], mu = mean ? mean[c] : 0.f, is = invstd ? invstd[c] : 0.f;
+    const int qend = min(Q, (tile + 1) * BW_ROWS);
+    for (int q = tile * BW_ROWS + rs; q < qend; q += 2) {
+      const size_t i = (size_t)q * C + c;
+      const bool up = sc >= 0.f;
+      const float ys = up ? gmax[i] : gmin[i];
+      const float z = fmaf(ys, sc, sh);
+      const float g = z > 0.f ? Gout[(size_t)q * ldg + c] : 0.f;
+      gz[i] = g; argsel[i] = up ? amax[i] : amin[i];
+      s1 += g; s2 = fmaf(g, (ys - mu) * is, s2);
+    }
+  }
+  red[0][rs][threadIdx.x & 127] = s1; red[1][rs][threadIdx.x & 127] = s2;
+  __syncthreads();
+  if (part && threadIdx.x < 128 && c < C) {
+    part[((size_t)tile * 2 + 0) * C + c] = red[0][0][threadIdx.x] + red[0][1][threadIdx.x];
+    part[((size_t)tile * 2 + 1) * C + c] = red[1][0][threadIdx.x] + red[1][1][threadIdx.x];
+  }
+}
+
+__global__ void groupmax_scatter_add_kernel(float* __restrict__ G, int ldg, const float* __restrict__ gsrc,
+                                            const int32_t* __restrict__ argsel, int K, int Q, int C) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Q * C) return;
+  int q = (int)(i / C), c = (int)(i - (size_t)q * C);
+  G[((size_t)q * K + argsel[i]) * ldg + c] += gsrc[i];        // unique target per (q,c): no atomics needed
+}
+
+__global__ void __launch_bounds__(256)
+groupmax_bwd_apply_kernel(const float* __restrict__ Y, int ldy, const float* __restrict__ gz,
+                          const int32_t* __restrict__ argsel, const float* __restrict__ scale,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const float* __restrict__ c1, const float* __restrict__ c2, float* __restrict__ GY, int ldo,
+                          int K, int P, int C) {
+  const int c4n = C / 4;
+  const size_t total = (size_t)P * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i - (size_t)r * c4n) * 4;
+    const int q = r / K, k = r - q * K;
+    const float4 y4 = *reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(gz + (size_t)q * C + c);
+    const int4 a4 = *reinterpret_cast<const int4*>(argsel + (size_t)q * C + c);
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+    const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = (av[j] == k) ? gv[j] : 0.f;
+      o[j] = scale[c + j] * (g - c1[c + j] - (yv[j] - mean[c + j]) * invstd[c + j] * c2[c + j]);
+    }
+    *reinterpret_cast<float4*>(GY + (size_t)r * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// out[q,c] = sum_k G[(q*K+k), c]
+__global__ void group_sum_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out, int ldo, int K, int Q,
+                                 int C) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C / 4;
+  if (i >= (size_t)Q * c4n) return;
+  int q = (int)(i / c4n), c = (int)(i - (size_t)q * c4n) * 4;
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int k = 0; k < K; ++k) {
+    float4 v = *reinterpret_cast<const float4*>(G + ((size_t)q * K + k) * ldg + c);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)q * ldo + c) = s;
+}
+
+// out[seg,c] = sum over the contiguous rows of the segment (warp per segment)
+__global__ void __launch_bounds__(256)
+seg_sum_kernel(const float* __restrict__ G, int ldg, const int32_t* __restrict__ seg_off, float* __restrict__ out,
+               int ldo, int B, int N, int M, int C) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * M) return;
+  const int b = w / M, m = w - b * M;
+  const int s = seg_off[(size_t)b * (M + 1) + m], e = seg_off[(size_t)b * (M + 1) + m + 1];
+  for (int c4 = lane; c4 * 4 < C; c4 += 32) {
+    float4 a = make_float4(0, 0, 0, 0);
+    for (int r = s; r < e; ++r) {
+      float4 v = *reinterpret_cast<const float4*>(G + ((size_t)b * N + r) * ldg + c4 * 4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)w * ldo + c4 * 4) = a;
+  }
+}
+
+// arg-max un-pooling: G[arg[q,c], c] (+)= gp[q,c]; arg = global row or -1 (empty node)
+__global__ void unpool_scatter_kernel(float* __restrict__ G, int ldg, const float* __restrict__ gp, int ldp,
+                                      const int32_t* __restrict__ arg, int Q, int C, int accumulate) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Q * C) return;
+  int q = (int)(i / C), c = (int)(i - (size_t)q * C);
+  int r = arg[i];
+  if (r < 0) return;
+  float v = gp[(size_t)q * ldp + c];
+  float* dst = G + (size_t)r * ldg + c;
+  *dst = accumulate ? *dst + v : v;                          // targets are unique per (q,c)
+}
+
+// backward of usip_knn_combine: G_Z[b*M+nbr] += GY[row]; gWxyz[c,0..2] += GY[row,c]*delta
+__global__ void __launch_bounds__(256)
+knn_combine_bwd_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__ pts,
+                       const int32_t* __restrict__ knn_idx, float* __restrict__ GZ, int ldz, float* __restrict__ gW,
+                       int ldw, int B, int M, int K, int C) {
+  extern __shared__ float sw[];                              // [C][3]
+  for (int i = threadIdx.x; i < C * 3; i += 256) sw[i] = 0.f;
+  __syncthreads();
+  const int row0 = blockIdx.x * BW_ROWS, G = B * M * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c4 = lane; c4 * 4 < C; c4 += 32) {
+    float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    for (int r = row0 + warp; r < min(row0 + BW_ROWS, G); r += 8) {
+      const int q = r / K, b = q / M, m = q - b * M, j = knn_idx[r];
+      const float* p = pts + (size_t)b * 3 * M;
+      const float dx = p[j] - p[m], dy = p[M + j] - p[M + m], dz = p[2 * M + j] - p[2 * M + m];
+      const float4 g = *reinterpret_cast<const float4*>(GY + (size_t)r * ldg + c4 * 4);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
+      float* z = GZ + ((size_t)b * M + j) * ldz + c4 * 4;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        atomicAdd(z + t, gv[t]);
+        a0[t] = fmaf(gv[t], dx, a0[t]); a1[t] = fmaf(gv[t], dy, a1[t]); a2[t] = fmaf(gv[t], dz, a2[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      atomicAdd(&sw[(c4 * 4 + t) * 3 + 0], a0[t]); atomicAdd(&sw[(c4 * 4 + t) * 3 + 1], a1[t]);
+      atomicAdd(&sw[(c4 * 4 + t) * 3 + 2], a2[t]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 3; i += 256) atomicAdd(&gW[(size_t)(i / 3) * ldw + (i % 3)], sw[i]);
+}
+
+// column sums: out[c] (+)= sum_r G[r,c]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out, int P, int C) {
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.x * 1024, r1 = min(P, r0 + 1024);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += G[(size_t)r * ldg + c];
+  atomicAdd(out + c, s);
+}
+
+// networks.py:151-154 backward: G_out4[q,0:3] = g_kp, G_out4[q,3] = g_sig * sigmoid(x)
+__global__ void head_bwd_kernel(const float* __restrict__ g_kp, const float* __restrict__ g_sig,
+                                const float* __restrict__ out4, int ld, float* __restrict__ G, int B, int M) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * M) return;
+  int b = t / M, m = t - b * M;
+  float4 o;
+  o.x = g_kp ? g_kp[(size_t)b * 3 * M + m] : 0.f;
+  o.y = g_kp ? g_kp[(size_t)b * 3 * M + M + m] : 0.f;
+  o.z = g_kp ? g_kp[(size_t)b * 3 * M + 2 * M + m] : 0.f;
+  float x = out4[(size_t)t * ld + 3];
+  float ds = x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
+  o.w = g_sig ? g_sig[t] * ds : 0.f;
+  *reinterpret_cast<float4*>(G + (size_t)t * 4) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad: gW[Cout,Cin] += GY[P,Cout]^T * act(X)[P,Cin]   (split over row ranges, atomic accumulation)
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_BK = 16;
+constexpr int WG_LD = 128 + 4;
+
+__global__ void __launch_bounds__(256, 2)
+wgrad_simt_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__ X, int ldx,
+                  const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu,
+                  float* __restrict__ gW, int ldw, int P, int Cout, int Cin, int rows_per_cta) {
+  __shared__ __align__(16) float As[2][WG_BK][WG_LD];
+  __shared__ __align__(16) float Bs[2][WG_BK][WG_LD];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.z * 128;       // m: Cout index, n: Cin index
+  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(P, r_begin + rows_per_cta);
+  const int lk = tid >> 5, l4 = tid & 31;                        // row-in-chunk (0..7, +8), float4 column
+  const bool a_vec = ((ldg & 3) == 0) && ((reinterpret_cast<uintptr_t>(GY) & 15) == 0);
+  const bool b_vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+  const int bc = n0 + l4 * 4;
+  if (in_scale) {
+    float s[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] = bc + j < Cin ? in_scale[bc + j] : 0.f; h[j] = bc + j < Cin ? in_shift[bc + j] : 0.f; }
+    sc = make_float4(s[0], s[1], s[2], s[3]); sh = make_float4(h[0], h[1], h[2], h[3]);
+  }
+  float4 ar[2], br[2];
+  auto load = [&](int r0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + lk + 8 * h;
+      const int ac = m0 + l4 * 4;
+      float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+      if (r < r_end) {
+        if (a_vec && ac + 4 <= Cout) { float4 v = *reinterpret_cast<const float4*>(GY + (size_t)r * ldg + ac); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+        else { for (int j = 0; j < 4; ++j) if (ac + j < Cout) a[j] = GY[(size_t)r * ldg + ac + j]; }
+        if (b_vec && bc + 4 <= Cin) { float4 v = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + bc); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
+        else { for (int j = 0; j < 4; ++j) if (bc + j < Cin) b[j] = X[(size_t)r * ldx + bc + j]; }
+        if (in_scale) { b[0] = fmaf(b[0], sc.x, sh.x); b[1] = fmaf(b[1], sc.y, sh.y); b[2] = fmaf(b[2], sc.z, sh.z); b[3] = fmaf(b[3], sc.w, sh.w); }
+        if (in_relu) { b[0] = fmaxf(b[0], 0.f); b[1] = fmaxf(b[1], 0.f); b[2] = fmaxf(b[2], 0.f); b[3] = fmaxf(b[3], 0.f); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (bc + j >= Cin) b[j] = 0.f;
+      }
+      ar[h] = make_float4(a[0], a[1], a[2], a[3]); br[h] = make_float4(b[0], b[1], b[2], b[3]);
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(&As[buf][lk + 8 * h][l4 * 4]) = ar[h];
+      *reinterpret_cast<float4*>(&Bs[buf][lk + 8 * h][l4 * 4]) = br[h];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  const int nchunks = (r_end - r_begin + WG_BK - 1) / WG_BK;
+  if (nchunks <= 0) return;
+  load(r_begin); store(0);
+  __syncthreads();
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) load(r_begin + (ch + 1) * WG_BK);
+#pragma unroll
+    for (int k = 0; k < WG_BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (ch + 1 < nchunks) store(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < Cin) atomicAdd(gW + (size_t)m * ldw + n, acc[i][j]);
+    }
+  }
+}
+
+}  // namespace usip
+
+using namespace usip;
+
+extern "C" int usip_bn_bwd_reduce(const float* G, int ldg, const float* Y, int ldy, const float* scale,
+                                  const float* shift, const float* mean, const float* invstd, int relu,
+                                  float* part, int P, int C, void* stream) {
+  USIP_REQUIRE(G && Y && scale && shift && mean && invstd && part && C % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 &&
+               (C <= 128 ? (128 % C == 0 || C % 4 == 0) : C % 128 == 0), "bn_bwd_reduce: bad args");
+  USIP_REQUIRE(C >= 32, "bn_bwd_reduce: C must be >= 32");
+  dim3 grid(cdiv(P, BW_ROWS), cdiv(C, 128));
+  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, relu, part, P, C);
+  return check_launch("bn_bwd_reduce_kernel");
+}
+
+extern "C" int usip_bn_bwd_finalize(const float* part, int ntiles, int64_t count, int C, float* g_gamma, float* g_beta,
+                                    float* c1, float* c2, int accumulate, void* stream) {
+  USIP_REQUIRE(part && c1 && c2 && ntiles > 0, "bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(part, ntiles, (double)count, C, g_gamma, g_beta,
+                                                                         c1, c2, accumulate);
+  return check_launch("bn_bwd_finalize_kernel");
+}
+
+extern "C" int usip_bn_bwd_apply(const float* G, int ldg, const float* Y, int ldy, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, const float* c1, const float* c2, int relu,
+                                 float* GY, int ldo, int P, int C, void* stream) {
+  USIP_REQUIRE(G && Y && GY && C % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0, "bn_bwd_apply: bad args");
+  size_t total = (size_t)P * (C / 4);
+  int blocks = (int)min((size_t)148 * 16, cdiv64(total, 256));
+  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, c1, c2, relu,
+                                                                GY, ldo, P, C);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
+extern "C" int usip_groupmax_bwd_select(const float* Gout, int ldg, const float* gmax, const float* gmin,
+                                        const int32_t* amax, const int32_t* amin, const float* scale,
+                                        const float* shift, const float* mean, const float* invstd, float* gz,
+                                        int32_t* argsel, float* part, int Q, int C, void* stream) {
+  USIP_REQUIRE(Gout && gmax && gmin && amax && amin && scale && shift && gz && argsel, "groupmax_bwd_select: bad args");
+  dim3 grid(cdiv(Q, BW_ROWS), cdiv(C, 128));
+  groupmax_bwd_select_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Gout, ldg, gmax, gmin, amax, amin, scale, shift, mean,
+                                                                     invstd, gz, argsel, part, Q, C);
+  return check_launch("groupmax_bwd_select_kernel");
+}
+
+extern "C" int usip_groupmax_scatter_add(float* G, int ldg, const float* gsrc, const int32_t* argsel, int K, int Q,
+                                         int C, void* stream) {
+  USIP_REQUIRE(G && gsrc && argsel, "groupmax_scatter_add: bad args");
+  size_t n = (size_t)Q * C;
+  groupmax_scatter_add_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(G, ldg, gsrc, argsel, K, Q, C);
+  return check_launch("groupmax_scatter_add_kernel");
+}
+
+extern "C" int usip_groupmax_bwd_apply(const float* Y, int ldy, const float* gz, const int32_t* argsel,
+                                       const float* scale, const float* mean, const float* invstd, const float* c1,
+                                       const float* c2, float* GY, int ldo, int K, int P, int C, void* stream) {
+  USIP_REQUIRE(Y && gz && argsel && GY && C % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0, "groupmax_bwd_apply: bad args");
+  size_t total = (size_t)P * (C / 4);
+  int blocks = (int)min((size_t)148 * 16, cdiv64(total, 256));
+  groupmax_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y, ldy, gz, argsel, scale, mean, invstd, c1, c2, GY,
+                                                                      ldo, K, P, C);
+  return check_launch("groupmax_bwd_apply_kernel");
+}
+
+extern "C" int usip_group_sum(const float* G, int ldg, float* out, int ldo, int K, int Q, int C, void* stream) {
+  USIP_REQUIRE(G && out && C % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0, "group_sum: bad args");
+  size_t n = (size_t)Q * (C / 4);
+  group_sum_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(G, ldg, out, ldo, K, Q, C);
+  return check_launch("group_sum_kernel");
+}
+
+extern "C" int usip_seg_sum(const float* G, int ldg, const int32_t* seg_off, float* out, int ldo, int B, int N, int M,
+                            int C, void* stream) {
+  USIP_REQUIRE(G && seg_off && out && C % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0, "seg_sum: bad args");
+  seg_sum_kernel<<<cdiv(B * M * 32, 256), 256, 0, (cudaStream_t)stream>>>(G, ldg, seg_off, out, ldo, B, N, M, C);
+  return check_launch("seg_sum_kernel");
+}
+
+extern "C" int usip_unpool_scatter(float* G, int ldg, const float* gp, int ldp, const int32_t* arg, int Q, int C,
+                                   int accumulate, void* stream) {
+  USIP_REQUIRE(G && gp && arg, "unpool_scatter: bad args");
+  size_t n = (size_t)Q * C;
+  unpool_scatter_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(G, ldg, gp, ldp, arg, Q, C, accumulate);
+  return check_launch("unpool_scatter_kernel");
+}
+
+extern "C" int usip_knn_combine_bwd(const float* GY, int ldg, const float* pts, const int32_t* knn_idx, float* GZ,
+                                    int ldz, float* gW, int ldw, int B, int M, int K, int C, void* stream) {
+  USIP_REQUIRE(GY && pts && knn_idx && GZ && gW && C % 4 == 0 && ldg % 4 == 0, "knn_combine_bwd: bad args");
+  int G = B * M * K;
+  knn_combine_bwd_kernel<<<cdiv(G, BW_ROWS), 256, (size_t)C * 3 * sizeof(float), (cudaStream_t)stream>>>(
+      GY, ldg, pts, knn_idx, GZ, ldz, gW, ldw, B, M, K, C);
+  return check_launch("knn_combine_bwd_kernel");
+}
+
+extern "C" int usip_colsum(const float* G, int ldg, float* out, int P, int C, void* stream) {
+  USIP_REQUIRE(G && out, "colsum: bad args");
+  dim3 grid(cdiv(P, 1024), cdiv(C, 256));
+  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, out, P, C);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int usip_head_bwd(const float* g_kp, const float* g_sig, const float* out4, int ld, float* G, int B, int M,
+                             void* stream) {
+  USIP_REQUIRE(out4 && G, "head_bwd: bad args");
+  head_bwd_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(g_kp, g_sig, out4, ld, G, B, M);
+  return check_launch("head_bwd_kernel");
+}
+
+extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale,
+                          const float* in_shift, int in_relu, float* gW, int ldw, int P, int Cout, int Cin,
+                          void* stream) {
+  USIP_REQUIRE(GY && X && gW && P > 0 && Cout > 0 && Cin > 0 && (!in_scale == !in_shift), "wgrad: bad args");
+  const int tiles = cdiv(Cout, 128) * cdiv(Cin, 128);
+  int splits = max(1, min(cdiv(P, 128), (148 * 4) / tiles));
+  int rows = cdiv(cdiv(P, splits), WG_BK) * WG_BK;
+  splits = cdiv(P, rows);
+  dim3 grid(splits, cdiv(Cout, 128), cdiv(Cin, 128));
+  wgrad_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout,
+                                                            Cin, rows);
+  return check_launch("wgrad_simt_kernel");
+}

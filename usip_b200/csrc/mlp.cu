@@ -54,8 +54,8 @@ layer_fwd_simt_kernel(const usip_layer_desc d) {
   constexpr int BKW = L_BK / BKH;                          // k per thread: 8 / 4
   const int b_n = tid % BN, b_kh = tid / BN;
   const bool b_row_ok = (n0 + b_n) < Cout;
-  const float* b_ptr = d.W + (size_t)(n0 + b_n) * d.ldw;
-  const bool b_vec = ((d.ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
+  const float* b_ptr = d.w_transposed ? d.W + (n0 + b_n) : d.W + (size_t)(n0 + b_n) * d.ldw;
+  const bool b_vec = !d.w_transposed && ((d.ldw & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
   const bool has_affine = d.in_scale != nullptr;
 
   float a_reg[8], b_reg[BKW];
@@ -93,7 +93,8 @@ layer_fwd_simt_kernel(const usip_layer_desc d) {
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < BKW; ++j) b_reg[j] = (b_row_ok && kb + j < Cin) ? b_ptr[kb + j] : 0.f;
+      for (int j = 0; j < BKW; ++j)
+        b_reg[j] = (b_row_ok && kb + j < Cin) ? (d.w_transposed ? b_ptr[(size_t)(kb + j) * d.ldw] : b_ptr[kb + j]) : 0.f;
     }
   };
   auto store_tile = [&](int buf) {
@@ -403,7 +404,8 @@ extern "C" int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout) { return (in
 extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
   USIP_REQUIRE(dp, "layer_fwd: null desc");
   const usip_layer_desc& d = *dp;
-  USIP_REQUIRE(d.X && d.W && d.P > 0 && d.Cin > 0 && d.Cout > 0 && d.ldx >= d.Cin && d.ldw >= d.Cin, "layer_fwd: bad args");
+  USIP_REQUIRE(d.X && d.W && d.P > 0 && d.Cin > 0 && d.Cout > 0 && d.ldx >= d.Cin &&
+               d.ldw >= (d.w_transposed ? d.Cout : d.Cin), "layer_fwd: bad args");
   USIP_REQUIRE(!d.Y || d.ldy >= d.Cout, "layer_fwd: bad ldy");
   USIP_REQUIRE(!d.in_scale == !d.in_shift, "layer_fwd: in_scale/in_shift must come together");
   if (d.gmax || d.gmin) {

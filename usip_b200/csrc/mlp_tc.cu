@@ -141,7 +141,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk): [hi | lo] blocks of BN x 128 B,
 // already 128B-swizzled, so a tile is one contiguous bulk copy.
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int Cout, int Cin, int BN,
+__global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int transposed, int Cout, int Cin, int BN,
                                        uint32_t* __restrict__ out) {
   const int KC = Cin / TC_BK;
   const int total = Cout * (Cin / 4);                 // one thread per 16-byte chunk
@@ -150,10 +150,12 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int
   const int n = t / (Cin / 4), k4 = t - n * (Cin / 4);
   const int kc = k4 / 8, c = k4 & 7;                  // chunk c of K chunk kc
   const int nt = n / BN, r = n - nt * BN;
-  const float* src = W + (size_t)n * ldw + k4 * 4;
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) split_tf32(src[j], hi[j], lo[j]);
+  for (int j = 0; j < 4; ++j) {
+    const float w = transposed ? W[(size_t)(k4 * 4 + j) * ldw + n] : W[(size_t)n * ldw + k4 * 4 + j];
+    split_tf32(w, hi[j], lo[j]);
+  }
   const size_t blk = ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;     // in 32-bit words
   const size_t off = (size_t)r * TC_BK + (size_t)((c ^ (r & 7)) * 4);
   *reinterpret_cast<uint4*>(out + blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -166,7 +168,7 @@ struct TcSmem {
   static constexpr int A_STAGE = 2 * TC_BM * 128;                 // hi + lo
   static constexpr int B_STAGE = 2 * BN * 128;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int TRANS = TC_EPI_WARPS * 32 * 33 * 4;       // per-warp 32x33 transpose tile
+  static constexpr int TRANS = TC_EPI_WARPS * 32 * 36 * 4;       // per-warp 32x36 transpose tile (16B-aligned rows)
   static constexpr int COMB = (BN <= 128 ? 6 : 2) * TC_EPI_WARPS * BN * 4;   // sum, sumsq (+ max, min, args for group > 32)
   static constexpr int BARS = 256;
   static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + BARS + 1024;   // +1024 alignment slack
@@ -305,7 +307,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   } else {
     // =============================== epilogue warps 0..3 ========================================
     const int q = warp;                               // TMEM lane quarter
-    float* tw = trans + q * (32 * 33);
+    float* tw = trans + q * (32 * 36);
     const int g = d.group;
     const bool want_stats = d.stat_partial != nullptr;
     const bool want_grp = (d.gmax != nullptr) || (d.gmin != nullptr);
@@ -345,23 +347,31 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
             v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
           }
         }
-        if (d.Y && rok) {
-          float* yp = d.Y + (size_t)row * d.ldy + cb;
+        // stage the 32x32 chunk in shared memory (conflict-free 128-bit stores, row stride 36 floats)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(tw + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        if (d.Y) {
+          // coalesced stores: 8 lanes cover one 128-byte row segment, a warp instruction writes 4 full lines
+          const int l8 = lane & 7, rsub = lane >> 3;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + rsub;
+            if (r < nvalid) {
+              const float4 o = *reinterpret_cast<const float4*>(tw + r * 36 + l8 * 4);
+              *reinterpret_cast<float4*>(d.Y + (size_t)(wrow0 + r) * d.ldy + cb + l8 * 4) = o;
+            }
+          }
         }
         if (want_stats || want_grp) {
-          // transpose through shared memory: afterwards lane j owns column cb + j of this warp's 32 rows
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tw[lane * 33 + j] = v[j];
-          __syncwarp();
           float s = 0.f, ss = 0.f;
           float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
           int ax0 = 0, an0 = 0, ax1 = 0, an1 = 0;
           const int half = (g == 16) ? 16 : 32;       // rows per in-warp group segment
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const float x = tw[r * 33 + lane];
+            const float x = tw[r * 36 + lane];
             const bool ok = r < nvalid;
             if (ok) { s += x; ss = fmaf(x, x, ss); }
             if (r < half) {
@@ -372,7 +382,6 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
               if (ok && x < mn1) { mn1 = x; an1 = r; }
             }
           }
-          __syncwarp();
           const int cl = ch * 32 + lane;              // column inside the tile
           if (want_stats) { comb[(0 * 4 + q) * BN + cl] = s; comb[(1 * 4 + q) * BN + cl] = ss; }
           if (want_grp) {
@@ -405,6 +414,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
             }
           }
         }
+        __syncwarp();                                   // tw is rewritten by the next chunk
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -488,7 +498,7 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {
     const int total = d.Cout * (d.Cin / 4);
-    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.Cout, d.Cin, BN, wpack);
+    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.w_transposed, d.Cout, d.Cin, BN, wpack);
     int e = check_launch("tc_pack_weights_kernel");
     if (e) return e;
   }

@@ -153,6 +153,10 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     keep=True."""
     opt = net.opt
     assert opt.k == 1, "only k=1 is supported (every shipped config; networks.py:91-92)"
+    if keep and not net.training:
+        raise NotImplementedError("gradients through eval-mode BatchNorm are not part of the hot path "
+                                  "(the reference only back-propagates in train mode, keypoint_detector.py:170)")
+    assert len(net.knnlayer_1.layers_before) >= 2 and len(net.knnlayer_1.layers_after) >= 2
     dev = x.device
     Bp, _, N = x.shape
     M = node.shape[2]
@@ -236,7 +240,7 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
         last = li == len(ka) - 1
         Yn, bnn, grp = R.run(YA, G, _w2d(ka[li].conv.weight), ka[li].conv.bias.detach(), ka[li].norm,
                              _bn_mom(ka[li].norm, epoch), prev=prevA, group=Kn, want_group=last, want_arg=last and keep,
-                             write_y=not last, name="knn_a%d" % li)
+                             write_y=(not last) or keep, name="knn_a%d" % li)
         prevA, YA = bnn, Yn
         saved_after.append((Yn, bnn))
         grp_a = grp if last else grp_a
@@ -273,8 +277,200 @@ def chamfer_prob_forward(src, dst, sig_src, sig_dst):
     return out3, (d_sd, i_sd, d_ds, i_ds)
 
 
+class _Bwd:
+    """Small helper bundle for the backward plans: raw C-ABI calls + gradient bookkeeping."""
+
+    def __init__(self, net, dev, use_tc):
+        from . import _lib
+        self.lib = _lib.load()
+        self.check = _lib.check
+        self.dev = dev
+        self.use_tc = use_tc
+        self.grads = {p: torch.zeros_like(p, memory_format=torch.contiguous_format) for p in net.parameters()}
+
+    def g2d(self, w):
+        g = self.grads[w]
+        return g.view(g.shape[0], -1)
+
+    def bn_bwd(self, G, Y, st, norm, P, C, relu=True, name="bn_bwd"):
+        """g_y of a train-mode BN(+ReLU) layer; writes g_gamma / g_beta; returns GY [P,C] (new buffer)."""
+        nt = (P + 127) // 128
+        part = torch.empty((nt, 2, C), dtype=f32, device=self.dev)
+        c1 = torch.empty(C, dtype=f32, device=self.dev); c2 = torch.empty(C, dtype=f32, device=self.dev)
+        GY = torch.empty((P, C), dtype=f32, device=self.dev)
+        s = ops._stream(); p = ops._p
+        with _Prof(name, nbytes=4.0 * P * C * 5):
+            self.check(self.lib.usip_bn_bwd_reduce(p(G), G.stride(0), p(Y), Y.stride(0), p(st.scale), p(st.shift), p(st.mean),
+                                                   p(st.invstd), 1 if relu else 0, p(part), P, C, s), "usip_bn_bwd_reduce")
+            self.check(self.lib.usip_bn_bwd_finalize(p(part), nt, P, C, p(self.grads[norm.weight]), p(self.grads[norm.bias]),
+                                                     p(c1), p(c2), 0, s), "usip_bn_bwd_finalize")
+            self.check(self.lib.usip_bn_bwd_apply(p(G), G.stride(0), p(Y), Y.stride(0), p(st.scale), p(st.shift), p(st.mean),
+                                                  p(st.invstd), p(c1), p(c2), 1 if relu else 0, p(GY), GY.stride(0), P, C, s),
+                       "usip_bn_bwd_apply")
+        return GY
+
+    def wgrad(self, GY, X, gW, P, Cout, Cin, prev=None, relu=False, name="wgrad"):
+        s = ops._stream(); p = ops._p
+        with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout, precision="fp32 SIMT"):
+            self.check(self.lib.usip_wgrad(p(GY), GY.stride(0), p(X), X.stride(0), None if prev is None else p(prev.scale),
+                                           None if prev is None else p(prev.shift), 1 if (relu or prev is not None) else 0,
+                                           p(gW), gW.stride(0), P, Cout, Cin, s), "usip_wgrad")
+
+    def dgrad(self, GY, W2d, P, name="dgrad", out=None):
+        """G_in[P,Cin] = GY[P,Cout] @ W2d[Cout,Cin] (the forward weight, used transposed by the layer kernel)."""
+        Cout, Cin = W2d.shape
+        if out is None:
+            out = torch.empty((P, Cin), dtype=f32, device=self.dev)
+        prec = _precision_for(P, Cout, Cin, self.use_tc)
+        with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
+                   precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
+            ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True)
+        return out
+
+    def colsum(self, G, out, P, C):
+        self.check(self.lib.usip_colsum(ops._p(G), G.stride(0), ops._p(out), P, C, ops._stream()), "usip_colsum")
+
+
 def detector_backward(net, ctx, g_kp, g_sig):
-    raise NotImplementedError("detector backward plan not built yet")
+    """Backward of detector_forward.  Returns the gradients of net.parameters() in order."""
+    dev = ctx["cmean"].device
+    Bp, N, M, Kn = ctx["Bp"], ctx["N"], ctx["M"], ctx["Kn"]
+    H, C1, C2, Cb = ctx["H"], ctx["C1"], ctx["C2"], ctx["Cb"]
+    P, Q = Bp * N, Bp * M
+    G = Q * Kn
+    bw = _Bwd(net, dev, ctx["use_tc"])
+    lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
+    fp, sp = net.first_pointnet.layers, net.second_pointnet.layers
+    kb, ka = net.knnlayer_1.layers_before, net.knnlayer_1.layers_after
+    g_kp = None if g_kp is None else g_kp.contiguous()
+    g_sig = None if g_sig is None else g_sig.contiguous()
+
+    # ---- head (networks.py:143-154)
+    G_OUT = torch.empty((Q, 4), dtype=f32, device=dev)
+    check(lib.usip_head_bwd(p(g_kp), p(g_sig), p(ctx["OUT"]), ctx["OUT"].stride(0), p(G_OUT), Bp, M, s()), "usip_head_bwd")
+    W12 = _w2d(net.mlp3.conv.weight)
+    bw.wgrad(G_OUT, ctx["Y11"], bw.g2d(net.mlp3.conv.weight), Q, 4, W12.shape[1], prev=ctx["bn11"], name="wgrad_mlp3")
+    bw.colsum(G_OUT, bw.grads[net.mlp3.conv.bias], Q, 4)
+    G_a11 = bw.dgrad(G_OUT, W12, Q, name="dgrad_mlp3")
+    GY11 = bw.bn_bwd(G_a11, ctx["Y11"], ctx["bn11"], net.mlp2.norm, Q, G_a11.shape[1])
+    W11 = _w2d(net.mlp2.conv.weight)
+    bw.wgrad(GY11, ctx["Y10"], bw.g2d(net.mlp2.conv.weight), Q, W11.shape[0], W11.shape[1], prev=ctx["bn10"], name="wgrad_mlp2")
+    G_a10 = bw.dgrad(GY11, W11, Q, name="dgrad_mlp2")
+    GY10 = bw.bn_bwd(G_a10, ctx["Y10"], ctx["bn10"], net.mlp1.norm, Q, G_a10.shape[1])
+    W10 = _w2d(net.mlp1.conv.weight)
+    bw.wgrad(GY10, ctx["AGG"], bw.g2d(net.mlp1.conv.weight), Q, W10.shape[0], W10.shape[1], name="wgrad_mlp1")
+    G_AGG = bw.dgrad(GY10, W10, Q, name="dgrad_mlp1")                      # [Q, C1+C2]
+    G_pool2 = G_AGG[:, :C1]
+    G_feat = G_AGG[:, C1:]
+
+    # ---- kNN fusion, layers_after (layers.py:435-438)
+    def groupmax_select(Gout, grp, st, Qn, C, with_stats):
+        gz = torch.empty((Qn, C), dtype=f32, device=dev)
+        argsel = torch.empty((Qn, C), dtype=i32, device=dev)
+        nt = (Qn + 127) // 128
+        part = torch.empty((nt, 2, C), dtype=f32, device=dev) if with_stats else None
+        check(lib.usip_groupmax_bwd_select(p(Gout), Gout.stride(0), p(grp["gmax"]), p(grp["gmin"]), p(grp["amax"]),
+                                           p(grp["amin"]), p(st.scale), p(st.shift), p(st.mean), p(st.invstd), p(gz),
+                                           p(argsel), p(part), Qn, C, s()), "usip_groupmax_bwd_select")
+        return gz, argsel, part, nt
+
+    Ya_last, bna_last = ctx["after"][-1]
+    gz9, arg9, part9, nt9 = groupmax_select(G_feat, ctx["grp_a"], bna_last, Q, C2, True)
+    c1 = torch.empty(C2, dtype=f32, device=dev); c2 = torch.empty(C2, dtype=f32, device=dev)
+    check(lib.usip_bn_bwd_finalize(p(part9), nt9, G, C2, p(bw.grads[ka[-1].norm.weight]), p(bw.grads[ka[-1].norm.bias]),
+                                   p(c1), p(c2), 0, s()), "usip_bn_bwd_finalize")
+    GYa = torch.empty((G, C2), dtype=f32, device=dev)
+    with _Prof("groupmax_bwd_apply", nbytes=8.0 * G * C2):
+        check(lib.usip_groupmax_bwd_apply(p(Ya_last), Ya_last.stride(0), p(gz9), p(arg9), p(bna_last.scale), p(bna_last.mean),
+                                          p(bna_last.invstd), p(c1), p(c2), p(GYa), GYa.stride(0), Kn, G, C2, s()),
+              "usip_groupmax_bwd_apply")
+    # remaining after-layers, last -> first (li >= 1: plain BN+ReLU chains)
+    for li in range(len(ka) - 1, 0, -1):
+        Wl = _w2d(ka[li].conv.weight)
+        Yin, bnin = ctx["after"][li - 1]
+        bw.wgrad(GYa, Yin, bw.g2d(ka[li].conv.weight), G, Wl.shape[0], Wl.shape[1], prev=bnin, name="wgrad_knn_a%d" % li)
+        G_in = bw.dgrad(GYa, Wl, G, name="dgrad_knn_a%d" % li)
+        GYa = bw.bn_bwd(G_in, Yin, bnin, ka[li - 1].norm, G, G_in.shape[1], name="bn_bwd_knn_a%d" % (li - 1))
+        del G_in
+    # ka[0]: Y8 = a7 Wnb^T + U[row/K] + b, U = amax Wmax^T
+    W8 = _w2d(ka[0].conv.weight)
+    Yb_last, bnb_last = ctx["before"][-1]
+    gW8 = bw.g2d(ka[0].conv.weight)
+    bw.wgrad(GYa, Yb_last, gW8[:, Cb:], G, C2, Cb, prev=bnb_last, name="wgrad_knn_a0")
+    G_a7 = bw.dgrad(GYa, W8[:, Cb:], G, name="dgrad_knn_a0")               # [G, Cb]
+    G_U = torch.empty((Q, C2), dtype=f32, device=dev)
+    check(lib.usip_group_sum(p(GYa), GYa.stride(0), p(G_U), G_U.stride(0), Kn, Q, C2, s()), "usip_group_sum")
+    del GYa
+    bw.wgrad(G_U, ctx["amax"], gW8[:, :Cb], Q, C2, Cb, name="wgrad_knn_a0_node")
+    G_amax = bw.dgrad(G_U, W8[:, :Cb], Q, name="dgrad_knn_a0_node")        # [Q, Cb]
+    # max path joins the dense gradient of a7 at the arg rows (ReLU mask is applied by bn_bwd below)
+    _, arg7, _, _ = groupmax_select(G_amax, ctx["grp_b"], bnb_last, Q, Cb, False)
+    check(lib.usip_groupmax_scatter_add(p(G_a7), G_a7.stride(0), p(G_amax), p(arg7), Kn, Q, Cb, s()), "usip_groupmax_scatter_add")
+    # ---- layers_before, last -> 1
+    GYb = bw.bn_bwd(G_a7, Yb_last, bnb_last, kb[-1].norm, G, Cb, name="bn_bwd_knn_b%d" % (len(kb) - 1))
+    del G_a7
+    for li in range(len(kb) - 1, 0, -1):
+        Wl = _w2d(kb[li].conv.weight)
+        Yin, bnin = ctx["before"][li - 1]
+        bw.wgrad(GYb, Yin, bw.g2d(kb[li].conv.weight), G, Wl.shape[0], Wl.shape[1], prev=bnin, name="wgrad_knn_b%d" % li)
+        G_in = bw.dgrad(GYb, Wl, G, name="dgrad_knn_b%d" % li)
+        GYb = bw.bn_bwd(G_in, Yin, bnin, kb[li - 1].norm, G, G_in.shape[1], name="bn_bwd_knn_b%d" % (li - 1))
+        del G_in
+    # kb[0] = knn_combine: Y5 = Z[nbr] + Wxyz*delta + b, Z = pool2 Wf^T
+    W5 = _w2d(kb[0].conv.weight)
+    gW5 = bw.g2d(kb[0].conv.weight)
+    G_Z = torch.zeros((Q, Cb), dtype=f32, device=dev)
+    with _Prof("knn_combine_bwd"):
+        check(lib.usip_knn_combine_bwd(p(GYb), GYb.stride(0), p(ctx["cmean"]), p(ctx["knn_i"]), p(G_Z), G_Z.stride(0), p(gW5),
+                                       gW5.stride(0), Bp, M, Kn, Cb, s()), "usip_knn_combine_bwd")
+    del GYb
+    pool2 = ctx["AGG"][:, :C1]
+    bw.wgrad(G_Z, pool2, gW5[:, 3:], Q, Cb, C1, name="wgrad_knn_b0_node")
+    G_pool2_knn = bw.dgrad(G_Z, W5[:, 3:], Q, name="dgrad_knn_b0_node")    # [Q, C1]
+    G_pool2_tot = G_pool2_knn
+    G_pool2_tot += G_pool2                                                 # tiny [Q,C1] plumbing add
+
+    # ---- pool 2 un-pool (index_max gather backward), second PointNet
+    G_F2 = torch.zeros((P, C1), dtype=f32, device=dev)
+    check(lib.usip_unpool_scatter(p(G_F2), G_F2.stride(0), p(G_pool2_tot), G_pool2_tot.stride(0), p(ctx["arg2"]), Q, C1, 0, s()),
+          "usip_unpool_scatter")
+    W4 = _w2d(sp[1].conv.weight)
+    bw.wgrad(G_F2, ctx["Y3"], bw.g2d(sp[1].conv.weight), P, C1, C1, prev=ctx["bn3"], name="wgrad_pn2.1")
+    bw.colsum(G_F2, bw.grads[sp[1].conv.bias], P, C1)
+    G_a3 = bw.dgrad(G_F2, W4, P, name="dgrad_pn2.1")
+    del G_F2
+    GY3 = bw.bn_bwd(G_a3, ctx["Y3"], ctx["bn3"], sp[0].norm, P, C1, name="bn_bwd_pn2.0")
+    del G_a3
+    W3 = _w2d(sp[0].conv.weight)
+    gW3 = bw.g2d(sp[0].conv.weight)
+    bw.wgrad(GY3, ctx["F1"], gW3[:, :H], P, C1, H, name="wgrad_pn2.0")
+    G_F1 = bw.dgrad(GY3, W3[:, :H], P, name="dgrad_pn2.0")                  # [P, H]
+    G_V = torch.empty((Q, C1), dtype=f32, device=dev)
+    check(lib.usip_seg_sum(p(GY3), GY3.stride(0), p(ctx["seg_off"]), p(G_V), G_V.stride(0), Bp, N, M, C1, s()), "usip_seg_sum")
+    del GY3
+    bw.wgrad(G_V, ctx["pool1"], gW3[:, H:], Q, C1, H, name="wgrad_pn2.0_node")
+    G_pool1 = bw.dgrad(G_V, W3[:, H:], Q, name="dgrad_pn2.0_node")          # [Q, H]
+    check(lib.usip_unpool_scatter(p(G_F1), G_F1.stride(0), p(G_pool1), G_pool1.stride(0), p(ctx["arg1"]), Q, H, 1, s()),
+          "usip_unpool_scatter")
+    # ---- first PointNet
+    W2 = _w2d(fp[2].conv.weight)
+    bw.wgrad(G_F1, ctx["Y1"], bw.g2d(fp[2].conv.weight), P, H, H, prev=ctx["bn1"], name="wgrad_pn1.2")
+    bw.colsum(G_F1, bw.grads[fp[2].conv.bias], P, H)
+    G_a1 = bw.dgrad(G_F1, W2, P, name="dgrad_pn1.2")
+    del G_F1
+    GY1 = bw.bn_bwd(G_a1, ctx["Y1"], ctx["bn1"], fp[1].norm, P, H, name="bn_bwd_pn1.1")
+    del G_a1
+    W1 = _w2d(fp[1].conv.weight)
+    bw.wgrad(GY1, ctx["Y0"], bw.g2d(fp[1].conv.weight), P, H, H, prev=ctx["bn0"], name="wgrad_pn1.1")
+    G_a0 = bw.dgrad(GY1, W1, P, name="dgrad_pn1.1")
+    del GY1
+    GY0 = bw.bn_bwd(G_a0, ctx["Y0"], ctx["bn0"], fp[0].norm, P, H, name="bn_bwd_pn1.0")
+    del G_a0
+    W0 = _w2d(fp[0].conv.weight)
+    bw.wgrad(GY0, ctx["X0"], bw.g2d(fp[0].conv.weight), P, H, W0.shape[1], name="wgrad_pn1.0")
+    # conv biases in front of a train-mode BatchNorm receive exactly zero gradient (BN removes the mean); they
+    # stay zero-initialised in bw.grads.
+    return [bw.grads[q] for q in net.parameters()]
 
 
 def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):

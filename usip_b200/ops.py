@@ -144,11 +144,12 @@ def knn_nodes(pts, K):
 # ----------------------------------------------------------------------------- shared-MLP stack
 def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_shift=None, in_relu=False,
               addend=None, add_index=None, add_group=0, Y=None, ldy=None, stat_partial=None,
-              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False):
+              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False, w_transposed=False):
     d = LayerDesc()
     d.X = X.data_ptr(); d.ldx = X.stride(0) if ldx is None else ldx
     d.P = P; d.Cin = Cin; d.Cout = Cout
     d.W = W.data_ptr(); d.ldw = (W.stride(0) if ldw is None else ldw)
+    d.w_transposed = 1 if w_transposed else 0
     d.bias = None if bias is None else bias.data_ptr()
     d.in_scale = None if in_scale is None else in_scale.data_ptr()
     d.in_shift = None if in_shift is None else in_shift.data_ptr()
