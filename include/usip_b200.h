@@ -47,11 +47,12 @@ int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
 /* Fused replacement of models/networks.py:355-373 (distance matrix + ball_query + gather + decenter):
  * xyz (B,3,N), feat (B,S,N) (S may be 0), centers (B,3,M) ->
  *   out_idx (B,M,K) i32      (bit-identical to ball_query on torch.norm(centers-xyz))
- *   out_group (B,3+S,M,K) f32 = x_aug gathered, xyz channels minus the centre  (`x_features`)
+ *   out_group (B,3+S,M,K) f32 = x_aug gathered, xyz channels minus the centre  (`x_features`) (or NULL)
+ *   out_rows  [B*M*K, ld_rows] f32: the same group as point-major rows for the MLP stack (or NULL)
  * scratch_i32: B*(N + 2*cells+2) + ... see usip_ball_group_scratch_bytes(). */
 int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
-                        int32_t* out_idx, float* out_group, void* scratch, int64_t scratch_bytes,
-                        int B, int S, int N, int M, int K, void* stream);
+                        int32_t* out_idx, float* out_group, float* out_rows, int ld_rows,
+                        void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 
 /* operations.knn_gather_by_indexing                         models/operations.py:271-287
@@ -149,6 +150,9 @@ int usip_group_select(const float* gmax, const float* gmin, const float* scale, 
 /* networks.py:151-154: keypoints (B,3,M) = out[:, :3] + cluster_mean ; sigmas (B,M) = softplus(out[:,3]) + lb */
 int usip_head_finalize(const float* out4, int ld, const float* cluster_mean, float sigma_lower_bound,
                        float* keypoints, float* sigmas, int B, int M, void* stream);
+
+/* networks.py:383: out (B,C,M) = X[q,:] / (||X[q,:]||_2 + 1e-5); norm_out [B*M] optional (saved for backward) */
+int usip_l2norm_to_bcm(const float* X, int ldx, float* out, float* norm_out, int B, int M, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Losses                                                  models/losses.py:44-143

@@ -105,8 +105,8 @@ def test_detector_train_step_vs_reference_golden(fname, use_tc):
         ref = g["grad/" + k]
         gr = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
         absmax, norm = float(ref[2]), float(ref[3])
-        if k.endswith("conv.bias") and norm < 1e-6:
-            assert np.linalg.norm(gr) < 1e-5, k          # bias in front of BN: true gradient is 0 (reference: fp noise)
+        if k.endswith("conv.bias") and norm < 1e-4:
+            assert np.linalg.norm(gr) < 1e-4, k          # bias in front of BN: true gradient is 0 (reference: ~1e-6 fp noise)
             continue
         e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
         e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
@@ -126,3 +126,25 @@ def test_detector_train_step_vs_reference_golden(fname, use_tc):
         assert diff.max() <= 2.2e-3, (k, diff.max())
         assert (diff <= tol).mean() >= 0.85 or k.endswith("conv.bias"), (k, diff, tol)
     print("worst gradient rel err", worst)
+
+
+def test_descriptor_forward_vs_reference_golden():
+    """DescriptorLiteOld (ball query + gather + MLP + max + L2 normalise) vs the reference golden, eval and train BN."""
+    from usip_b200.models import networks
+    g = golden("descriptor.npz")
+    B, N, M, S, K, seed = [int(v) for v in g["cfg"]]
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K,
+                   descriptor_len=128)
+    P = {k[len("param/"):]: g[k] for k in g.files if k.startswith("param/")}
+    for use_tc in (False, True):
+        opt.use_tensor_cores = use_tc
+        net = networks.DescriptorLiteOld(opt).to(dev())
+        load_params(net, P)
+        for mode in ("eval", "train"):
+            net.train(mode == "train")
+            np.random.seed(seed)                                   # forward draws np.random.permutation(N) (networks.py:345)
+            with torch.no_grad():
+                desc, feats = net(cu(g["pc"]), cu(g["sn"]), cu(g["kp"]), mode == "train", None)
+            assert np.array_equal(feats.cpu().numpy(), g[mode + "_feats"]), (mode, "x_features must be bit-exact")
+            e = rel_err(desc.cpu().numpy(), g[mode + "_desc"])
+            assert e < REL, (mode, use_tc, e)

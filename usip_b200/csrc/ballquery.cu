@@ -56,7 +56,8 @@ ball_query_dist_kernel(const float* __restrict__ dist, float radius, int32_t* __
 __global__ void __launch_bounds__(256)
 ball_group_brute_kernel(const float* __restrict__ xyz, const float* __restrict__ feat,
                         const float* __restrict__ centers, float t_max, int32_t* __restrict__ out_idx,
-                        float* __restrict__ out_group, int B, int S, int N, int M, int K) {
+                        float* __restrict__ out_group, float* __restrict__ out_rows, int ld_rows, int B, int S, int N,
+                        int M, int K) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= B * M) return;
   const int b = w / M, m = w - b * M;
@@ -86,16 +87,24 @@ ball_group_brute_kernel(const float* __restrict__ xyz, const float* __restrict__
     }
   }
   ball_pad(o, cnt, K, lane);
-  if (!out_group) return;
+  if (!out_group && !out_rows) return;
   const int C = 3 + S;
   const float ctr[3] = {cx, cy, cz};
   for (int k = lane; k < K; k += 32) {
     int n = o[k];
+    float* rowp = out_rows ? out_rows + ((size_t)w * K + k) * ld_rows : nullptr;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      out_group[(((size_t)b * C + c) * M + m) * K + k] = px[(size_t)c * N + n] - ctr[c];   // networks.py:373
-    for (int c = 0; c < S; ++c)
-      out_group[(((size_t)b * C + 3 + c) * M + m) * K + k] = feat[((size_t)b * S + c) * N + n];
+    for (int c = 0; c < 3; ++c) {
+      float v = px[(size_t)c * N + n] - ctr[c];                                            // networks.py:373
+      if (out_group) out_group[(((size_t)b * C + c) * M + m) * K + k] = v;
+      if (rowp) rowp[c] = v;
+    }
+    for (int c = 0; c < S; ++c) {
+      float v = feat[((size_t)b * S + c) * N + n];
+      if (out_group) out_group[(((size_t)b * C + 3 + c) * M + m) * K + k] = v;
+      if (rowp) rowp[3 + c] = v;
+    }
+    if (rowp) for (int c = C; c < ld_rows; ++c) rowp[c] = 0.f;
   }
 }
 
@@ -131,14 +140,15 @@ extern "C" int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int
 }
 
 extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
-                                   int32_t* out_idx, float* out_group, void* scratch, int64_t scratch_bytes,
-                                   int B, int S, int N, int M, int K, void* stream) {
+                                   int32_t* out_idx, float* out_group, float* out_rows, int ld_rows, void* scratch,
+                                   int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream) {
   (void)scratch; (void)scratch_bytes;
   USIP_REQUIRE(xyz && centers && out_idx && (S == 0 || feat) && B > 0 && N > 0 && M > 0 && K > 0,
                "ball_group: bad args");
+  USIP_REQUIRE(!out_rows || ld_rows >= 3 + S, "ball_group: ld_rows too small");
   float t_max = radius_to_tmax(radius);
   int rows = B * M;
   ball_group_brute_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(xyz, feat, centers, t_max, out_idx,
-                                                                         out_group, B, S, N, M, K);
+                                                                         out_group, out_rows, ld_rows, B, S, N, M, K);
   return check_launch("ball_group_brute_kernel");
 }

@@ -378,6 +378,23 @@ __global__ void head_finalize_kernel(const float* __restrict__ out4, int ld, con
   sig[t] = (x > 20.f ? x : log1pf(expf(x))) + lb;                                                     // networks.py:72,154
 }
 
+// descriptor / (||descriptor||_2 + 1e-5) over channels, [Q,C] rows -> reference (B,C,M) layout (networks.py:383)
+__global__ void __launch_bounds__(256)
+l2norm_to_bcm_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, float* __restrict__ norm_out, int B,
+                     int M, int C) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * M) return;
+  const int b = w / M, m = w - b * M;
+  const float* x = X + (size_t)w * ldx;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) ss = fmaf(x[c], x[c], ss);
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float inv = 1.0f / (nrm + 1e-5f);
+  if (norm_out && lane == 0) norm_out[w] = nrm;
+  for (int c = lane; c < C; c += 32) out[((size_t)b * C + c) * M + m] = x[c] * inv;
+}
+
 template <int BN>
 static int launch_layer_simt(const usip_layer_desc& d, cudaStream_t st) {
   static bool attr_done = false;
@@ -465,4 +482,11 @@ extern "C" int usip_head_finalize(const float* out4, int ld, const float* cluste
   head_finalize_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(out4, ld, cluster_mean, sigma_lower_bound,
                                                                           keypoints, sigmas, B, M);
   return check_launch("head_finalize_kernel");
+}
+
+extern "C" int usip_l2norm_to_bcm(const float* X, int ldx, float* out, float* norm_out, int B, int M, int C,
+                                  void* stream) {
+  USIP_REQUIRE(X && out && ldx >= C, "l2norm_to_bcm: bad args");
+  l2norm_to_bcm_kernel<<<cdiv(B * M * 32, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, out, norm_out, B, M, C);
+  return check_launch("l2norm_to_bcm_kernel");
 }

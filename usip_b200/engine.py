@@ -474,7 +474,44 @@ def detector_backward(net, ctx, g_kp, g_sig):
 
 
 def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):
-    raise NotImplementedError("descriptor plan not built yet")
+    """DescriptorLiteOld.forward (models/networks.py:333-385) on the fused plan.
+    Returns (descriptor (B,C,M), x_features (B,3+S,M,K), ctx)."""
+    from . import _lib
+    opt = net.opt
+    dev = x.device
+    if keep:
+        raise NotImplementedError("descriptor backward plan is not built yet (SURVEY 8f-1 'next' row): run under "
+                                  "torch.no_grad() / freeze_model()")
+    Bp, _, N = x.shape
+    M = keypoints.shape[2]
+    K = opt.ball_nsamples
+    S = opt.surface_normal_len if opt.surface_normal_len > 0 else 0
+    G, Q = Bp * M * K, Bp * M
+    R = LayerRunner(net, net.training, use_tc, dev)
+    # permute the points on the host-drawn permutation: the ball query keeps the FIRST K hits in index order
+    x = x.detach()[:, :, permute_idx].contiguous()
+    snp = sn.detach()[:, :, permute_idx].contiguous() if S else None
+    kp = keypoints.detach().contiguous()
+    with _Prof("ball_group", nbytes=4.0 * Bp * (N * (3 + S) + 3 * M + M * K + (3 + S) * M * K)):
+        idx, feats, rows = ops.ball_group(x, snp, kp, float(opt.ball_radius), K, want_group=True, rows_ld=8)
+    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
+    D = c3.conv.weight.shape[0]
+    Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, _bn_mom(c1.norm, epoch), name="desc.conv1")
+    Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, _bn_mom(c2.norm, epoch), prev=bn1, name="desc.conv2")
+    Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, _bn_mom(c3.norm, epoch), prev=bn2,
+                          group=K, want_group=True, name="desc.conv3")
+    amax = torch.empty((Q, D), dtype=f32, device=dev)
+    ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
+    W4 = _w2d(c4.conv.weight)
+    U, _, _ = R.run(amax, Q, W4[:, D:], None, relu_in=False, name="desc.conv4_node")        # cat(y_first, max): max is LAST
+    Y4, bn4, _ = R.run(Y3, G, W4[:, :D], c4.conv.bias.detach(), c4.norm, _bn_mom(c4.norm, epoch), prev=bn3, addend=U,
+                       add_group=K, name="desc.conv4")
+    _, _, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), prev=bn4, group=K, want_group=True,
+                       write_y=False, name="desc.conv5")
+    desc = torch.empty((Bp, D, M), dtype=f32, device=dev)
+    _lib.check(_lib.load().usip_l2norm_to_bcm(ops._p(grp5["gmax"]), grp5["gmax"].stride(0), ops._p(desc), None, Bp, M, D,
+                                              ops._stream()), "usip_l2norm_to_bcm")
+    return desc, feats, None
 
 
 def descriptor_backward(net, ctx, g_desc):

@@ -58,7 +58,7 @@ def ball_query_dist(dist, radius, K):
     return out
 
 
-def ball_group(xyz, feat, centers, radius, K, want_group=True):
+def ball_group(xyz, feat, centers, radius, K, want_group=True, rows_ld=0):
     """Fused distance + ball query + gather + decentre.  Returns (idx (B,M,K) i32, group (B,3+S,M,K) f32)."""
     _req(xyz, f32, "xyz"); _req(centers, f32, "centers")
     B, _, N = xyz.shape
@@ -69,11 +69,15 @@ def ball_group(xyz, feat, centers, radius, K, want_group=True):
     lib = _lib.load()
     idx = torch.empty((B, M, int(K)), dtype=i32, device=xyz.device)
     grp = torch.empty((B, 3 + S, M, int(K)), dtype=f32, device=xyz.device) if want_group else None
+    rows = torch.empty((B * M * int(K), rows_ld), dtype=f32, device=xyz.device) if rows_ld else None
     nbytes = lib.usip_ball_group_scratch_bytes(B, S, N, M, int(K))
     scratch = torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=xyz.device)
     with torch.cuda.device(xyz.device):
         check(lib.usip_ball_group_f32(_p(xyz), _p(feat) if S else None, _p(centers), float(radius), _p(idx), _p(grp),
-                                      _p(scratch), int(nbytes), B, S, N, M, int(K), _stream()), "usip_ball_group_f32")
+                                      _p(rows), rows_ld, _p(scratch), int(nbytes), B, S, N, M, int(K), _stream()),
+              "usip_ball_group_f32")
+    if rows_ld:
+        return idx, grp, rows
     return idx, grp
 
 
