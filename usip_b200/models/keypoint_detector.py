@@ -35,7 +35,7 @@ class ModelDetector():
         self.old_lr_detector = self.opt.lr
         self.optimizer_detector = torch.optim.Adam(self.detector.parameters(), lr=self.old_lr_detector,
                                                    betas=(0.9, 0.999), weight_decay=0)
-        self._dp_group = None
+        self._dp = None
         self._flat_grad = None
 
         dev = self.opt.device
@@ -60,28 +60,13 @@ class ModelDetector():
     # ------------------------------------------------------------------ data parallel (one process / GPU)
     def enable_data_parallel(self, process_group=None):
         """Switch on the gradient all-reduce.  Call after torch.distributed.init_process_group."""
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            raise RuntimeError("torch.distributed is not initialised")
-        self._dp_group = process_group if process_group is not None else dist.group.WORLD
-        params = [p for p in self.detector.parameters() if p.requires_grad]
-        n = sum(p.numel() for p in params)
-        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=params[0].device)
-        # parameters' .grad become views into one flat buffer: one collective, no packing copies
-        off = 0
-        for p in params:
-            p.grad = self._flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        # identical initial weights on every rank
-        for t in list(self.detector.parameters()) + list(self.detector.buffers()):
-            dist.broadcast(t.data, src=0, group=self._dp_group)
+        from ..dp import FlatGradAllReduce
+        self._dp = FlatGradAllReduce(self.detector.parameters(), process_group, buffers=list(self.detector.buffers()))
+        self._flat_grad = self._dp.flat
 
     def _allreduce_grads(self):
-        if self._dp_group is None:
-            return
-        import torch.distributed as dist
-        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM, group=self._dp_group)
-        self._flat_grad.mul_(1.0 / dist.get_world_size(self._dp_group))
+        if self._dp is not None:
+            self._dp.allreduce_mean()
 
     # ------------------------------------------------------------------ reference API
     def set_input(self, src_pc, src_sn, src_node, dst_pc, dst_sn, dst_node, src_R_dst, src_scale_dst, src_shift_dst):
