@@ -296,3 +296,38 @@ def test_pairwise_min_full_size_properties():
     samp = pc[:, :, ::64]
     dd = np.sqrt(((kp[:, :, :, None] - samp[:, :, None, :]) ** 2).sum(1)).min(2)
     assert np.all(dh <= dd * (1 + 1e-6))
+
+
+def test_ball_group_grid_full_size_vs_reference_cuda():
+    """Oxford descriptor shape (B'=16, N=16384, 1024 keypoints, r=1, K=64): cell-binned fused kernel vs the reference
+    kernel on the materialised torch.norm distance matrix (bit-exact indices), plus a dense cloud that exercises the
+    sort path (hits > K) and the in-order fallback (hits > 256)."""
+    from usip_b200 import ball_query
+    ref = ref_ext("ball_query")
+    torch.manual_seed(3)
+    for dense in (False, True):
+        B, N, M, K = (16, 16384, 1024, 64) if not dense else (2, 8192, 256, 64)
+        ext = torch.tensor([40.0, 2.0, 40.0], device=dev()).view(1, 3, 1) * (0.08 if dense else 1.0)
+        pc = (torch.rand(B, 3, N, device=dev()) * 2 - 1) * ext
+        sn = torch.randn(B, 4, N, device=dev())
+        sel = torch.randint(0, N, (B, M), device=dev())
+        kp = torch.gather(pc, 2, sel.unsqueeze(1).expand(B, 3, M)) + 0.1 * torch.randn(B, 3, M, device=dev())
+        idx, grp, rows = ops_ball_group(pc, sn, kp, 1.0, K)
+        if ref is not None:
+            dist = torch.norm(kp.unsqueeze(3) - pc.unsqueeze(2), dim=1).contiguous()
+            theirs = ref.forward_cuda_shared_mem(dist, 1.0, K)
+            torch.cuda.synchronize()
+            assert torch.equal(idx, theirs), dense
+        else:
+            assert np.array_equal(idx[:2].cpu().numpy(), orc.ball_query_xyz(pc[:2].cpu().numpy(), kp[:2].cpu().numpy(), 1.0, K))
+        x_aug = torch.cat([pc, sn], 1)
+        gi = idx.long().view(B, 1, M * K).expand(B, 7, M * K)
+        ball = torch.gather(x_aug, 2, gi).view(B, 7, M, K).clone()
+        ball[:, :3] -= kp.unsqueeze(3)
+        assert torch.equal(grp, ball)
+        assert torch.equal(rows.view(B, M, K, 8)[..., :7].permute(0, 3, 1, 2), ball)
+
+
+def ops_ball_group(pc, sn, kp, r, K):
+    from usip_b200 import ops
+    return ops.ball_group(pc.contiguous(), sn.contiguous(), kp.contiguous(), r, K, want_group=True, rows_ld=8)

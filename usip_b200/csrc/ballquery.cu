@@ -108,6 +108,234 @@ ball_group_brute_kernel(const float* __restrict__ xyz, const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cell-binned variant: points are binned once per cloud into a uniform grid with cell size h >= 1.001*r, a
+// keypoint only tests the <= 27 neighbouring cells (9 x-contiguous ranges), collects the hits (unordered),
+// sorts their indices ascending and keeps the first K -- bit-identical to the in-order scan, without the O(N)
+// pass per keypoint.  Dense balls (more than BG_CAP hits) fall back to the early-exit in-order scan, which is
+// cheap exactly there.
+// ------------------------------------------------------------------------------------------------
+constexpr int BG_MAX_CELLS = 65536;
+constexpr int BG_CAP = 256;
+
+struct BgGrid { float ox, oy, oz, inv_h; int nx, ny, nz, ok; };
+
+__global__ void __launch_bounds__(1024)
+bg_bbox_kernel(const float* __restrict__ xyz, float radius, BgGrid* __restrict__ grids, int N) {
+  __shared__ float smin[3][32], smax[3][32];
+  const int b = blockIdx.x;
+  const float* p = xyz + (size_t)b * 3 * N;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool bad = false;
+  for (int n = threadIdx.x; n < N; n += 1024)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = p[(size_t)c * N + n];
+      bad |= !(fabsf(v) <= 1e30f);
+      mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
+    }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned anybad = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    if (lane == 0) { smin[c][w] = anybad ? NAN : mn[c]; smax[c][w] = mx[c]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BgGrid g; g.ok = 1;
+    float lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) {
+      lo[c] = INFINITY; hi[c] = -INFINITY;
+      for (int i = 0; i < 32; ++i) { if (smin[c][i] != smin[c][i]) g.ok = 0; lo[c] = fminf(lo[c], smin[c][i]); hi[c] = fmaxf(hi[c], smax[c][i]); }
+    }
+    if (!(radius >= 0.f) || !(radius <= 1e30f)) g.ok = 0;
+    float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float h = fmaxf(fmaxf(radius * 1.001f, ext * (1.0f / 126.0f)), 1e-6f);
+    int nx = 1, ny = 1, nz = 1;
+    if (g.ok) {
+      for (int it = 0; it < 64; ++it) {
+        nx = (int)floorf((hi[0] - lo[0]) / h) + 1; ny = (int)floorf((hi[1] - lo[1]) / h) + 1; nz = (int)floorf((hi[2] - lo[2]) / h) + 1;
+        if ((long long)nx * ny * nz <= BG_MAX_CELLS) break;
+        h *= 1.26f;
+      }
+      if ((long long)nx * ny * nz > BG_MAX_CELLS) g.ok = 0;
+    }
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = 1.0f / h; g.nx = nx; g.ny = ny; g.nz = nz;
+    grids[b] = g;
+  }
+}
+
+__device__ __forceinline__ int bg_cell1(float v, float o, float inv_h, int n) {
+  int c = (int)floorf((v - o) * inv_h);
+  return min(max(c, 0), n - 1);
+}
+
+// per point: cell id + histogram; also writes the 32-byte AoS record (x,y,z,feat...) used by the gather
+__global__ void __launch_bounds__(256)
+bg_count_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const BgGrid* __restrict__ grids,
+                int32_t* __restrict__ cell_of, int32_t* __restrict__ cell_cnt, float* __restrict__ rec, int S, int N) {
+  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  const BgGrid g = grids[b];
+  const float* p = xyz + (size_t)b * 3 * N;
+  const float x = p[n], y = p[N + n], z = p[2 * N + n];
+  float r[8] = {x, y, z, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < S && c < 5; ++c) r[3 + c] = feat[((size_t)b * S + c) * N + n];
+  float4* rp = reinterpret_cast<float4*>(rec + ((size_t)b * N + n) * 8);
+  rp[0] = make_float4(r[0], r[1], r[2], r[3]); rp[1] = make_float4(r[4], r[5], r[6], r[7]);
+  if (!g.ok) return;
+  const int cell = (bg_cell1(z, g.oz, g.inv_h, g.nz) * g.ny + bg_cell1(y, g.oy, g.inv_h, g.ny)) * g.nx + bg_cell1(x, g.ox, g.inv_h, g.nx);
+  cell_of[(size_t)b * N + n] = cell;
+  atomicAdd(&cell_cnt[(size_t)b * (BG_MAX_CELLS + 1) + cell], 1);
+}
+
+// exclusive scan of the cell histogram (one CTA per cloud); cell_cnt becomes cell_start, fill cursor zeroed
+__global__ void __launch_bounds__(1024)
+bg_scan_kernel(int32_t* __restrict__ cell_cnt, int32_t* __restrict__ cell_fill, const BgGrid* __restrict__ grids) {
+  __shared__ int part[1024];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const BgGrid g = grids[b];
+  if (!g.ok) return;
+  const int cells = g.nx * g.ny * g.nz;
+  int32_t* cnt = cell_cnt + (size_t)b * (BG_MAX_CELLS + 1);
+  int32_t* fill = cell_fill + (size_t)b * BG_MAX_CELLS;
+  const int per = (cells + 1023) / 1024, lo = min(tid * per, cells), hi = min(lo + per, cells);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += cnt[i];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) { int run = 0; for (int t = 0; t < 1024; ++t) { int v = part[t]; part[t] = run; run += v; } cnt[cells] = run; }
+  __syncthreads();
+  int run = part[tid];
+  for (int i = lo; i < hi; ++i) { int v = cnt[i]; cnt[i] = run; fill[i] = 0; run += v; }
+}
+
+__global__ void __launch_bounds__(256)
+bg_fill_kernel(const float* __restrict__ xyz, const BgGrid* __restrict__ grids, const int32_t* __restrict__ cell_of,
+               const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill, float4* __restrict__ sorted, int N) {
+  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N || !grids[b].ok) return;
+  const int cell = cell_of[(size_t)b * N + n];
+  const int pos = cell_start[(size_t)b * (BG_MAX_CELLS + 1) + cell] + atomicAdd(&cell_fill[(size_t)b * BG_MAX_CELLS + cell], 1);
+  const float* p = xyz + (size_t)b * 3 * N;
+  sorted[(size_t)b * N + pos] = make_float4(p[n], p[N + n], p[2 * N + n], __int_as_float(n));
+}
+
+__global__ void __launch_bounds__(256)
+bg_query_kernel(const float* __restrict__ xyz, const float* __restrict__ centers, const BgGrid* __restrict__ grids,
+                const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted, const float* __restrict__ rec,
+                float t_max, int32_t* __restrict__ out_idx, float* __restrict__ out_group, float* __restrict__ out_rows,
+                int ld_rows, int B, int S, int N, int M, int K) {
+  __shared__ int hits[8][BG_CAP];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + wib;
+  if (w >= B * M) return;
+  const int b = w / M, m = w - b * M;
+  const BgGrid g = grids[b];
+  const float cx = centers[(size_t)b * 3 * M + m], cy = centers[(size_t)b * 3 * M + M + m], cz = centers[(size_t)b * 3 * M + 2 * M + m];
+  int32_t* o = out_idx + (size_t)w * K;
+  int* hl = hits[wib];
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt = 0;
+  bool brute = !g.ok;
+  if (!brute) {
+    // un-clamped cell coordinates of the centre; neighbour ranges are clipped to the grid
+    const int kx = (int)floorf((cx - g.ox) * g.inv_h), ky = (int)floorf((cy - g.oy) * g.inv_h), kz = (int)floorf((cz - g.oz) * g.inv_h);
+    const bool cfin = fabsf(cx) <= 1e30f && fabsf(cy) <= 1e30f && fabsf(cz) <= 1e30f;
+    const int x0 = max(kx - 1, 0), x1 = min(kx + 1, g.nx - 1);
+    const int32_t* cs = cell_start + (size_t)b * (BG_MAX_CELLS + 1);
+    const float4* sp = sorted + (size_t)b * N;
+    if (cfin && x0 <= x1)
+      for (int dz = -1; dz <= 1 && !brute; ++dz) {
+        const int z = kz + dz;
+        if (z < 0 || z >= g.nz) continue;
+        for (int dy = -1; dy <= 1 && !brute; ++dy) {
+          const int y = ky + dy;
+          if (y < 0 || y >= g.ny) continue;
+          const int base = (z * g.ny + y) * g.nx;
+          const int s = cs[base + x0], e = cs[base + x1 + 1];
+          for (int i = s; i < e; i += 32) {
+            const int j = i + lane;
+            bool hit = false; int n = 0;
+            if (j < e) {
+              const float4 q = sp[j];
+              n = __float_as_int(q.w);
+              hit = sqdist_rn(cx, cy, cz, q.x, q.y, q.z) <= t_max;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, hit);
+            if (bal) {
+              const int pos = cnt + __popc(bal & lt);
+              if (hit && pos < BG_CAP) hl[pos] = n;
+              cnt += __popc(bal);
+              if (cnt > BG_CAP) { brute = true; break; }
+            }
+          }
+        }
+      }
+  }
+  if (brute) {
+    // early-exit in-order scan (exactly the reference loop); used for dense balls / degenerate grids
+    const float* px = xyz + (size_t)b * 3 * N;
+    cnt = 0;
+    for (int base = 0; base < N && cnt < K; base += 32) {
+      const int n = base + lane;
+      const bool hit = (n < N) && (sqdist_rn(cx, cy, cz, __ldg(px + n), __ldg(px + N + n), __ldg(px + 2 * N + n)) <= t_max);
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        const int pos = cnt + __popc(bal & lt);
+        if (hit && pos < K) o[pos] = n;
+        cnt += __popc(bal);
+      }
+    }
+  } else {
+    // bitonic sort of the hit list (ascending point index), padded with INT_MAX to a power of two
+    __syncwarp();
+    int sz = 32;
+    while (sz < cnt) sz <<= 1;
+    for (int i = cnt + lane; i < sz; i += 32) hl[i] = 0x7fffffff;
+    __syncwarp();
+    for (int k2 = 2; k2 <= sz; k2 <<= 1)
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (int i = lane; i < sz; i += 32) {
+          const int ixj = i ^ j2;
+          if (ixj > i) {
+            const int a = hl[i], c2 = hl[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a > c2) == up) { hl[i] = c2; hl[ixj] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    for (int i = lane; i < min(cnt, K); i += 32) o[i] = hl[i];
+  }
+  ball_pad(o, cnt, K, lane);
+  if (!out_group && !out_rows) return;
+  const int C = 3 + S;
+  for (int k = lane; k < K; k += 32) {
+    const int n = o[k];
+    const float4* rp = reinterpret_cast<const float4*>(rec + ((size_t)b * N + n) * 8);
+    const float4 r0 = rp[0], r1 = rp[1];
+    float v[8] = {r0.x - cx, r0.y - cy, r0.z - cz, r0.w, r1.x, r1.y, r1.z, r1.w};          // networks.py:373
+    if (out_group)
+      for (int c = 0; c < C; ++c) out_group[(((size_t)b * C + c) * M + m) * K + k] = v[c];
+    if (out_rows) {
+      float* rowp = out_rows + ((size_t)w * K + k) * ld_rows;
+      if (ld_rows == 8) {
+        for (int c = C; c < 8; ++c) v[c] = 0.f;
+        reinterpret_cast<float4*>(rowp)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(rowp)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        for (int c = 0; c < ld_rows; ++c) rowp[c] = c < C ? v[c] : 0.f;
+      }
+    }
+  }
+}
+
 // largest float t with sqrtf(t) <= radius  (host, exact)
 static float radius_to_tmax(float radius) {
   if (!(radius >= 0.0f)) return -1.0f;           // negative or NaN radius: nothing is ever inside
@@ -134,21 +362,53 @@ extern "C" int usip_ball_query_dist_f32(const float* dist, float radius, int32_t
   return check_launch("ball_query_dist_kernel");
 }
 
+static size_t bg_align(size_t x) { return (x + 255) & ~(size_t)255; }
+struct BgScratch {
+  BgGrid* grids; int32_t* cell_cnt; int32_t* cell_fill; int32_t* cell_of; float4* sorted; float* rec; size_t total;
+  BgScratch(void* base, int B, int N) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += bg_align(bytes); return o; };
+    size_t o_g = take(sizeof(BgGrid) * B), o_c = take(sizeof(int32_t) * (size_t)B * (BG_MAX_CELLS + 1));
+    size_t o_f = take(sizeof(int32_t) * (size_t)B * BG_MAX_CELLS), o_o = take(sizeof(int32_t) * (size_t)B * N);
+    size_t o_s = take(sizeof(float4) * (size_t)B * N), o_r = take(sizeof(float) * 8 * (size_t)B * N);
+    total = off;
+    char* p = (char*)base;
+    grids = (BgGrid*)(p + o_g); cell_cnt = (int32_t*)(p + o_c); cell_fill = (int32_t*)(p + o_f);
+    cell_of = (int32_t*)(p + o_o); sorted = (float4*)(p + o_s); rec = (float*)(p + o_r);
+  }
+};
+
 extern "C" int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K) {
-  (void)B; (void)S; (void)N; (void)M; (void)K;
-  return 16;   // the brute-force path needs none; kept in the ABI for the cell-grid path
+  (void)S; (void)M; (void)K;
+  BgScratch sc(nullptr, B, N);
+  return (int64_t)sc.total + 256;
 }
 
 extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
                                    int32_t* out_idx, float* out_group, float* out_rows, int ld_rows, void* scratch,
                                    int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream) {
-  (void)scratch; (void)scratch_bytes;
   USIP_REQUIRE(xyz && centers && out_idx && (S == 0 || feat) && B > 0 && N > 0 && M > 0 && K > 0,
                "ball_group: bad args");
   USIP_REQUIRE(!out_rows || ld_rows >= 3 + S, "ball_group: ld_rows too small");
-  float t_max = radius_to_tmax(radius);
-  int rows = B * M;
-  ball_group_brute_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(xyz, feat, centers, t_max, out_idx,
-                                                                         out_group, out_rows, ld_rows, B, S, N, M, K);
-  return check_launch("ball_group_brute_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float t_max = radius_to_tmax(radius);
+  const int rows = B * M;
+  const bool grid_ok = scratch && S <= 5 && (reinterpret_cast<uintptr_t>(scratch) % 256) == 0 &&
+                       scratch_bytes >= usip_ball_group_scratch_bytes(B, S, N, M, K) - 256 &&
+                       (!out_rows || (reinterpret_cast<uintptr_t>(out_rows) % 16) == 0);
+  if (!grid_ok) {
+    ball_group_brute_kernel<<<cdiv(rows, 8), 256, 0, st>>>(xyz, feat, centers, t_max, out_idx, out_group, out_rows,
+                                                           ld_rows, B, S, N, M, K);
+    return check_launch("ball_group_brute_kernel");
+  }
+  BgScratch sc(scratch, B, N);
+  cudaMemsetAsync(sc.cell_cnt, 0, sizeof(int32_t) * (size_t)B * (BG_MAX_CELLS + 1), st);
+  bg_bbox_kernel<<<B, 1024, 0, st>>>(xyz, radius, sc.grids, N);
+  dim3 gp(cdiv(N, 256), B);
+  bg_count_kernel<<<gp, 256, 0, st>>>(xyz, feat, sc.grids, sc.cell_of, sc.cell_cnt, sc.rec, S, N);
+  bg_scan_kernel<<<B, 1024, 0, st>>>(sc.cell_cnt, sc.cell_fill, sc.grids);
+  bg_fill_kernel<<<gp, 256, 0, st>>>(xyz, sc.grids, sc.cell_of, sc.cell_cnt, sc.cell_fill, sc.sorted, N);
+  bg_query_kernel<<<cdiv(rows, 8), 256, 0, st>>>(xyz, centers, sc.grids, sc.cell_cnt, sc.sorted, sc.rec, t_max, out_idx,
+                                                 out_group, out_rows, ld_rows, B, S, N, M, K);
+  return check_launch("ball_group_grid");
 }
