@@ -251,7 +251,8 @@ def main():
     roof = None
     pk = peaks()
     if prof:
-        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        layer_ops = {k: v for k, v in prof.items() if v.get("flops")}
+        top = max((layer_ops or prof).items(), key=lambda kv: kv[1]["ms"])
         name, rec = top
         step_ms = sum(r["ms"] for r in prof.values())
         if rec.get("flops"):
@@ -265,7 +266,7 @@ def main():
                     "frac_issued_tf32": 3 * ach / tf32_peak, "kernel_ms": rec["ms"], "kernel_share_of_step": rec["ms"] / step_ms,
                     "precision": rec.get("precision", "fp32")}
         else:
-            ach = rec.get("bytes", 0) / (rec["ms"] * 1e-3) / 1e9
+            ach = (rec.get("bytes") or 0) / (rec["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": rec["ms"],
                     "kernel_share_of_step": rec["ms"] / step_ms, "note": pk["source"]}

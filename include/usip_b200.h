@@ -102,7 +102,7 @@ typedef struct usip_layer_desc {
   const int32_t* add_index;            /* row -> g  (NULL: g = row / add_group)                       */
   int32_t add_group;
   float* Y; int32_t ldy;               /* [P,Cout] output (NULL: not written)                         */
-  float* stat_partial;                 /* [ntiles,2,Cout] per-tile (sum, sumsq) or NULL               */
+  float* stat_partial;                 /* [nstat,2,Cout] per-slice (sum, sumsq) or NULL (see stat_rows) */
   float* gmax; float* gmin;            /* [P/group,Cout] per-group max / min of Y, or NULL            */
   int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
   int32_t group;
@@ -113,8 +113,9 @@ typedef struct usip_layer_desc {
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);
-/* rows per stat tile (ntiles = ceil(P / usip_layer_tile_rows())) */
+/* rows per BN-statistic partial: stat_partial is [ceil(P / usip_layer_stat_rows(precision)), 2, Cout] */
 int usip_layer_tile_rows(void);
+int usip_layer_stat_rows(int precision);
 /* bytes of tc_workspace (hi/lo TF32 split of W, pre-swizzled into tcgen05 operand tiles) */
 int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout);
 

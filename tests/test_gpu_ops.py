@@ -209,7 +209,7 @@ def test_layer_fwd(P, Cin, Cout, group, precision):
     add_idx = rng.integers(0, G, size=P).astype(np.int32)
     Xd = cu(X)
     Y = torch.empty((P, Cout), device=dev())
-    tile = ops.tile_rows(); nt = (P + tile - 1) // tile
+    tile = ops.stat_rows(precision); nt = (P + tile - 1) // tile
     part = torch.zeros((nt, 2, Cout), device=dev())
     kw = {}
     if group and P % group == 0:

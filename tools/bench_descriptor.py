@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Oxford descriptor configuration (BASELINE.json configs[3]): B'=16 clouds, N=16384, 1024 keypoints, r=1.0, K=64, S=4.
+
+Reports (JSON, one line): device time of the fused ball-query+group operator against the HBM roofline with the
+ALGORITHMIC bytes of SURVEY.md 8(d) row G (2,568,192 B per cloud), the stand-alone index_max / ball_query operators
+against the reference's own CUDA kernels (oracle/_ref, when present), and the descriptor forward in clouds/s.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def time_ms(fn, iters=20, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()                                  # > L2: evict between iterations
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    from usip_b200 import ops, index_max, ball_query
+    from usip_b200.models import networks
+    from tests.util_gpu import make_opt, ref_ext
+    import bench
+    dev = torch.device("cuda:0")
+    pk = bench.peaks()
+    torch.manual_seed(1234 + 3)
+    B, N, M, K, S = 16, 16384, 1024, 64, 4
+    pc = torch.stack([torch.empty(B, N, device=dev).uniform_(-40, 40), torch.empty(B, N, device=dev).uniform_(-2, 2),
+                      torch.empty(B, N, device=dev).uniform_(-40, 40)], 1).contiguous()
+    sn = torch.randn(B, S, N, device=dev)
+    sel = torch.randint(0, N, (B, M), device=dev)
+    kp = (torch.gather(pc, 2, sel.unsqueeze(1).expand(B, 3, M)) + 0.1 * torch.randn(B, 3, M, device=dev)).contiguous()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    out = {"workload": "Oxford descriptor: B'=16, N=16384, M=1024 keypoints, r=1.0, K=64, S=4", "peaks": pk}
+
+    # --- fused ball query + group (idx + (B,7,M,K) group)
+    alg_bytes = 4 * (N * (3 + S) + 3 * M + M * K + (3 + S) * M * K) * B
+    med, best = time_ms(lambda: ops.ball_group(pc, sn, kp, 1.0, K, want_group=True), flush=flush)
+    out["ball_group_fused"] = {"ms_median": med, "ms_min": best, "algorithmic_bytes": alg_bytes,
+                               "achieved_GBs": alg_bytes / (med * 1e-3) / 1e9, "peak_GBs": pk["hbm_gbs"],
+                               "frac": alg_bytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"],
+                               "note": "5 launches (bbox, bin count, scan, fill, query); L2 flushed between iterations"}
+    # --- reference path for the same result: materialise (B,M,N) distances + reference ball_query kernel + gather
+    rb = ref_ext("ball_query")
+    if rb is not None:
+        def ref_path():
+            dist = torch.norm(kp.unsqueeze(3) - pc.unsqueeze(2), p=2, dim=1, keepdim=False)
+            idx = rb.forward_cuda_shared_mem(dist, 1.0, K).long()
+            x_aug = torch.cat((pc, sn), dim=1)
+            g = torch.gather(x_aug, 2, idx.unsqueeze(1).expand(B, 7, M, K).reshape(B, 7, M * K)).view(B, 7, M, K)
+            g[:, 0:3] = g[:, 0:3] - kp.unsqueeze(3)
+            return g
+        med_r, _ = time_ms(ref_path, iters=5, warm=1, flush=flush)
+        out["ball_group_reference_gpu"] = {"ms_median": med_r, "speedup": med_r / med}
+        dist = torch.norm(kp.unsqueeze(3) - pc.unsqueeze(2), dim=1).contiguous()
+        a, _ = time_ms(lambda: ball_query.forward_cuda_shared_mem(dist, 1.0, K), flush=flush)
+        b, _ = time_ms(lambda: rb.forward_cuda_shared_mem(dist, 1.0, K), iters=5, warm=1, flush=flush)
+        out["ball_query_dist_op"] = {"ours_ms": a, "reference_kernel_ms": b, "bytes": dist.numel() * 4,
+                                     "ours_GBs": dist.numel() * 4 / (a * 1e-3) / 1e9}
+    # --- index_max stand-alone at the KITTI shape
+    data = torch.randn(16, 128, 16384, device=dev)
+    index = torch.randint(0, 512, (16, 16384), device=dev, dtype=torch.int32)
+    a, _ = time_ms(lambda: index_max.forward_cuda_shared_mem(data, index, 512), flush=flush)
+    rec = {"ours_ms": a, "bytes": data.numel() * 4 + index.numel() * 4 + 16 * 128 * 512 * 4}
+    rec["ours_GBs"] = rec["bytes"] / (a * 1e-3) / 1e9
+    rec["frac_hbm"] = rec["ours_GBs"] / pk["hbm_gbs"]
+    ri = ref_ext("index_max")
+    if ri is not None:
+        b, _ = time_ms(lambda: ri.forward_cuda(data, index, 512), iters=5, warm=1, flush=flush)
+        rec["reference_kernel_ms"] = b
+    out["index_max_op"] = rec
+    # --- descriptor forward (eval BN), clouds/s
+    opt = make_opt(batch_size=B // 2, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K,
+                   descriptor_len=128)
+    net = networks.DescriptorLiteOld(opt).to(dev)
+    for mode in ("eval", "train"):
+        net.train(mode == "train")
+        with torch.no_grad():
+            med_d, _ = time_ms(lambda: net(pc, sn, kp, mode == "train", None), iters=10, warm=3)
+        out["descriptor_forward_" + mode] = {"ms": med_d, "clouds_per_s": B / (med_d * 1e-3)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

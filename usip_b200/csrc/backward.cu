@@ -63,11 +63,23 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int ntiles, double count,
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int t = sl; t < ntiles; t += 32) {
+  if (c < C) {
+    int t = sl;
+    for (; t + 7 * 32 < ntiles; t += 8 * 32) {
+      float x[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        x[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 0) * C + c);
+        y[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a += (double)x[u]; b += (double)y[u]; }
+    }
+    for (; t < ntiles; t += 32) {
       a += (double)part[((size_t)t * 2 + 0) * C + c];
       b += (double)part[((size_t)t * 2 + 1) * C + c];
     }
+  }
   sh[0][sl][cl] = a; sh[1][sl][cl] = b;
   __syncthreads();
   if (sl == 0 && c < C) {

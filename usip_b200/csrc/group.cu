@@ -94,10 +94,16 @@ sort_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ seg_off, int 
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   for (int m = tid; m < M; m += nt) {
     int run = 0;
-    for (int c = 0; c < chunks; ++c) {
-      int32_t* p = hist + ((size_t)b * chunks + c) * M + m;
-      int h = *p; *p = run; run += h;
+    int32_t* base = hist + (size_t)b * chunks * M + m;
+    int c = 0;
+    for (; c + 16 <= chunks; c += 16) {          // 16 independent loads in flight, then the serial prefix
+      int h[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) h[u] = base[(size_t)(c + u) * M];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { base[(size_t)(c + u) * M] = run; run += h[u]; }
     }
+    for (; c < chunks; ++c) { int h = base[(size_t)c * M]; base[(size_t)c * M] = run; run += h; }
     tot[m] = run;
   }
   __syncthreads();

@@ -260,15 +260,29 @@ bn_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int
                    float* __restrict__ running_mean, float* __restrict__ running_var,
                    float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  // block = 32 channels x 32 tile slices; every thread keeps 8 independent loads in flight per batch so the
+  // reduction is bandwidth- not latency-bound (the partial buffer has up to thousands of rows)
   __shared__ double sh[2][32][33];
   const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s = 0.0, ss = 0.0;
-  if (c < C)
-    for (int t = sl; t < ntiles; t += 32) {
+  if (c < C) {
+    int t = sl;
+    for (; t + 7 * 32 < ntiles; t += 8 * 32) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 0) * C + c);
+        b[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
+    }
+    for (; t < ntiles; t += 32) {
       s += (double)part[((size_t)t * 2 + 0) * C + c];
       ss += (double)part[((size_t)t * 2 + 1) * C + c];
     }
+  }
   sh[0][sl][cl] = s; sh[1][sl][cl] = ss;
   __syncthreads();
   if (sl == 0 && c < C) {
@@ -410,12 +424,14 @@ static int launch_layer_simt(const usip_layer_desc& d, cudaStream_t st) {
 }
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st);   // mlp_tc.cu
+int tc_stat_rows();
 
 }  // namespace usip
 
 using namespace usip;
 
 extern "C" int usip_layer_tile_rows(void) { return L_BM; }
+extern "C" int usip_layer_stat_rows(int precision) { return precision == 1 ? tc_stat_rows() : L_BM; }
 extern "C" int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout) { return (int64_t)2 * Cin * Cout * 4; }
 
 extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {

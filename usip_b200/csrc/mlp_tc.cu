@@ -6,11 +6,12 @@
 //     D += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi        (dropped term a_lo*w_lo ~ 2^-22 relative)
 // which keeps fp32-level accuracy (the 1e-4 parity bar) at 1/3 of the TF32 tensor rate.
 //
-// Persistent, warp-specialised CTA (one per SM), 13 warps:
-//   warps 0-3  : epilogue  (TMEM lanes 32*(w%4)..+31): tcgen05.ld -> bias/addend -> Y, BN statistic
-//                partials and per-group max/min (+arg) of the raw output
-//   warp  4    : TMEM allocation, mbarrier init, single-thread tcgen05.mma issue
-//   warps 5-12 : A-operand producers, two groups of four warps on alternating K chunks: coalesced
+// Persistent, warp-specialised CTA (one per SM), 17 warps:
+//   warps 0-7  : epilogue  (TMEM lanes 32*(w%4)..+31, two warps per quarter on alternating 32-column
+//                chunks): tcgen05.ld -> bias/addend -> Y, BN statistic partials and per-group max/min
+//                (+arg) of the raw output
+//   warp  8    : TMEM allocation, mbarrier init, single-thread tcgen05.mma issue
+//   warps 9-16 : A-operand producers, two groups of four warps on alternating K chunks: coalesced
 //                float4 loads of X, BN/ReLU prologue, hi/lo split, 128B-swizzled st.shared;
 //                one elected thread per chunk also issues the bulk-TMA (cp.async.bulk) copies of the
 //                pre-split, pre-swizzled weight tiles.
@@ -25,11 +26,12 @@ namespace usip {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                  // floats per K chunk (= one 128-byte swizzle row)
-constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_MMA_WARP = 4;
-constexpr int TC_PROD_WARP0 = 5;
+constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, on alternating 32-column chunks
+constexpr int TC_MMA_WARP = 8;
+constexpr int TC_PROD_WARP0 = 9;
 constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_PROD_WARP0 + TC_PROD_WARPS) * 32;   // 416
+constexpr int TC_THREADS = (TC_PROD_WARP0 + TC_PROD_WARPS) * 32;   // 544
+constexpr int TC_STAT_ROWS = 32;           // BN-statistic partials are emitted per 32-row warp slice
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,10 +102,10 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -163,21 +165,21 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COMBINE>
 struct TcSmem {
   static constexpr int A_STAGE = 2 * TC_BM * 128;                 // hi + lo
   static constexpr int B_STAGE = 2 * BN * 128;
   static constexpr int STAGE = A_STAGE + B_STAGE;
-  static constexpr int TRANS = TC_EPI_WARPS * 32 * 36 * 4;       // per-warp 32x36 transpose tile (16B-aligned rows)
-  static constexpr int COMB = (BN <= 128 ? 6 : 2) * TC_EPI_WARPS * BN * 4;   // sum, sumsq (+ max, min, args for group > 32)
+  static constexpr int TRANS = TC_EPI_WARPS * 32 * 32 * 4;       // per-warp 32x32 staging tile, XOR-swizzled 16B chunks
+  static constexpr int COMB = COMBINE ? 4 * 4 * BN * 4 : 0;      // max, min, argmax, argmin per lane quarter (group > 32 only)
   static constexpr int BARS = 256;
   static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + BARS + 1024;   // +1024 alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COMBINE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack) {
-  using SM = TcSmem<BN, STAGES>;
+  using SM = TcSmem<BN, STAGES, COMBINE>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -305,12 +307,14 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       }
     }
   } else {
-    // =============================== epilogue warps 0..3 ========================================
-    const int q = warp;                               // TMEM lane quarter
-    float* tw = trans + q * (32 * 36);
+    // =============================== epilogue warps 0..7 ========================================
+    const int q = warp & 3;                           // TMEM lane quarter
+    const int half = warp >> 2;                       // handles chunks with (ch & 1) == half
+    float* tw = trans + warp * (32 * 32);
     const int g = d.group;
     const bool want_stats = d.stat_partial != nullptr;
     const bool want_grp = (d.gmax != nullptr) || (d.gmin != nullptr);
+    // staging tile addressing: element (r, c) lives at r*32 + (((c>>2) ^ (r&7))<<2) + (c&3)
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -329,28 +333,32 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half; ch < BN / 32; ch += 2) {
+        const int cb = n0 + ch * 32;
+        // TMEM read and the addend gather are issued back to back so their latencies overlap
         float v[32];
         tmem_ld_32x32(taddr + ch * 32, v);
-        const int cb = n0 + ch * 32;
+        float4 a4[8];
+        if (addp) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(addp + ch * 32) + j);
+        }
+        tmem_ld_wait();
         if (d.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + cb + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + cb) + j);
+            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
         }
         if (addp) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 a4 = __ldg(reinterpret_cast<const float4*>(addp + ch * 32 + j));
-            v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-          }
+          for (int j = 0; j < 8; ++j) { v[4 * j] += a4[j].x; v[4 * j + 1] += a4[j].y; v[4 * j + 2] += a4[j].z; v[4 * j + 3] += a4[j].w; }
         }
-        // stage the 32x32 chunk in shared memory (conflict-free 128-bit stores, row stride 36 floats)
+        // stage the 32x32 chunk in shared memory: row = lane, 16-byte chunk j stored at chunk (j ^ (lane & 7))
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(tw + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tw + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         if (d.Y) {
           // coalesced stores: 8 lanes cover one 128-byte row segment, a warp instruction writes 4 full lines
@@ -359,22 +367,40 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + rsub;
             if (r < nvalid) {
-              const float4 o = *reinterpret_cast<const float4*>(tw + r * 36 + l8 * 4);
+              const float4 o = *reinterpret_cast<const float4*>(tw + r * 32 + ((l8 ^ (r & 7)) << 2));
               *reinterpret_cast<float4*>(d.Y + (size_t)(wrow0 + r) * d.ldy + cb + l8 * 4) = o;
             }
           }
         }
-        if (want_stats || want_grp) {
+        // column view: lane owns column cb + lane; element (r, lane) at r*32 + (((lane>>2) ^ (r&7))<<2) + (lane&3)
+        const int cl = ch * 32 + lane;                // column inside the tile
+        const int csub = lane & 3, cchunk = lane >> 2;
+        if (want_stats && !want_grp) {
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          if (nvalid == 32) {
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+              const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub];
+              const float x1 = tw[(r + 1) * 32 + ((cchunk ^ ((r + 1) & 7)) << 2) + csub];
+              s0 += x0; q0 = fmaf(x0, x0, q0); s1 += x1; q1 = fmaf(x1, x1, q1);
+            }
+          } else {
+            for (int r = 0; r < nvalid; ++r) { const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub]; s0 += x0; q0 = fmaf(x0, x0, q0); }
+          }
+          const size_t st = (size_t)(mt * 4 + q);
+          d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s0 + s1;
+          d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = q0 + q1;
+        } else if (want_grp) {
           float s = 0.f, ss = 0.f;
           float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
           int ax0 = 0, an0 = 0, ax1 = 0, an1 = 0;
-          const int half = (g == 16) ? 16 : 32;       // rows per in-warp group segment
+          const int hrows = (g == 16) ? 16 : 32;      // rows per in-warp group segment
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const float x = tw[r * 36 + lane];
+            const float x = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub];
             const bool ok = r < nvalid;
             if (ok) { s += x; ss = fmaf(x, x, ss); }
-            if (r < half) {
+            if (r < hrows) {
               if (ok && x > mx0) { mx0 = x; ax0 = r; }
               if (ok && x < mn0) { mn0 = x; an0 = r; }
             } else {
@@ -382,36 +408,37 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
               if (ok && x < mn1) { mn1 = x; an1 = r; }
             }
           }
-          const int cl = ch * 32 + lane;              // column inside the tile
-          if (want_stats) { comb[(0 * 4 + q) * BN + cl] = s; comb[(1 * 4 + q) * BN + cl] = ss; }
-          if (want_grp) {
-            if (g == 16) {
-              const int grow = wrow0 / 16;
-              if (nvalid > 0) {
-                if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
-                if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
-                if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
-                if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
-              }
-              if (nvalid > 16) {
-                if (d.gmax) d.gmax[(size_t)(grow + 1) * Cout + cb + lane] = mx1;
-                if (d.gmin) d.gmin[(size_t)(grow + 1) * Cout + cb + lane] = mn1;
-                if (d.garg_max) d.garg_max[(size_t)(grow + 1) * Cout + cb + lane] = ax1 - 16;
-                if (d.garg_min) d.garg_min[(size_t)(grow + 1) * Cout + cb + lane] = an1 - 16;
-              }
-            } else if (g == 32) {
-              if (nvalid > 0) {
-                const int grow = wrow0 / 32;
-                if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
-                if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
-                if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
-                if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
-              }
-            } else {                                    // 64 / 128: combine across warps below
-              comb[(2 * 4 + q) * BN + cl] = mx0; comb[(3 * 4 + q) * BN + cl] = mn0;
-              reinterpret_cast<int*>(comb)[(4 * 4 + q) * BN + cl] = q * 32 + ax0;
-              reinterpret_cast<int*>(comb)[(5 * 4 + q) * BN + cl] = q * 32 + an0;
+          if (want_stats) {
+            const size_t st = (size_t)(mt * 4 + q);
+            d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s;
+            d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = ss;
+          }
+          if (g == 16) {
+            const int grow = wrow0 / 16;
+            if (nvalid > 0) {
+              if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
+              if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
+              if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
+              if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
             }
+            if (nvalid > 16) {
+              if (d.gmax) d.gmax[(size_t)(grow + 1) * Cout + cb + lane] = mx1;
+              if (d.gmin) d.gmin[(size_t)(grow + 1) * Cout + cb + lane] = mn1;
+              if (d.garg_max) d.garg_max[(size_t)(grow + 1) * Cout + cb + lane] = ax1 - 16;
+              if (d.garg_min) d.garg_min[(size_t)(grow + 1) * Cout + cb + lane] = an1 - 16;
+            }
+          } else if (g == 32) {
+            if (nvalid > 0) {
+              const int grow = wrow0 / 32;
+              if (d.gmax) d.gmax[(size_t)grow * Cout + cb + lane] = mx0;
+              if (d.gmin) d.gmin[(size_t)grow * Cout + cb + lane] = mn0;
+              if (d.garg_max) d.garg_max[(size_t)grow * Cout + cb + lane] = ax0;
+              if (d.garg_min) d.garg_min[(size_t)grow * Cout + cb + lane] = an0;
+            }
+          } else if (COMBINE) {                       // 64 / 128: combine the lane quarters below
+            comb[(0 * 4 + q) * BN + cl] = mx0; comb[(1 * 4 + q) * BN + cl] = mn0;
+            reinterpret_cast<int*>(comb)[(2 * 4 + q) * BN + cl] = q * 32 + ax0;
+            reinterpret_cast<int*>(comb)[(3 * 4 + q) * BN + cl] = q * 32 + an0;
           }
         }
         __syncwarp();                                   // tw is rewritten by the next chunk
@@ -420,33 +447,23 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
-      if (want_stats || (want_grp && g > 32)) {
+      if (COMBINE && want_grp && g > 32) {
         named_bar_sync(1, TC_EPI_WARPS * 32);
-        const int t = threadIdx.x;                     // 0..127
-        for (int cl = t; cl < BN; cl += TC_EPI_WARPS * 32) {
-          if (want_stats) {
-            float s = 0.f, ss = 0.f;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) { s += comb[(0 * 4 + w) * BN + cl]; ss += comb[(1 * 4 + w) * BN + cl]; }
-            d.stat_partial[((size_t)mt * 2 + 0) * Cout + n0 + cl] = s;
-            d.stat_partial[((size_t)mt * 2 + 1) * Cout + n0 + cl] = ss;
-          }
-          if (want_grp && g > 32) {
-            const int wpg = g / 32;                    // warps per group: 2 or 4
-            for (int gi = 0; gi < 4 / wpg; ++gi) {
-              const int grow = row0 / g + gi;
-              if ((size_t)grow * g >= (size_t)P) break;
-              float mx = -INFINITY, mn = INFINITY; int ax = 0, an = 0;
-              for (int w = gi * wpg; w < (gi + 1) * wpg; ++w) {
-                float a = comb[(2 * 4 + w) * BN + cl], b = comb[(3 * 4 + w) * BN + cl];
-                if (a > mx) { mx = a; ax = reinterpret_cast<int*>(comb)[(4 * 4 + w) * BN + cl]; }
-                if (b < mn) { mn = b; an = reinterpret_cast<int*>(comb)[(5 * 4 + w) * BN + cl]; }
-              }
-              if (d.gmax) d.gmax[(size_t)grow * Cout + n0 + cl] = mx;
-              if (d.gmin) d.gmin[(size_t)grow * Cout + n0 + cl] = mn;
-              if (d.garg_max) d.garg_max[(size_t)grow * Cout + n0 + cl] = ax - gi * g;
-              if (d.garg_min) d.garg_min[(size_t)grow * Cout + n0 + cl] = an - gi * g;
+        const int wpg = g / 32;                        // lane quarters per group: 2 or 4
+        for (int cl = threadIdx.x; cl < BN; cl += TC_EPI_WARPS * 32) {
+          for (int gi = 0; gi < 4 / wpg; ++gi) {
+            const int grow = row0 / g + gi;
+            if ((size_t)grow * g >= (size_t)P) break;
+            float mx = -INFINITY, mn = INFINITY; int ax = 0, an = 0;
+            for (int w = gi * wpg; w < (gi + 1) * wpg; ++w) {
+              const float a = comb[(0 * 4 + w) * BN + cl], b = comb[(1 * 4 + w) * BN + cl];
+              if (a > mx) { mx = a; ax = reinterpret_cast<int*>(comb)[(2 * 4 + w) * BN + cl]; }
+              if (b < mn) { mn = b; an = reinterpret_cast<int*>(comb)[(3 * 4 + w) * BN + cl]; }
             }
+            if (d.gmax) d.gmax[(size_t)grow * Cout + n0 + cl] = mx;
+            if (d.gmin) d.gmin[(size_t)grow * Cout + n0 + cl] = mn;
+            if (d.garg_max) d.garg_max[(size_t)grow * Cout + n0 + cl] = ax - gi * g;
+            if (d.garg_min) d.garg_min[(size_t)grow * Cout + n0 + cl] = an - gi * g;
           }
         }
         named_bar_sync(1, TC_EPI_WARPS * 32);          // comb is reused by the next tile
@@ -463,25 +480,26 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COMBINE>
 static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
-  using SM = TcSmem<BN, STAGES>;
+  using SM = TcSmem<BN, STAGES, COMBINE>;
   static_assert(SM::BYTES <= 232448, "shared memory budget");
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
     if (e != cudaSuccess) { sm_count = 0; set_last_error("layer_fwd_tc smem attr"); return (int)e; }
   }
   const int m_tiles = cdiv(d.P, TC_BM), n_tiles = d.Cout / BN;
   const int grid = min(sm_count, m_tiles * n_tiles);
-  layer_fwd_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
+  layer_fwd_tc_kernel<BN, STAGES, COMBINE><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
   return check_launch("layer_fwd_tc_kernel");
 }
 
 int tc_tile_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
+int tc_stat_rows() { return TC_STAT_ROWS; }
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   USIP_REQUIRE(d.Cin % TC_BK == 0 && d.Cout % 64 == 0, "layer_fwd_tc: needs Cin%32==0 and Cout%64==0");
@@ -495,6 +513,8 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   if (d.gmax || d.gmin) USIP_REQUIRE(d.group == 16 || d.group == 32 || d.group == 64 || d.group == 128, "layer_fwd_tc: group must be 16/32/64/128");
   int BN = tc_tile_n(d.Cout);
   if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
+  // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
+  while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {
     const int total = d.Cout * (d.Cin / 4);
@@ -502,9 +522,11 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
     int e = check_launch("tc_pack_weights_kernel");
     if (e) return e;
   }
-  if (BN == 256) return launch_tc<256, 2>(d, wpack, st);
-  if (BN == 128) return launch_tc<128, 3>(d, wpack, st);
-  return launch_tc<64, 4>(d, wpack, st);
+  const bool combine = (d.gmax || d.gmin) && d.group > 32;
+  if (combine) return BN == 128 ? launch_tc<128, 2, true>(d, wpack, st) : launch_tc<64, 3, true>(d, wpack, st);
+  if (BN == 256) return launch_tc<256, 2, false>(d, wpack, st);
+  if (BN == 128) return launch_tc<128, 3, false>(d, wpack, st);
+  return launch_tc<64, 4, false>(d, wpack, st);
 }
 
 }  // namespace usip

@@ -65,6 +65,23 @@ class BNState:
     __slots__ = ("scale", "shift", "mean", "invstd", "count")
 
 
+# Packed (hi/lo TF32, pre-swizzled) weight tiles are cached per weight view and re-used while the parameter's
+# autograd version counter is unchanged (inference / fwd-only loops); an optimizer step bumps the version and the
+# next launch re-packs into the same workspace.
+_TC_WS = {}
+
+
+def _tc_workspace(W, P, Cin, Cout, group, transposed):
+    key = (W.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32, W.device.index)
+    ver = W._version
+    ent = _TC_WS.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1], True
+    ws = ent[1] if ent is not None else torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device)
+    _TC_WS[key] = (ver, ws)
+    return ws, False
+
+
 def _precision_for(P, Cin, Cout, use_tc):
     return 1 if (use_tc and Cin % 32 == 0 and Cout % 64 == 0 and P >= 1024) else 0
 
@@ -78,6 +95,7 @@ class LayerRunner:
         self.use_tc = use_tc
         self.dev = dev
         self.tile = ops.tile_rows()
+        self.stat_rows = (ops.stat_rows(0), ops.stat_rows(1))
 
     def bn_state(self, norm, part, ntiles, count, momentum):
         C = norm.weight.numel()
@@ -96,8 +114,9 @@ class LayerRunner:
                                st.scale, st.shift)
         return st
 
-    def partials(self, P, Cout):
-        ntiles = (P + self.tile - 1) // self.tile
+    def partials(self, P, Cout, prec=0):
+        rows = self.stat_rows[prec]
+        ntiles = (P + rows - 1) // rows
         if not self.training:
             return None, ntiles
         return torch.empty((ntiles, 2, Cout), dtype=f32, device=self.dev), ntiles
@@ -108,7 +127,8 @@ class LayerRunner:
         Cout, Cin = W.shape
         if Y is None and write_y:
             Y = torch.empty((P, Cout), dtype=f32, device=self.dev)
-        part, ntiles = self.partials(P, Cout) if norm is not None else (None, 0)
+        prec = _precision_for(P, Cin, Cout, self.use_tc)
+        part, ntiles = self.partials(P, Cout, prec) if norm is not None else (None, 0)
         grp = None
         if want_group:
             Q = P // group
@@ -117,7 +137,7 @@ class LayerRunner:
             if want_arg:
                 grp["amax"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
                 grp["amin"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
-        prec = _precision_for(P, Cin, Cout, self.use_tc)
+        ws, packed = _tc_workspace(W, P, Cin, Cout, group if want_group else 0, False) if prec else (None, False)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(X, W, bias, P, Cin, Cout,
@@ -128,7 +148,7 @@ class LayerRunner:
                           gmax=None if grp is None else grp["gmax"], gmin=None if grp is None else grp["gmin"],
                           garg_max=None if grp is None else grp.get("amax"),
                           garg_min=None if grp is None else grp.get("amin"),
-                          group=group, precision=prec)
+                          group=group, precision=prec, tc_ws=ws, tc_packed=packed)
         st = None
         if norm is not None:
             with _Prof("bn_finalize"):
@@ -322,9 +342,10 @@ class _Bwd:
         if out is None:
             out = torch.empty((P, Cin), dtype=f32, device=self.dev)
         prec = _precision_for(P, Cout, Cin, self.use_tc)
+        ws, packed = _tc_workspace(W2d, P, Cout, Cin, 0, True) if prec else (None, False)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
-            ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True)
+            ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed)
         return out
 
     def colsum(self, G, out, P, C):

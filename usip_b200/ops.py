@@ -33,6 +33,10 @@ def tile_rows():
     return _lib.load().usip_layer_tile_rows()
 
 
+def stat_rows(precision):
+    return _lib.load().usip_layer_stat_rows(int(precision))
+
+
 # ----------------------------------------------------------------------------- reference operators
 def index_max(data, index, K):
     """(B,C,N) f32, (B,N) i32 -> (B,C,K) i32.  index_max.forward_cuda_shared_mem semantics."""
