@@ -127,7 +127,7 @@ def test_detector_train_step_vs_reference_golden(fname, use_tc):
         assert diff.max() <= 2.2e-3, (k, diff.max())
         if k.endswith("conv.bias") and float(g["grad/" + k][3]) < 1e-3 * max(float(g["grad/" + k.replace("bias", "weight")][3]), 1e-12):
             continue      # bias feeding a train-mode BN: true gradient 0, reference has rounding noise
-        solid = np.abs(gref[:n]) > 1e-5
+        solid = np.abs(gref[:n]) > max(1e-5, 1e-2 * float(g["grad/" + k][2]))     # well above our 5e-3*absmax gradient tolerance
         assert np.all(diff[solid] <= 2e-5 + 2e-4 * np.abs(ref[3:3 + n][solid])), (k, diff, gref[:n])
     print("worst gradient rel err", worst)
 

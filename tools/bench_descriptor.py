@@ -53,7 +53,7 @@ def main():
     out["ball_group_fused"] = {"ms_median": med, "ms_min": best, "algorithmic_bytes": alg_bytes,
                                "achieved_GBs": alg_bytes / (med * 1e-3) / 1e9, "peak_GBs": pk["hbm_gbs"],
                                "frac": alg_bytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"],
-                               "note": "5 launches (bbox, bin count, scan, fill, query); L2 flushed between iterations"}
+                               "note": "2 launches (fused per-cloud grid build, query); L2 flushed between iterations"}
     # --- reference path for the same result: materialise (B,M,N) distances + reference ball_query kernel + gather
     rb = ref_ext("ball_query")
     if rb is not None:

@@ -226,6 +226,110 @@ bg_fill_kernel(const float* __restrict__ xyz, const BgGrid* __restrict__ grids, 
   sorted[(size_t)b * N + pos] = make_float4(p[n], p[N + n], p[2 * N + n], __int_as_float(n));
 }
 
+// Fused per-cloud preparation (one CTA per cloud): bounding box -> grid -> shared-memory cell histogram -> exclusive
+// scan -> cell-sorted point array + 32-byte AoS records.  Replaces bbox/count/scan/fill (4 launches + memset) when
+// the grid fits in shared memory.
+constexpr int BG_PREP_CELLS = 49152;      // int32 counters in dynamic shared memory (192 KB)
+
+__global__ void __launch_bounds__(1024)
+bg_prep_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, float radius, BgGrid* __restrict__ grids,
+               int32_t* __restrict__ cell_start, float4* __restrict__ sorted, float* __restrict__ rec, int S, int N) {
+  extern __shared__ int hist[];                          // [cells]
+  __shared__ float smin[3][32], smax[3][32];
+  __shared__ int wsum[32];
+  __shared__ BgGrid sg;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* p = xyz + (size_t)b * 3 * N;
+  // ---- phase 1: bounding box (+ AoS records)
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  bool bad = false;
+  for (int n = tid; n < N; n += 1024) {
+    const float x = p[n], y = p[N + n], z = p[2 * N + n];
+    bad |= !(fabsf(x) <= 1e30f) || !(fabsf(y) <= 1e30f) || !(fabsf(z) <= 1e30f);
+    mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x); mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
+    mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+    float r[8] = {x, y, z, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < S && c < 5; ++c) r[3 + c] = feat[((size_t)b * S + c) * N + n];
+    float4* rp = reinterpret_cast<float4*>(rec + ((size_t)b * N + n) * 8);
+    rp[0] = make_float4(r[0], r[1], r[2], r[3]); rp[1] = make_float4(r[4], r[5], r[6], r[7]);
+  }
+  const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    if (lane == 0) { smin[c][w] = anybad ? NAN : mn[c]; smax[c][w] = mx[c]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    BgGrid g; g.ok = 1;
+    float lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) {
+      lo[c] = INFINITY; hi[c] = -INFINITY;
+      for (int i = 0; i < 32; ++i) { if (smin[c][i] != smin[c][i]) g.ok = 0; lo[c] = fminf(lo[c], smin[c][i]); hi[c] = fmaxf(hi[c], smax[c][i]); }
+    }
+    if (!(radius >= 0.f) || !(radius <= 1e30f)) g.ok = 0;
+    const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float h = fmaxf(fmaxf(radius * 1.001f, ext * (1.0f / 126.0f)), 1e-6f);
+    int nx = 1, ny = 1, nz = 1;
+    if (g.ok) {
+      for (int it = 0; it < 64; ++it) {
+        nx = (int)floorf((hi[0] - lo[0]) / h) + 1; ny = (int)floorf((hi[1] - lo[1]) / h) + 1; nz = (int)floorf((hi[2] - lo[2]) / h) + 1;
+        if ((long long)nx * ny * nz <= BG_PREP_CELLS) break;
+        h *= 1.26f;
+      }
+      if ((long long)nx * ny * nz > BG_PREP_CELLS) g.ok = 0;
+    }
+    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = 1.0f / h; g.nx = nx; g.ny = ny; g.nz = nz;
+    sg = g; grids[b] = g;
+  }
+  __syncthreads();
+  const BgGrid g = sg;
+  if (!g.ok) return;
+  const int cells = g.nx * g.ny * g.nz;
+  // ---- phase 2: histogram in shared memory
+  for (int i = tid; i < cells; i += 1024) hist[i] = 0;
+  __syncthreads();
+  for (int n = tid; n < N; n += 1024) {
+    const int cell = (bg_cell1(p[2 * N + n], g.oz, g.inv_h, g.nz) * g.ny + bg_cell1(p[N + n], g.oy, g.inv_h, g.ny)) * g.nx +
+                     bg_cell1(p[n], g.ox, g.inv_h, g.nx);
+    atomicAdd(&hist[cell], 1);
+  }
+  __syncthreads();
+  // ---- phase 3: exclusive scan (thread slice -> warp scan -> block)
+  const int per = (cells + 1023) / 1024, lo = min(tid * per, cells), hi = min(lo + per, cells);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += hist[i];
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    wsum[lane] = iv - v;                                 // exclusive warp offsets
+  }
+  __syncthreads();
+  int run = wsum[w] + incl - s;
+  int32_t* cs = cell_start + (size_t)b * (BG_MAX_CELLS + 1);
+  for (int i = lo; i < hi; ++i) { const int v = hist[i]; hist[i] = run; cs[i] = run; run += v; }
+  if (tid == 0) cs[cells] = N;
+  __syncthreads();
+  // ---- phase 4: fill the cell-sorted array (hist is now the running cursor)
+  float4* sp = sorted + (size_t)b * N;
+  for (int n = tid; n < N; n += 1024) {
+    const float x = p[n], y = p[N + n], z = p[2 * N + n];
+    const int cell = (bg_cell1(z, g.oz, g.inv_h, g.nz) * g.ny + bg_cell1(y, g.oy, g.inv_h, g.ny)) * g.nx + bg_cell1(x, g.ox, g.inv_h, g.nx);
+    const int pos = atomicAdd(&hist[cell], 1);
+    sp[pos] = make_float4(x, y, z, __int_as_float(n));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 bg_query_kernel(const float* __restrict__ xyz, const float* __restrict__ centers, const BgGrid* __restrict__ grids,
                 const int32_t* __restrict__ cell_start, const float4* __restrict__ sorted, const float* __restrict__ rec,
@@ -250,33 +354,41 @@ bg_query_kernel(const float* __restrict__ xyz, const float* __restrict__ centers
     const int x0 = max(kx - 1, 0), x1 = min(kx + 1, g.nx - 1);
     const int32_t* cs = cell_start + (size_t)b * (BG_MAX_CELLS + 1);
     const float4* sp = sorted + (size_t)b * N;
-    if (cfin && x0 <= x1)
-      for (int dz = -1; dz <= 1 && !brute; ++dz) {
-        const int z = kz + dz;
-        if (z < 0 || z >= g.nz) continue;
-        for (int dy = -1; dy <= 1 && !brute; ++dy) {
-          const int y = ky + dy;
-          if (y < 0 || y >= g.ny) continue;
-          const int base = (z * g.ny + y) * g.nx;
-          const int s = cs[base + x0], e = cs[base + x1 + 1];
-          for (int i = s; i < e; i += 32) {
-            const int j = i + lane;
-            bool hit = false; int n = 0;
-            if (j < e) {
-              const float4 q = sp[j];
-              n = __float_as_int(q.w);
-              hit = sqdist_rn(cx, cy, cz, q.x, q.y, q.z) <= t_max;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (bal) {
-              const int pos = cnt + __popc(bal & lt);
-              if (hit && pos < BG_CAP) hl[pos] = n;
-              cnt += __popc(bal);
-              if (cnt > BG_CAP) { brute = true; break; }
-            }
-          }
-        }
+    // lanes 0..8 fetch the bounds of the 9 x-contiguous ranges in one round trip
+    int rs = 0, rn = 0;
+    if (lane < 9 && cfin && x0 <= x1) {
+      const int y = ky + (lane % 3) - 1, z = kz + (lane / 3) - 1;
+      if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        const int base = (z * g.ny + y) * g.nx;
+        rs = cs[base + x0]; rn = cs[base + x1 + 1] - rs;
       }
+    }
+    int incl = rn;                                       // inclusive prefix of the range lengths over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 8);
+    int pre[9], st[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) { pre[r] = __shfl_sync(0xffffffffu, incl - rn, r); st[r] = __shfl_sync(0xffffffffu, rs, r); }
+    for (int base = 0; base < total; base += 32) {
+      const int j = base + lane;
+      bool hit = false; int n = 0;
+      if (j < total) {
+        int src = st[0] + j;
+#pragma unroll
+        for (int r = 1; r < 9; ++r) if (j >= pre[r]) src = st[r] + (j - pre[r]);
+        const float4 q = sp[src];
+        n = __float_as_int(q.w);
+        hit = sqdist_rn(cx, cy, cz, q.x, q.y, q.z) <= t_max;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        const int pos = cnt + __popc(bal & lt);
+        if (hit && pos < BG_CAP) hl[pos] = n;
+        cnt += __popc(bal);
+        if (cnt > BG_CAP) { brute = true; break; }
+      }
+    }
   }
   if (brute) {
     // early-exit in-order scan (exactly the reference loop); used for dense balls / degenerate grids
@@ -402,12 +514,13 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
     return check_launch("ball_group_brute_kernel");
   }
   BgScratch sc(scratch, B, N);
-  cudaMemsetAsync(sc.cell_cnt, 0, sizeof(int32_t) * (size_t)B * (BG_MAX_CELLS + 1), st);
-  bg_bbox_kernel<<<B, 1024, 0, st>>>(xyz, radius, sc.grids, N);
-  dim3 gp(cdiv(N, 256), B);
-  bg_count_kernel<<<gp, 256, 0, st>>>(xyz, feat, sc.grids, sc.cell_of, sc.cell_cnt, sc.rec, S, N);
-  bg_scan_kernel<<<B, 1024, 0, st>>>(sc.cell_cnt, sc.cell_fill, sc.grids);
-  bg_fill_kernel<<<gp, 256, 0, st>>>(xyz, sc.grids, sc.cell_of, sc.cell_cnt, sc.cell_fill, sc.sorted, N);
+  static bool prep_attr = false;
+  if (!prep_attr) {
+    cudaError_t e = cudaFuncSetAttribute(bg_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_PREP_CELLS * 4);
+    if (e != cudaSuccess) { set_last_error("bg_prep smem attr"); return (int)e; }
+    prep_attr = true;
+  }
+  bg_prep_kernel<<<B, 1024, BG_PREP_CELLS * 4, st>>>(xyz, feat, radius, sc.grids, sc.cell_cnt, sc.sorted, sc.rec, S, N);
   bg_query_kernel<<<cdiv(rows, 8), 256, 0, st>>>(xyz, centers, sc.grids, sc.cell_cnt, sc.sorted, sc.rec, t_max, out_idx,
                                                  out_group, out_rows, ld_rows, B, S, N, M, K);
   return check_launch("ball_group_grid");

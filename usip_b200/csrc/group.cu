@@ -87,6 +87,50 @@ sort_hist_kernel(const int32_t* __restrict__ min_idx, int32_t* __restrict__ hist
   if (key >= 0 && !later) h[key] = rank + 1;
 }
 
+// Warp-match variants (M <= 4096): per-warp key counts in shared memory instead of the O(chunk^2) rank loop.
+__global__ void __launch_bounds__(SORT_CHUNK)
+sort_hist_match_kernel(const int32_t* __restrict__ min_idx, int32_t* __restrict__ hist, int N, int M, int chunks) {
+  extern __shared__ unsigned short cnt[];               // [8][M]
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 8 * M; i += SORT_CHUNK) cnt[i] = 0;
+  __syncthreads();
+  const int n = chunk * SORT_CHUNK + tid;
+  const int key = n < N ? min_idx[(size_t)b * N + n] : -1 - tid;
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  if (key >= 0 && (m & ((1u << lane) - 1u)) == 0) cnt[w * M + key] = (unsigned short)__popc(m);
+  __syncthreads();
+  int32_t* h = hist + ((size_t)b * chunks + chunk) * M;
+  for (int mm = tid; mm < M; mm += SORT_CHUNK) {
+    int s = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += cnt[ww * M + mm];
+    h[mm] = s;
+  }
+}
+
+__global__ void __launch_bounds__(SORT_CHUNK)
+sort_place_match_kernel(const int32_t* __restrict__ min_idx, const int32_t* __restrict__ hist,
+                        const int32_t* __restrict__ seg_off, int32_t* __restrict__ perm,
+                        int32_t* __restrict__ row_seg, int N, int M, int chunks) {
+  extern __shared__ unsigned short cnt[];               // [8][M]
+  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 8 * M; i += SORT_CHUNK) cnt[i] = 0;
+  __syncthreads();
+  const int n = chunk * SORT_CHUNK + tid;
+  const int key = n < N ? min_idx[(size_t)b * N + n] : -1 - tid;
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  const int below = __popc(m & ((1u << lane) - 1u));
+  if (key >= 0 && below == 0) cnt[w * M + key] = (unsigned short)__popc(m);
+  __syncthreads();
+  if (key >= 0) {
+    int rank = below;
+    for (int ww = 0; ww < w; ++ww) rank += cnt[ww * M + key];
+    const int pos = seg_off[(size_t)b * (M + 1) + key] + hist[((size_t)b * chunks + chunk) * M + key] + rank;
+    perm[(size_t)b * N + pos] = n;
+    row_seg[(size_t)b * N + pos] = b * M + key;
+  }
+}
+
 __global__ void __launch_bounds__(1024)
 sort_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ seg_off, int N, int M, int chunks) {
   extern __shared__ int tot[];          // M totals, then 1024 partials
@@ -417,12 +461,23 @@ extern "C" int usip_cluster_sort(const int32_t* min_idx, int32_t* seg_off, int32
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = cdiv(N, SORT_CHUNK);
   dim3 grid(chunks, B);
-  sort_hist_kernel<<<grid, SORT_CHUNK, 0, st>>>(min_idx, scratch, N, M, chunks);
+  const bool match = M <= 4096;
+  const size_t msm = (size_t)8 * M * sizeof(unsigned short);
+  if (match) {
+    if (msm > 48 * 1024) {
+      cudaFuncSetAttribute(sort_hist_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+      cudaFuncSetAttribute(sort_place_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+    }
+    sort_hist_match_kernel<<<grid, SORT_CHUNK, msm, st>>>(min_idx, scratch, N, M, chunks);
+  } else {
+    sort_hist_kernel<<<grid, SORT_CHUNK, 0, st>>>(min_idx, scratch, N, M, chunks);
+  }
   size_t smem = (size_t)(M + 1024) * sizeof(int);
   USIP_REQUIRE(smem <= 200 * 1024, "cluster_sort: M too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(sort_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   sort_scan_kernel<<<B, 1024, smem, st>>>(scratch, seg_off, N, M, chunks);
-  sort_place_kernel<<<grid, SORT_CHUNK, 0, st>>>(min_idx, scratch, seg_off, perm, row_seg, N, M, chunks);
+  if (match) sort_place_match_kernel<<<grid, SORT_CHUNK, msm, st>>>(min_idx, scratch, seg_off, perm, row_seg, N, M, chunks);
+  else sort_place_kernel<<<grid, SORT_CHUNK, 0, st>>>(min_idx, scratch, seg_off, perm, row_seg, N, M, chunks);
   return check_launch("cluster_sort");
 }
 

@@ -6,22 +6,24 @@
 namespace usip {
 
 constexpr int PM_THREADS = 256;
-constexpr int PM_TILE = 1024;   // database points staged per CTA (float4 each -> 16 KB)
+constexpr int PM_Q = 128;       // queries per CTA (two threads per query, each on half of the tile)
+constexpr int PM_TILE = 512;    // database points staged per CTA (float4 each -> 8 KB)
 
 __global__ void pm_init_kernel(unsigned long long* packed, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) packed[i] = ~0ull;
 }
 
-// grid (ceil(Nb/PM_TILE), ceil(Ma/PM_THREADS), B): each thread owns one query a_i and scans one
-// shared-memory tile of b; partial results merge through a 64-bit atomicMin on (d2 bits << 32 | j),
-// which yields the first index among exact ties (d2 >= 0 so float bits order like uints).
+// grid (ceil(Nb/PM_TILE), ceil(Ma/PM_Q), B): thread = (query, tile half); partial results merge through a 64-bit
+// atomicMin on (d2 bits << 32 | j), which yields the first index among exact ties (d2 >= 0 so float bits order like
+// uints).  Small tiles keep the per-thread dependent min chain short and put >1000 CTAs on the machine.
 __global__ void __launch_bounds__(PM_THREADS)
 pairwise_min_kernel(const float* __restrict__ a, const float* __restrict__ b,
                     unsigned long long* __restrict__ packed, int Ma, int Nb) {
   __shared__ float4 sb[PM_TILE];
   const int bb = blockIdx.z;
-  const int i = blockIdx.y * PM_THREADS + threadIdx.x;
+  const int i = blockIdx.y * PM_Q + (threadIdx.x & (PM_Q - 1));
+  const int hf = threadIdx.x >> 7;
   const int j0 = blockIdx.x * PM_TILE;
   const int jc = min(PM_TILE, Nb - j0);
   const float* pb = b + (size_t)bb * 3 * Nb;
@@ -31,13 +33,19 @@ pairwise_min_kernel(const float* __restrict__ a, const float* __restrict__ b,
   if (i >= Ma) return;
   const float* pa = a + (size_t)bb * 3 * Ma;
   const float ax = pa[i], ay = pa[Ma + i], az = pa[2 * Ma + i];
-  float best = INFINITY; int bj = 0;
-#pragma unroll 4
-  for (int t = 0; t < jc; ++t) {
-    float4 q = sb[t];
-    float d = sqdist_rn(ax, ay, az, q.x, q.y, q.z);
-    if (d < best) { best = d; bj = t; }
+  const int t0 = hf * (PM_TILE / 2), t1 = min(jc, t0 + PM_TILE / 2);
+  float best0 = INFINITY, best1 = INFINITY; int bj0 = 0, bj1 = 0;
+  int t = t0;
+  for (; t + 1 < t1; t += 2) {                       // two independent chains
+    const float4 q0 = sb[t], q1 = sb[t + 1];
+    const float d0 = sqdist_rn(ax, ay, az, q0.x, q0.y, q0.z), d1 = sqdist_rn(ax, ay, az, q1.x, q1.y, q1.z);
+    if (d0 < best0) { best0 = d0; bj0 = t; }
+    if (d1 < best1) { best1 = d1; bj1 = t + 1; }
   }
+  if (t < t1) { const float4 q0 = sb[t]; const float d0 = sqdist_rn(ax, ay, az, q0.x, q0.y, q0.z); if (d0 < best0) { best0 = d0; bj0 = t; } }
+  // merge the chains: smaller distance, then smaller index
+  float best = best0; int bj = bj0;
+  if (best1 < best || (best1 == best && bj1 < bj)) { best = best1; bj = bj1; }
   if (best == best && best < INFINITY) {
     unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)(j0 + bj);
     atomicMin(&packed[(size_t)bb * Ma + i], key);
@@ -208,7 +216,7 @@ extern "C" int usip_pairwise_min_f32(const float* a, const float* b, float* min_
   cudaStream_t st = (cudaStream_t)stream;
   size_t n = (size_t)B * Ma;
   pm_init_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(packed, n);
-  dim3 grid(cdiv(Nb, PM_TILE), cdiv(Ma, PM_THREADS), B);
+  dim3 grid(cdiv(Nb, PM_TILE), cdiv(Ma, PM_Q), B);
   pairwise_min_kernel<<<grid, PM_THREADS, 0, st>>>(a, b, packed, Ma, Nb);
   pm_finish_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(packed, min_d, arg, n);
   return check_launch("pairwise_min");

@@ -392,6 +392,44 @@ __global__ void head_finalize_kernel(const float* __restrict__ out4, int ld, con
   sig[t] = (x > 20.f ? x : log1pf(expf(x))) + lb;                                                     // networks.py:72,154
 }
 
+// Narrow output layers (Cout <= 8, e.g. the 256->4 head): one warp per row, lanes stride over K, weights in shared
+// memory, warp-shuffle reduction.  Same prologue as the tiled kernels; no statistics / group epilogue.
+template <int NOUT>
+__global__ void __launch_bounds__(256)
+layer_fwd_rowwarp_kernel(const usip_layer_desc d) {
+  extern __shared__ float sw[];                         // [NOUT][Cin] weights, then scale/shift [2][Cin]
+  const int Cin = d.Cin, Cout = d.Cout;
+  for (int i = threadIdx.x; i < NOUT * Cin; i += 256) {
+    const int n = i / Cin, k = i - n * Cin;
+    sw[i] = n < Cout ? (d.w_transposed ? d.W[(size_t)k * d.ldw + n] : d.W[(size_t)n * d.ldw + k]) : 0.f;
+  }
+  float* ssc = sw + NOUT * Cin; float* ssh = ssc + Cin;
+  for (int k = threadIdx.x; k < Cin; k += 256) { ssc[k] = d.in_scale ? d.in_scale[k] : 1.f; ssh[k] = d.in_shift ? d.in_shift[k] : 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= d.P) return;
+  const float* x = d.X + (size_t)row * d.ldx;
+  float acc[NOUT];
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+  for (int k = lane; k < Cin; k += 32) {
+    float a = fmaf(x[k], ssc[k], ssh[k]);
+    if (d.in_relu) a = fmaxf(a, 0.f);
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(a, sw[n * Cin + k], acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane < Cout && lane < NOUT) {
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) if (lane == n) v = acc[n];
+    if (d.bias) v += d.bias[lane];
+    if (d.Y) d.Y[(size_t)row * d.ldy + lane] = v;
+  }
+}
+
 // descriptor / (||descriptor||_2 + 1e-5) over channels, [Q,C] rows -> reference (B,C,M) layout (networks.py:383)
 __global__ void __launch_bounds__(256)
 l2norm_to_bcm_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, float* __restrict__ norm_out, int B,
@@ -448,6 +486,11 @@ extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
   if (d.addend) USIP_REQUIRE(d.add_index || d.add_group > 0, "layer_fwd: addend needs add_index or add_group");
   cudaStream_t st = (cudaStream_t)stream;
   if (d.precision == 1) return layer_fwd_tc(d, st);
+  if (d.Cout <= 8 && !d.stat_partial && !d.gmax && !d.gmin && !d.addend && (size_t)(8 + 2) * d.Cin * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)(8 + 2) * d.Cin * sizeof(float);
+    layer_fwd_rowwarp_kernel<8><<<cdiv(d.P, 8), 256, smem, st>>>(d);
+    return check_launch("layer_fwd_rowwarp_kernel");
+  }
   if (d.Cout <= 64) return launch_layer_simt<64>(d, st);
   return launch_layer_simt<128>(d, st);
 }
