@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT layers only")
     ap.add_argument("--train", action="store_true", help="also time the full train step (fwd+loss+bwd+Adam)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     ap.add_argument("--nbatches", type=int, default=18, help="distinct resident input batches (18 x 7.3 MB > 126 MB L2)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -218,8 +219,9 @@ def main():
     # ---- kernel-path number: inputs resident in HBM
     def step_resident(i):
         assign(resident[i % nb])
-        md.forward_loss(epoch=0, train_bn=True)
+        md.forward_loss(epoch=0, train_bn=True, graph=use_graph)
 
+    use_graph = not args.no_graph
     for i in range(W):
         step_resident(i)
     sampler = ClockSampler(local); sampler.start()
@@ -232,7 +234,7 @@ def main():
     def step_e2e(i):
         b = pinned[i % nb]
         md.set_input(*[b[k] for k in KEYS])
-        md.forward_loss(epoch=0, train_bn=True)
+        md.forward_loss(epoch=0, train_bn=True, graph=use_graph)
         return md.loss.item()
 
     for i in range(3):
@@ -244,7 +246,8 @@ def main():
     # ---- per-op device times (CUDA events on the launching stream) for the roofline of the dominant kernel
     engine.PROFILE = {}
     for i in range(min(K, 10)):
-        step_resident(i)
+        assign(resident[i % nb])
+        md.forward_loss(epoch=0, train_bn=True, graph=False)    # eager: events around every op
     torch.cuda.synchronize()
     prof = engine.collect_profile()
     engine.PROFILE = None
@@ -297,7 +300,8 @@ def main():
                                        "N=16384, M=512, S=4, node_knn_k=16, train-mode BN, chamfer + 2x keypoint-on-pc",
                            "global_pairs": cfg["B"] * world, "parallelism": "dp%d (independent ranks, no collective on fwd+loss)" % world,
                            "l2": "inputs rotate over %d distinct resident batches (%.0f MB > 126 MB L2); activations per step ~1.5 GB" % (nb, nb * h2d_bytes / 1e6),
-                           "matmul_precision": "fp32 SIMT" if args.no_tc else "3xTF32 tcgen05 (fp32-equivalent) + fp32 SIMT for narrow layers"},
+                           "matmul_precision": "fp32 SIMT" if args.no_tc else "3xTF32 tcgen05 (fp32-equivalent) + fp32 SIMT for narrow layers",
+                           "launch": "CUDA-graph replay of the step (ModelDetector.forward_loss(graph=True))" if use_graph else "eager"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
         if roof:
             line["roofline"] = roof

@@ -152,3 +152,22 @@ def test_descriptor_forward_vs_reference_golden():
             assert np.array_equal(feats.cpu().numpy(), g[mode + "_feats"]), (mode, "x_features must be bit-exact")
             e = rel_err(desc.cpu().numpy(), g[mode + "_desc"])
             assert e < REL, (mode, use_tc, e)
+
+
+def test_forward_loss_cuda_graph_matches_eager():
+    """ModelDetector.forward_loss(graph=True) replays the captured launch sequence: results must equal the eager run
+    bit for bit (all kernels on the fwd+loss path are deterministic), also after the inputs change."""
+    g, d, P, md = _setup("detector_kitti_small.npz", True)
+    keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
+    d2 = orc.synth_pair(2, 2048, 64, 4, kind="lidar", seed=999)
+    for data in (d, d2, d):
+        md.set_input(*[torch.from_numpy(data[k]) for k in keys])
+        sd0 = {k: v.clone() for k, v in md.detector.state_dict().items()}
+        md.forward_loss(epoch=0, train_bn=True, graph=False)
+        eager = (md.loss.item(), torch.cat([md.src_keypoints, md.dst_keypoints]).clone(), torch.cat([md.src_sigmas, md.dst_sigmas]).clone())
+        md.detector.load_state_dict(sd0)                       # undo the running-stat update, same starting state
+        md.set_input(*[torch.from_numpy(data[k]) for k in keys])
+        md.forward_loss(epoch=0, train_bn=True, graph=True)
+        assert md.loss.item() == eager[0]
+        assert torch.equal(torch.cat([md.src_keypoints, md.dst_keypoints]), eager[1])
+        assert torch.equal(torch.cat([md.src_sigmas, md.dst_sigmas]), eager[2])

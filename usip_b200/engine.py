@@ -57,7 +57,17 @@ def collect_profile():
 
 
 def _w2d(w):
-    return w.detach().reshape(w.shape[0], -1)
+    """(Cout, Cin[,1[,1]]) conv weight -> [Cout, Cin] view that remembers its owning Parameter (packed-weight cache)."""
+    t = w.detach().reshape(w.shape[0], -1)
+    t._owner = w
+    return t
+
+
+def _cols(t, a, b=None):
+    """Column slice of a _w2d view (concat halves of a conv weight), keeping the owner."""
+    v = t[:, a:b]
+    v._owner = getattr(t, "_owner", None)
+    return v
 
 
 class BNState:
@@ -68,17 +78,18 @@ class BNState:
 # Packed (hi/lo TF32, pre-swizzled) weight tiles are cached per weight view and re-used while the parameter's
 # autograd version counter is unchanged (inference / fwd-only loops); an optimizer step bumps the version and the
 # next launch re-packs into the same workspace.
-_TC_WS = {}
-
-
 def _tc_workspace(W, P, Cin, Cout, group, transposed):
-    key = (W.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32, W.device.index)
-    ver = W._version
-    ent = _TC_WS.get(key)
-    if ent is not None and ent[0] == ver:
+    owner = getattr(W, "_owner", None)
+    if owner is None:                                  # unknown provenance: never reuse packed tiles
+        return torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device), False
+    cache = owner.__dict__.setdefault("_usip_tc", {})  # lives and dies with the Parameter object
+    key = (W.data_ptr() - owner.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32)
+    ver = owner._version
+    ent = cache.get(key)
+    if ent is not None and ent[0] == ver and ent[2] == owner.data_ptr():
         return ent[1], True
     ws = ent[1] if ent is not None else torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device)
-    _TC_WS[key] = (ver, ws)
+    cache[key] = (ver, ws, owner.data_ptr())
     return ws, False
 
 
@@ -210,8 +221,8 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     sp = net.second_pointnet.layers
     C1 = sp[0].conv.weight.shape[0]
     W3 = _w2d(sp[0].conv.weight)
-    V, _, _ = R.run(pool1, Q, W3[:, H:], None, relu_in=False, name="pn2.0_node")
-    Y3, bn3, _ = R.run(F1, P, W3[:, :H], sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
+    V, _, _ = R.run(pool1, Q, _cols(W3, H), None, relu_in=False, name="pn2.0_node")
+    Y3, bn3, _ = R.run(F1, P, _cols(W3, 0, H), sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
                        relu_in=False, addend=V, add_index=row_seg, name="pn2.0")
     F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3, name="pn2.1")
     # ---- pool 2 -> first C1 columns of the head input (networks.py:130-133,143)
@@ -228,7 +239,7 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
         knn_i = ops.knn_nodes(cmean, Kn)
     W5 = _w2d(kb[0].conv.weight)
     Cb = W5.shape[0]
-    Z, _, _ = R.run(pool2, Q, W5[:, 3:], None, relu_in=False, name="knn_b0_node")
+    Z, _, _ = R.run(pool2, Q, _cols(W5, 3), None, relu_in=False, name="knn_b0_node")
     Y5 = torch.empty((G, Cb), dtype=f32, device=dev)
     part5, nt5 = R.partials(G, Cb)
     with _Prof("knn_combine", nbytes=8.0 * G * Cb):
@@ -250,8 +261,8 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     with _Prof("group_select"):
         ops.group_select(grp_b["gmax"], grp_b["gmin"], prev.scale, prev.shift, amax, Q, Cb)
     W8 = _w2d(ka[0].conv.weight)
-    U, _, _ = R.run(amax, Q, W8[:, :Cb], None, relu_in=False, name="knn_a0_node")                                    # max half (layers.py:435)
-    Y8, bn8, _ = R.run(Yprev, G, W8[:, Cb:], ka[0].conv.bias.detach(), ka[0].norm, _bn_mom(ka[0].norm, epoch),
+    U, _, _ = R.run(amax, Q, _cols(W8, 0, Cb), None, relu_in=False, name="knn_a0_node")                                    # max half (layers.py:435)
+    Y8, bn8, _ = R.run(Yprev, G, _cols(W8, Cb), ka[0].conv.bias.detach(), ka[0].norm, _bn_mom(ka[0].norm, epoch),
                        prev=prev, addend=U, add_group=Kn, name="knn_a0")
     saved_after = [(Y8, bn8)]
     prevA, YA = bn8, Y8
@@ -418,12 +429,12 @@ def detector_backward(net, ctx, g_kp, g_sig):
     Yb_last, bnb_last = ctx["before"][-1]
     gW8 = bw.g2d(ka[0].conv.weight)
     bw.wgrad(GYa, Yb_last, gW8[:, Cb:], G, C2, Cb, prev=bnb_last, name="wgrad_knn_a0")
-    G_a7 = bw.dgrad(GYa, W8[:, Cb:], G, name="dgrad_knn_a0")               # [G, Cb]
+    G_a7 = bw.dgrad(GYa, _cols(W8, Cb), G, name="dgrad_knn_a0")               # [G, Cb]
     G_U = torch.empty((Q, C2), dtype=f32, device=dev)
     check(lib.usip_group_sum(p(GYa), GYa.stride(0), p(G_U), G_U.stride(0), Kn, Q, C2, s()), "usip_group_sum")
     del GYa
     bw.wgrad(G_U, ctx["amax"], gW8[:, :Cb], Q, C2, Cb, name="wgrad_knn_a0_node")
-    G_amax = bw.dgrad(G_U, W8[:, :Cb], Q, name="dgrad_knn_a0_node")        # [Q, Cb]
+    G_amax = bw.dgrad(G_U, _cols(W8, 0, Cb), Q, name="dgrad_knn_a0_node")        # [Q, Cb]
     # max path joins the dense gradient of a7 at the arg rows (ReLU mask is applied by bn_bwd below)
     _, arg7, _, _ = groupmax_select(G_amax, ctx["grp_b"], bnb_last, Q, Cb, False)
     check(lib.usip_groupmax_scatter_add(p(G_a7), G_a7.stride(0), p(G_amax), p(arg7), Kn, Q, Cb, s()), "usip_groupmax_scatter_add")
@@ -447,7 +458,7 @@ def detector_backward(net, ctx, g_kp, g_sig):
     del GYb
     pool2 = ctx["AGG"][:, :C1]
     bw.wgrad(G_Z, pool2, gW5[:, 3:], Q, Cb, C1, name="wgrad_knn_b0_node")
-    G_pool2_knn = bw.dgrad(G_Z, W5[:, 3:], Q, name="dgrad_knn_b0_node")    # [Q, C1]
+    G_pool2_knn = bw.dgrad(G_Z, _cols(W5, 3), Q, name="dgrad_knn_b0_node")    # [Q, C1]
     G_pool2_tot = G_pool2_knn
     G_pool2_tot += G_pool2                                                 # tiny [Q,C1] plumbing add
 
@@ -465,12 +476,12 @@ def detector_backward(net, ctx, g_kp, g_sig):
     W3 = _w2d(sp[0].conv.weight)
     gW3 = bw.g2d(sp[0].conv.weight)
     bw.wgrad(GY3, ctx["F1"], gW3[:, :H], P, C1, H, name="wgrad_pn2.0")
-    G_F1 = bw.dgrad(GY3, W3[:, :H], P, name="dgrad_pn2.0")                  # [P, H]
+    G_F1 = bw.dgrad(GY3, _cols(W3, 0, H), P, name="dgrad_pn2.0")                  # [P, H]
     G_V = torch.empty((Q, C1), dtype=f32, device=dev)
     check(lib.usip_seg_sum(p(GY3), GY3.stride(0), p(ctx["seg_off"]), p(G_V), G_V.stride(0), Bp, N, M, C1, s()), "usip_seg_sum")
     del GY3
     bw.wgrad(G_V, ctx["pool1"], gW3[:, H:], Q, C1, H, name="wgrad_pn2.0_node")
-    G_pool1 = bw.dgrad(G_V, W3[:, H:], Q, name="dgrad_pn2.0_node")          # [Q, H]
+    G_pool1 = bw.dgrad(G_V, _cols(W3, H), Q, name="dgrad_pn2.0_node")          # [Q, H]
     check(lib.usip_unpool_scatter(p(G_F1), G_F1.stride(0), p(G_pool1), G_pool1.stride(0), p(ctx["arg1"]), Q, H, 1, s()),
           "usip_unpool_scatter")
     # ---- first PointNet
@@ -524,8 +535,8 @@ def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, k
     amax = torch.empty((Q, D), dtype=f32, device=dev)
     ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
     W4 = _w2d(c4.conv.weight)
-    U, _, _ = R.run(amax, Q, W4[:, D:], None, relu_in=False, name="desc.conv4_node")        # cat(y_first, max): max is LAST
-    Y4, bn4, _ = R.run(Y3, G, W4[:, :D], c4.conv.bias.detach(), c4.norm, _bn_mom(c4.norm, epoch), prev=bn3, addend=U,
+    U, _, _ = R.run(amax, Q, _cols(W4, D), None, relu_in=False, name="desc.conv4_node")        # cat(y_first, max): max is LAST
+    Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, _bn_mom(c4.norm, epoch), prev=bn3, addend=U,
                        add_group=K, name="desc.conv4")
     _, _, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), prev=bn4, group=K, want_group=True,
                        write_y=False, name="desc.conv5")
