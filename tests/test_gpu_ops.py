@@ -331,3 +331,24 @@ def test_ball_group_grid_full_size_vs_reference_cuda():
 def ops_ball_group(pc, sn, kp, r, K):
     from usip_b200 import ops
     return ops.ball_group(pc.contiguous(), sn.contiguous(), kp.contiguous(), r, K, want_group=True, rows_ld=8)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("P,Cout,Cin", [(4096, 128, 64), (8192, 256, 256), (5000, 512, 512), (4100, 128, 128), (6144, 512, 640)])
+def test_wgrad(P, Cout, Cin, precision):
+    """gW += GY^T act(X): SIMT and tcgen05 (MN-major 3xTF32) kernels against fp64."""
+    from usip_b200 import _lib
+    from usip_b200.ops import _p, _stream
+    rng = np.random.default_rng(P + Cout)
+    GY = rng.normal(size=(P, Cout)).astype(np.float32)
+    X = rng.normal(size=(P, Cin)).astype(np.float32)
+    sc = rng.normal(size=Cin).astype(np.float32); sh = rng.normal(size=Cin).astype(np.float32)
+    gW = torch.zeros((Cout, Cin), device=dev())
+    gy, x, s_, h_ = cu(GY), cu(X), cu(sc), cu(sh)
+    _lib.check(_lib.load().usip_wgrad(_p(gy), Cout, _p(x), Cin, _p(s_), _p(h_), 1, _p(gW), Cin, P, Cout, Cin, precision,
+                                      _stream()), "usip_wgrad")
+    torch.cuda.synchronize()
+    A = np.maximum(X.astype(np.float64) * sc + sh, 0)
+    ref = GY.astype(np.float64).T @ A
+    e = rel_err(gW.cpu().numpy(), ref)
+    assert e < 2e-5, e

@@ -498,10 +498,19 @@ extern "C" int usip_head_bwd(const float* g_kp, const float* g_sig, const float*
   return check_launch("head_bwd_kernel");
 }
 
+namespace usip {
+int wgrad_tc(const float* GY, int ldg, const float* X, int ldx, const float* sc, const float* sh, int relu, float* gW,
+             int ldw, int P, int Cout, int Cin, cudaStream_t st);   // wgrad_tc.cu (-2: shape not eligible)
+}
+
 extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale,
                           const float* in_shift, int in_relu, float* gW, int ldw, int P, int Cout, int Cin,
-                          void* stream) {
+                          int precision, void* stream) {
   USIP_REQUIRE(GY && X && gW && P > 0 && Cout > 0 && Cin > 0 && (!in_scale == !in_shift), "wgrad: bad args");
+  if (precision == 1) {
+    int rc = wgrad_tc(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin, (cudaStream_t)stream);
+    if (rc != -2) return rc;
+  }
   const int tiles = cdiv(Cout, 128) * cdiv(Cin, 128);
   int splits = max(1, min(cdiv(P, 128), (148 * 4) / tiles));
   int rows = cdiv(cdiv(P, splits), WG_BK) * WG_BK;

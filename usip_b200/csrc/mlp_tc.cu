@@ -89,23 +89,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane).  The load is asynchronous: the
+// destination registers may only be read after tmem_ld_wait(), which also ties the registers ("+r") so the compiler
+// cannot hoist their uses above the wait.
+#define USIP_R32(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),          \
+    "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),         \
+    "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define USIP_RW32(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), \
+    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]),           \
+    "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]),          \
+    "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : USIP_R32(r)
       : "r"(taddr)
       : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : USIP_RW32(r) : : "memory");
+}
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t r;
@@ -203,7 +209,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
 
   if (warp == TC_MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 128 + 1); mbar_init(empty_bar(s), 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), TC_EPI_WARPS); }
       fence_barrier_init();
     }
@@ -270,8 +276,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
         fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar(s));
+        mbar_arrive(full_bar(s));                  // every producer thread arrives after fencing its own stores
       }
     }
   } else if (warp == TC_MMA_WARP) {
@@ -336,14 +341,17 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       for (int ch = half; ch < BN / 32; ch += 2) {
         const int cb = n0 + ch * 32;
         // TMEM read and the addend gather are issued back to back so their latencies overlap
-        float v[32];
-        tmem_ld_32x32(taddr + ch * 32, v);
+        uint32_t raw[32];
+        tmem_ld_32x32_issue(taddr + ch * 32, raw);
         float4 a4[8];
         if (addp) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(addp + ch * 32) + j);
         }
-        tmem_ld_wait();
+        tmem_ld_wait(raw);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         if (d.bias) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -342,10 +342,12 @@ class _Bwd:
 
     def wgrad(self, GY, X, gW, P, Cout, Cin, prev=None, relu=False, name="wgrad"):
         s = ops._stream(); p = ops._p
-        with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout, precision="fp32 SIMT"):
+        tc = self.use_tc and Cout % 128 == 0 and Cin % 64 == 0 and P >= 4096
+        with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
+                   precision="3xTF32 tcgen05" if tc else "fp32 SIMT"):
             self.check(self.lib.usip_wgrad(p(GY), GY.stride(0), p(X), X.stride(0), None if prev is None else p(prev.scale),
                                            None if prev is None else p(prev.shift), 1 if (relu or prev is not None) else 0,
-                                           p(gW), gW.stride(0), P, Cout, Cin, s), "usip_wgrad")
+                                           p(gW), gW.stride(0), P, Cout, Cin, 1 if self.use_tc else 0, s), "usip_wgrad")
 
     def dgrad(self, GY, W2d, P, name="dgrad", out=None):
         """G_in[P,Cin] = GY[P,Cout] @ W2d[Cout,Cin] (the forward weight, used transposed by the layer kernel)."""
