@@ -216,6 +216,17 @@ def main():
             ms = float(t.item())
         return ms, launches
 
+    # ---- per-op device times (CUDA events on the launching stream) for the roofline of the dominant kernel
+    for i in range(3):
+        assign(resident[i % nb]); md.forward_loss(epoch=0, train_bn=True, graph=False)
+    torch.cuda.synchronize()
+    engine.PROFILE = {}
+    for i in range(min(K, 10)):
+        assign(resident[i % nb])
+        md.forward_loss(epoch=0, train_bn=True, graph=False)    # eager: events around every op
+    torch.cuda.synchronize()
+    prof = engine.collect_profile()
+    engine.PROFILE = None
     # ---- kernel-path number: inputs resident in HBM
     def step_resident(i):
         assign(resident[i % nb])
@@ -243,14 +254,6 @@ def main():
     e2e = {"value": clouds * K / (ms_e2e * 1e-3), "unit": "clouds/s", "h2d_bytes_per_step": h2d_bytes,
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K}
 
-    # ---- per-op device times (CUDA events on the launching stream) for the roofline of the dominant kernel
-    engine.PROFILE = {}
-    for i in range(min(K, 10)):
-        assign(resident[i % nb])
-        md.forward_loss(epoch=0, train_bn=True, graph=False)    # eager: events around every op
-    torch.cuda.synchronize()
-    prof = engine.collect_profile()
-    engine.PROFILE = None
     roof = None
     pk = peaks()
     if prof:

@@ -395,9 +395,11 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           } else {
             for (int r = 0; r < nvalid; ++r) { const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub]; s0 += x0; q0 = fmaf(x0, x0, q0); }
           }
-          const size_t st = (size_t)(mt * 4 + q);
-          d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s0 + s1;
-          d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = q0 + q1;
+          if (nvalid > 0) {                          // slices entirely past P have no partial row
+            const size_t st = (size_t)(mt * 4 + q);
+            d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s0 + s1;
+            d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = q0 + q1;
+          }
         } else if (want_grp) {
           float s = 0.f, ss = 0.f;
           float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
@@ -416,7 +418,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
               if (ok && x < mn1) { mn1 = x; an1 = r; }
             }
           }
-          if (want_stats) {
+          if (want_stats && nvalid > 0) {
             const size_t st = (size_t)(mt * 4 + q);
             d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s;
             d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = ss;
