@@ -190,13 +190,15 @@ def _layer_ref(X, W, b, scale, shift, relu, addend, add_idx):
     return Y
 
 
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1, 3])
 @pytest.mark.parametrize("P,Cin,Cout,group", [(1000, 7, 64, 0), (4096, 64, 64, 16), (2048, 128, 128, 32),
                                               (1536, 256, 256, 16), (1024, 512, 512, 64), (700, 640, 512, 0),
-                                              (512, 256, 4, 0), (640, 131, 256, 0)])
+                                              (512, 256, 4, 0), (640, 131, 256, 0),
+                                              # enough 256x256 tiles for the CTA-pair (cta_group::2) kernel, ragged tails
+                                              (16512, 256, 256, 16), (8320, 512, 512, 32), (16400, 64, 256, 0)])
 def test_layer_fwd(P, Cin, Cout, group, precision):
     from usip_b200 import ops
-    if precision == 1 and not (Cin % 32 == 0 and Cout % 64 == 0):
+    if precision and not (Cin % 32 == 0 and Cout % 64 == 0):
         pytest.skip("tensor-core path needs Cin%32==0 and Cout%64==0")
     rng = np.random.default_rng(P + Cin)
     ldx = Cin + (8 - Cin % 8) % 8

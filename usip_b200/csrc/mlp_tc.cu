@@ -20,130 +20,16 @@
 //
 // Operand tiles are K-major, SWIZZLE_128B: row r (128 B = 32 tf32) at r*128, 16-byte chunk c stored at
 // chunk (c ^ (r & 7)); 8-row groups 1024 B apart (SBO).  One K chunk = 32 floats = 4 MMA k-steps of 8.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace usip {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                  // floats per K chunk (= one 128-byte swizzle row)
 constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, on alternating 32-column chunks
 constexpr int TC_MMA_WARP = 8;
 constexpr int TC_PROD_WARP0 = 9;
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_THREADS = (TC_PROD_WARP0 + TC_PROD_WARPS) * 32;   // 544
 constexpr int TC_STAT_ROWS = 32;           // BN-statistic partials are emitted per 32-row warp slice
-
-// ------------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, M=128, N from idesc, K=8
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane).  The load is asynchronous: the
-// destination registers may only be read after tmem_ld_wait(), which also ties the registers ("+r") so the compiler
-// cannot hoist their uses above the wait.
-#define USIP_R32(r) "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
-    "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),          \
-    "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),         \
-    "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-#define USIP_RW32(r) "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), \
-    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]),           \
-    "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]),          \
-    "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : USIP_R32(r)
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : USIP_RW32(r) : : "memory");
-}
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-//  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 (1024 B) |
-//  [46,48) version=1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32(1)@4, a=TF32(2)@7, b=TF32(2)@10,
-// a/b K-major (0), N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk): [hi | lo] blocks of BN x 128 B,
@@ -508,6 +394,9 @@ static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream
   return check_launch("layer_fwd_tc_kernel");
 }
 
+bool tc2_eligible(const usip_layer_desc& d);                                   // mlp_tc2.cu
+int launch_tc2(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st);
+
 int tc_tile_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
 int tc_stat_rows() { return TC_STAT_ROWS; }
 
@@ -525,6 +414,9 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
   // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
   while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
+  // wide layers with enough tiles go to the CTA-pair kernel (precision 3 forces the single-CTA kernel)
+  const bool pair = d.precision == 1 && d.Cout % 256 == 0 && tc2_eligible(d);
+  if (pair) BN = 256;
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {
     const int total = d.Cout * (d.Cin / 4);
@@ -532,6 +424,7 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
     int e = check_launch("tc_pack_weights_kernel");
     if (e) return e;
   }
+  if (pair) return launch_tc2(d, wpack, st);
   const bool combine = (d.gmax || d.gmin) && d.group > 32;
   if (combine) return BN == 128 ? launch_tc<128, 2, true>(d, wpack, st) : launch_tc<64, 3, true>(d, wpack, st);
   if (BN == 256) return launch_tc<256, 2, false>(d, wpack, st);
