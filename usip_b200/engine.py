@@ -93,8 +93,12 @@ def _tc_workspace(W, P, Cin, Cout, group, transposed):
     return ws, False
 
 
+import os as _os
+_TC_PREC = 3 if _os.environ.get("USIP_TC_SINGLE_CTA") else 1     # debugging / A-B switch: force the single-CTA kernel
+
+
 def _precision_for(P, Cin, Cout, use_tc):
-    return 1 if (use_tc and Cin % 32 == 0 and Cout % 64 == 0 and P >= 1024) else 0
+    return _TC_PREC if (use_tc and Cin % 32 == 0 and Cout % 64 == 0 and P >= 1024) else 0
 
 
 class LayerRunner:
@@ -106,7 +110,7 @@ class LayerRunner:
         self.use_tc = use_tc
         self.dev = dev
         self.tile = ops.tile_rows()
-        self.stat_rows = (ops.stat_rows(0), ops.stat_rows(1))
+        self.stat_rows = {0: ops.stat_rows(0), 1: ops.stat_rows(1), 3: ops.stat_rows(3)}
 
     def bn_state(self, norm, part, ntiles, count, momentum):
         C = norm.weight.numel()
