@@ -115,12 +115,30 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
     const int c = pt & 7;                           // 16-byte chunk (4 floats) of the 128-byte row
     const int r0 = pt >> 3;                         // rows r0 + 16*j
     const bool has_aff = d.in_scale != nullptr;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // flat iteration space over (tile, K chunk); this group handles every other iteration.  The X tile of the NEXT
+    // iteration is fetched into registers before waiting for the stage to be freed, so the global-load latency
+    // (1-2 us under load) overlaps the tensor core working on the other stage(s).
+    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total_it = (uint32_t)max(my_tiles, 0) * (uint32_t)KC;
+    auto fetch = [&](uint32_t it2, float4 (&x)[8]) {
+      const int tile2 = (int)blockIdx.x + (int)(it2 / KC) * (int)gridDim.x;
+      const int kc2 = (int)(it2 % KC);
+      const int row02 = (tile2 / n_tiles) * TC_BM;
+      const int k2 = kc2 * TC_BK + c * 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = row02 + r0 + 16 * j;
+        x[j] = row < P ? __ldg(reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + k2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 x[8];
+    if ((uint32_t)grp < total_it) fetch((uint32_t)grp, x);
+    for (uint32_t it = (uint32_t)grp; it < total_it; it += 2) {
+      const int tile = (int)blockIdx.x + (int)(it / KC) * (int)gridDim.x;
+      const int kc = (int)(it % KC);
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int row0 = mt * TC_BM;
-      for (int kc = 0; kc < KC; ++kc, ++it) {
-        if ((int)(it & 1) != grp) continue;
+      {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -137,12 +155,6 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
         if (has_aff) {
           sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + k));
           sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + k));
-        }
-        float4 x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int row = row0 + r0 + 16 * j;
-          x[j] = row < P ? __ldg(reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -161,6 +173,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
+        if (it + 2 < total_it) fetch(it + 2, x);  // next tile of this group: in flight while we fence / arrive / wait
         fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(s));                  // every producer thread arrives after fencing its own stores
       }
