@@ -9,7 +9,7 @@
 //
 // Synchronisation (all mbarriers, no __syncthreads in the steady state):
 //   bfull[s]  (local)  : the CTA's own two bulk-TMA weight copies of stage s (expect_tx)
-//   full[s]   (leader) : 2 x 128 producer threads (the peer arrives remotely through its cluster-mapped address)
+//   full[s]   (leader) : 2 x 4 producer warps (the peer arrives remotely through its cluster-mapped address)
 //   empty[s]  (local)  : tcgen05.commit.cta_group::2 ... multicast::cluster from the leader's MMA thread
 //   tfull[b]  (local)  : same multicast commit after the last K chunk of a tile
 //   tempty[b] (leader) : 2 x 8 epilogue warps
@@ -91,7 +91,7 @@ layer_fwd_tc2_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack
 
   if (warp == T2_MMA_WARP) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 256); mbar_init(empty_bar(s), 1); mbar_init(bfull_bar(s), 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 8); mbar_init(empty_bar(s), 1); mbar_init(bfull_bar(s), 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 2 * T2_EPI_WARPS); }
       fence_barrier_init();
     }
@@ -174,7 +174,8 @@ layer_fwd_tc2_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack
         if (it + 2 < total_it) fetch(it + 2, x);
         if (pt == 0) mbar_wait(bfull_bar(s), ph);  // this CTA's weight half has landed (async proxy writes)
         asm volatile("fence.proxy.async;" ::: "memory");
-        mbar_arrive_cluster(mapa_u32(full_bar(s), 0));    // arrive on the LEADER's full barrier
+        __syncwarp();                              // one (remote) arrive per warp: 8 per stage instead of 256
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(full_bar(s), 0));    // arrive on the LEADER's full barrier
       }
     }
   } else if (warp == T2_MMA_WARP) {
