@@ -106,8 +106,8 @@ typedef struct usip_layer_desc {
   float* gmax; float* gmin;            /* [P/group,Cout] per-group max / min of Y, or NULL            */
   int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
   int32_t group;
-  int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0; CTA-pair
-                                          kernel for wide layers), 3 = tcgen05, single-CTA kernel only      */
+  int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0),
+                                          2 = same, CTA-pair (cta_group::2) kernel where eligible, 3 = alias of 1 */
   void* tc_workspace;                  /* precision 1: >= usip_layer_tc_workspace_bytes(Cin,Cout) bytes */
   int64_t tc_workspace_bytes;
   int32_t tc_weights_packed;           /* 1: tc_workspace already holds the packed weights of this W  */

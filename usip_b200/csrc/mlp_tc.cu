@@ -427,8 +427,9 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
   // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
   while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
-  // wide layers with enough tiles go to the CTA-pair kernel (precision 3 forces the single-CTA kernel)
-  const bool pair = d.precision == 1 && d.Cout % 256 == 0 && tc2_eligible(d);
+  // precision 2 opts into the CTA-pair (cta_group::2) kernel for wide layers with enough tiles.  Measured on B200 it
+  // is ~10-25% SLOWER than the single-CTA kernel with register prefetch, so it is not the default.
+  const bool pair = d.precision == 2 && d.Cout % 256 == 0 && tc2_eligible(d);
   if (pair) BN = 256;
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {

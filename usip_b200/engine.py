@@ -94,7 +94,7 @@ def _tc_workspace(W, P, Cin, Cout, group, transposed):
 
 
 import os as _os
-_TC_PREC = 3 if _os.environ.get("USIP_TC_SINGLE_CTA") else 1     # debugging / A-B switch: force the single-CTA kernel
+_TC_PREC = 2 if _os.environ.get("USIP_TC_PAIR") else 1     # A/B switch: opt into the CTA-pair kernel for wide layers
 
 
 def _precision_for(P, Cin, Cout, use_tc):
@@ -110,7 +110,7 @@ class LayerRunner:
         self.use_tc = use_tc
         self.dev = dev
         self.tile = ops.tile_rows()
-        self.stat_rows = {0: ops.stat_rows(0), 1: ops.stat_rows(1), 3: ops.stat_rows(3)}
+        self.stat_rows = {0: ops.stat_rows(0), 1: ops.stat_rows(1), 2: ops.stat_rows(2), 3: ops.stat_rows(3)}
 
     def bn_state(self, norm, part, ntiles, count, momentum):
         C = norm.weight.numel()
