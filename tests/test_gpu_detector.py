@@ -171,3 +171,31 @@ def test_forward_loss_cuda_graph_matches_eager():
         assert md.loss.item() == eager[0]
         assert torch.equal(torch.cat([md.src_keypoints, md.dst_keypoints]), eager[1])
         assert torch.equal(torch.cat([md.src_sigmas, md.dst_sigmas]), eager[2])
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_detector_ragged_sizes_vs_oracle(use_tc):
+    """Sizes that are not multiples of any tile: N=3001 points (what random point dropout produces), M=50 nodes, B'=6 clouds,
+    plus one node moved far away so that a cluster is empty.  Train-mode BN, fused CUDA plan vs the numpy oracle."""
+    from usip_b200.models.keypoint_detector import ModelDetector
+    B, N, M, S, Kn = 3, 3001, 50, 4, 16
+    d = orc.synth_pair(B, N, M, S, kind="lidar", seed=31)
+    d["src_node"][0, :, 7] = 500.0                      # empty cluster: mean (0,0,0), pooled features 0
+    P = orc.init_detector_params(S=S, seed=9, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn, use_tensor_cores=use_tc)
+    md = ModelDetector(opt)
+    load_params(md.detector, P)
+    keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
+    md.set_input(*[torch.from_numpy(d[k]) for k in keys])
+    md.forward_loss(train_bn=True)
+    r = orc.detector_fwd_loss(P, *[d[k] for k in keys], node_knn_k=Kn, sigma_lower_bound=opt.loss_sigma_lower_bound,
+                              alpha=opt.keypoint_on_pc_alpha, training=True)
+    kp = torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy()
+    sig = torch.cat([md.src_sigmas, md.dst_sigmas]).cpu().numpy()
+    assert rel_err(kp, np.concatenate([r["src_keypoints"], r["dst_keypoints"]])) < REL
+    assert rel_err(sig, np.concatenate([r["src_sigmas"], r["dst_sigmas"]])) < REL
+    assert abs(md.loss.item() - r["loss"]) <= REL * abs(r["loss"])
+    md.optimize(epoch=0)                                # backward on ragged sizes must run and stay finite
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(p.grad).all() for p in md.detector.parameters())
