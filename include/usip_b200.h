@@ -178,6 +178,13 @@ int usip_transform_points(const float* kp, const float* R, const float* scale, c
 int usip_mean_scale(const float* d, int64_t n, float alpha, float* out, void* stream);
 
 
+/* DescPairScanLoss (models/losses.py:190-237): min_j ||a[:,i] - b[:,j]||_2 over C-dim descriptors, a (B,C,Ma), b (B,C,Nb) */
+int usip_desc_pairmin_f32(const float* a, const float* b, float* min_d, int32_t* arg, int B, int C, int Ma, int Nb,
+                          void* stream);
+/* loss (B,M) = w * clamp(dpos - dneg + gamma, 0), w = clamp(sigma_max - sigma, 0)/mean; active (B) = mean(> 0) */
+int usip_desc_triplet(const float* dpos, const float* dneg, const float* sigma, float gamma, float sigma_max,
+                      float* loss, float* active, int B, int M, void* stream);
+
 /* ---- backward of the loss kernels (autograd of models/losses.py / keypoint_detector.py:182-184) ---- */
 /* grad of sum_i g_i*gscale*min_d_i: grad_a (B,3,Ma) overwritten, grad_b (B,3,Nb) ACCUMULATED (pre-zero) or NULL */
 int usip_pairwise_min_bwd(const float* a, const float* b, const float* min_d, const int32_t* arg,

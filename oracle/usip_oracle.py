@@ -294,6 +294,18 @@ def detector_fwd_loss(P, src_pc, src_sn, src_node, dst_pc, dst_sn, dst_node, R, 
                 src_keypoints_transformed=kp_t, node_recomputed=f["node_recomputed"], new_stats=f["new_stats"])
 
 
+def desc_pair_scan_loss(anc, pos, neg, anc_sigmas, gamma=0.5, sigma_max=3.0):
+    """DescPairScanLoss.forward (models/losses.py:200-237) -> (loss (B,M), active_percentage (B))."""
+    a = anc.astype(np.float64); p = pos.astype(np.float64); n = neg.astype(np.float64)
+    dpos = np.sqrt(((a[:, :, :, None] - p[:, :, None, :]) ** 2).sum(1)).min(2)
+    dneg = np.sqrt(((a[:, :, :, None] - n[:, :, None, :]) ** 2).sum(1)).min(2)
+    before = dpos - dneg + gamma
+    active = (before > 0).mean(1)
+    w = np.maximum(sigma_max - anc_sigmas.astype(np.float64), 0)
+    w = w / w.mean(1, keepdims=True)
+    return (w * np.maximum(before, 0)).astype(np.float32), active.astype(np.float32)
+
+
 # ----------------------------------------------------------------------------- descriptor forward
 def descriptor_forward(P, x, sn, keypoints, radius=1.0, nsamples=64, training=False, momentum=0.1,
                        permute_idx=None, dtype=np.float32):

@@ -199,3 +199,32 @@ def test_detector_ragged_sizes_vs_oracle(use_tc):
     md.optimize(epoch=0)                                # backward on ragged sizes must run and stay finite
     torch.cuda.synchronize()
     assert all(torch.isfinite(p.grad).all() for p in md.detector.parameters())
+
+
+def test_desc_pair_scan_loss_and_model_descriptor_api():
+    """DescPairScanLoss forward vs the reference golden; ModelDescriptor.test_model / run_model plumbing."""
+    from usip_b200.models import losses
+    from usip_b200.models.keypoint_descriptor import ModelDescriptor
+    g = golden("desc_loss.npz")
+    opt = make_opt(triple_loss_gamma=float(g["gamma"]), sigma_max=float(g["sigma_max"]))
+    anc = cu(g["anc"]); pos = cu(g["pos"]); idx = torch.from_numpy(g["neg_idx"]).to(dev())
+    with torch.no_grad():
+        loss, active = losses.DescPairScanLoss(opt)(anc, pos, anc[idx], cu(g["sig"]))
+    assert rel_err(loss.cpu().numpy(), g["loss"]) < 1e-5
+    assert np.array_equal(active.cpu().numpy(), g["active"])
+    # model-level API on the descriptor golden inputs
+    gd = golden("descriptor.npz")
+    B, N, M, S, K, seed = [int(v) for v in gd["cfg"]]
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K, descriptor_len=128)
+    md = ModelDescriptor(opt)
+    load_params(md.descriptor, {k[len("param/"):]: gd[k] for k in gd.files if k.startswith("param/")})
+    np.random.seed(seed)
+    desc = md.run_model(cu(gd["pc"]), cu(gd["sn"]), cu(gd["kp"]))
+    assert rel_err(desc.cpu().numpy(), gd["eval_desc"]) < REL
+    sig = torch.rand(B, M)
+    md.set_input(torch.from_numpy(gd["pc"]), torch.from_numpy(gd["sn"]), torch.from_numpy(gd["kp"]), sig,
+                 torch.from_numpy(gd["pc"]), torch.from_numpy(gd["sn"]), torch.from_numpy(gd["kp"]), sig, torch.tensor([1, 0]))
+    md.test_model()
+    assert np.isfinite(md.get_current_errors()["O_loss"])
+    with pytest.raises(NotImplementedError):
+        md.optimize()

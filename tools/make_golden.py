@@ -171,6 +171,20 @@ def golden_descriptor(ref):
     np.savez_compressed(os.path.join(OUT, "descriptor.npz"), **out)
 
 
+def golden_desc_loss(ref):
+    torch.manual_seed(5)
+    B, C, M = 3, 128, 40
+    anc = torch.nn.functional.normalize(torch.randn(B, C, M), dim=1)
+    pos = torch.nn.functional.normalize(anc + 0.3 * torch.randn(B, C, M), dim=1)
+    neg_idx = torch.tensor([1, 2, 0])
+    sig = torch.rand(B, M) * 4
+    opt = ref_shim.make_opt()
+    loss, act = ref.losses.DescPairScanLoss(opt)(anc, pos, anc[neg_idx], sig)
+    np.savez_compressed(os.path.join(OUT, "desc_loss.npz"), anc=anc.numpy(), pos=pos.numpy(), neg_idx=neg_idx.numpy(),
+                        sig=sig.numpy(), loss=loss.numpy(), active=act.numpy(),
+                        gamma=np.float32(opt.triple_loss_gamma), sigma_max=np.float32(opt.sigma_max))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -182,6 +196,7 @@ def main():
     detector_case(ref, "modelnet_small", B=3, N=1000, M=32, S=3, Kn=32, kind="object", seed=1236, lb=1e-4, alpha=1.0)
     detector_case(ref, "lite_small", B=2, N=1024, M=32, S=4, Kn=16, kind="lidar", seed=1238, scene="indoor")
     golden_descriptor(ref)
+    golden_desc_loss(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KB")
 

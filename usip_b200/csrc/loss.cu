@@ -206,6 +206,69 @@ __global__ void transform_points_bwd_kernel(const float* __restrict__ g, const f
   for (int c = 0; c < 3; ++c) gk[(size_t)b * 3 * M + (size_t)c * M + m] = r[0 * 3 + c] * gx + r[1 * 3 + c] * gy + r[2 * 3 + c] * gz;
 }
 
+// ---- descriptor losses (models/losses.py:190-237, DescPairScanLoss) -----------------------------------------
+// min_j || a[:, i] - b[:, j] ||_2 over C-dimensional descriptors, a (B,C,Ma), b (B,C,Nb) channel-major.
+// CTA = (batch, 32 queries): the query tile lives in shared memory, database columns stream through a second tile.
+constexpr int DP_Q = 32, DP_J = 64;
+__global__ void __launch_bounds__(256)
+desc_pairmin_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ min_d,
+                    int32_t* __restrict__ arg, int C, int Ma, int Nb) {
+  extern __shared__ float sm[];                  // [C][DP_Q] queries, then [C][DP_J] database tile
+  float* sa = sm; float* sb = sm + (size_t)C * DP_Q;
+  __shared__ float rbest[8][DP_Q]; __shared__ int rarg[8][DP_Q];
+  const int bb = blockIdx.y, i0 = blockIdx.x * DP_Q;
+  const int qi = threadIdx.x & 31, js = threadIdx.x >> 5;          // query, database slice (8 slices of 8 columns)
+  const float* pa = a + (size_t)bb * C * Ma; const float* pb = b + (size_t)bb * C * Nb;
+  for (int t = threadIdx.x; t < C * DP_Q; t += 256) { int c = t / DP_Q, q = t - c * DP_Q; sa[t] = (i0 + q) < Ma ? pa[(size_t)c * Ma + i0 + q] : 0.f; }
+  float best = INFINITY; int bj = 0;
+  for (int j0 = 0; j0 < Nb; j0 += DP_J) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < C * DP_J; t += 256) { int c = t / DP_J, j = t - c * DP_J; sb[t] = (j0 + j) < Nb ? pb[(size_t)c * Nb + j0 + j] : 0.f; }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float av = sa[c * DP_Q + qi];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float df = av - sb[c * DP_J + js * 8 + u]; acc[u] = fmaf(df, df, acc[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int j = j0 + js * 8 + u; if (j < Nb && acc[u] < best) { best = acc[u]; bj = j; } }
+  }
+  rbest[js][qi] = best; rarg[js][qi] = bj;
+  __syncthreads();
+  if (threadIdx.x < DP_Q && i0 + threadIdx.x < Ma) {
+    float bst = INFINITY; int bjj = 0;
+    for (int t = 0; t < 8; ++t) { float v = rbest[t][threadIdx.x]; int j = rarg[t][threadIdx.x]; if (v < bst || (v == bst && j < bjj)) { bst = v; bjj = j; } }
+    min_d[(size_t)bb * Ma + i0 + threadIdx.x] = sqrtf(bst);
+    if (arg) arg[(size_t)bb * Ma + i0 + threadIdx.x] = bjj;
+  }
+}
+
+// loss[b,m] = w[b,m] * max(dpos - dneg + gamma, 0), w = clamp(sigma_max - sigma, 0) / mean_m(...); active[b] = mean(dpos-dneg+gamma > 0)
+__global__ void __launch_bounds__(256)
+desc_triplet_kernel(const float* __restrict__ dpos, const float* __restrict__ dneg, const float* __restrict__ sigma,
+                    float gamma, float sigma_max, float* __restrict__ loss, float* __restrict__ active, int M) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  double wsum = 0.0, act = 0.0;
+  for (int m = threadIdx.x; m < M; m += 256) {
+    wsum += fmaxf(sigma_max - sigma[(size_t)b * M + m], 0.f);
+    act += (dpos[(size_t)b * M + m] - dneg[(size_t)b * M + m] + gamma) > 0.f ? 1.0 : 0.0;
+  }
+  __shared__ float wmean;
+  double r = block_sum(wsum, sh);
+  if (threadIdx.x == 0) wmean = (float)(r / M);
+  r = block_sum(act, sh);
+  if (threadIdx.x == 0) active[b] = (float)(r / M);
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += 256) {
+    const float w = fmaxf(sigma_max - sigma[(size_t)b * M + m], 0.f) / wmean;
+    loss[(size_t)b * M + m] = w * fmaxf(dpos[(size_t)b * M + m] - dneg[(size_t)b * M + m] + gamma, 0.f);
+  }
+}
+
 }  // namespace usip
 
 using namespace usip;
@@ -269,4 +332,22 @@ extern "C" int usip_transform_points_bwd(const float* g_out, const float* R, con
   USIP_REQUIRE(g_out && R && scale && g_kp, "transform_points_bwd: bad args");
   transform_points_bwd_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(g_out, R, scale, g_kp, B, M);
   return check_launch("transform_points_bwd_kernel");
+}
+
+extern "C" int usip_desc_pairmin_f32(const float* a, const float* b, float* min_d, int32_t* arg, int B, int C, int Ma,
+                                     int Nb, void* stream) {
+  USIP_REQUIRE(a && b && min_d && B > 0 && C > 0 && Ma > 0 && Nb > 0, "desc_pairmin: bad args");
+  size_t smem = (size_t)C * (DP_Q + DP_J) * sizeof(float);
+  USIP_REQUIRE(smem <= 200 * 1024, "desc_pairmin: C too large");
+  if (smem > 48 * 1024) cudaFuncSetAttribute(desc_pairmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(cdiv(Ma, DP_Q), B);
+  desc_pairmin_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, min_d, arg, C, Ma, Nb);
+  return check_launch("desc_pairmin_kernel");
+}
+
+extern "C" int usip_desc_triplet(const float* dpos, const float* dneg, const float* sigma, float gamma, float sigma_max,
+                                 float* loss, float* active, int B, int M, void* stream) {
+  USIP_REQUIRE(dpos && dneg && sigma && loss && active, "desc_triplet: bad args");
+  desc_triplet_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dpos, dneg, sigma, gamma, sigma_max, loss, active, M);
+  return check_launch("desc_triplet_kernel");
 }

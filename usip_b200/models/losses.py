@@ -150,3 +150,28 @@ class KeypointOnPCLoss(nn.Module):
             raise NotImplementedError("point_to_plane (PointOnSurfaceLoss, losses.py:146-183) is a non-default "
                                       "option outside the B200 hot path; use keypoint_on_pc_type='point_to_point'")
         return self.single_side_chamfer(keypoint, pc)
+
+
+class DescPairScanLoss(nn.Module):
+    """Triplet loss over scan pairs (models/losses.py:190-237): for every anchor keypoint the closest descriptor in
+    the positive and in the negative scan (two fused C-dimensional pairwise-min kernels instead of two (B,C,M,M)
+    difference tensors), sigma-derived weights.  Forward only in this round (SURVEY 8f-1 'next' row)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+
+    def forward(self, anc_descriptors, pos_descriptors, neg_descriptors, anc_sigmas):
+        if torch.is_grad_enabled() and (anc_descriptors.requires_grad or pos_descriptors.requires_grad):
+            raise NotImplementedError("DescPairScanLoss backward is not built yet; evaluate under torch.no_grad()")
+        lib = _lib.load()
+        a = anc_descriptors.contiguous(); p_ = pos_descriptors.contiguous(); n_ = neg_descriptors.contiguous()
+        B, C, M = a.shape
+        dev = a.device
+        dpos = torch.empty((B, M), dtype=torch.float32, device=dev); dneg = torch.empty_like(dpos)
+        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(p_), _p(dpos), None, B, C, M, p_.shape[2], _stream()), "usip_desc_pairmin_f32")
+        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(n_), _p(dneg), None, B, C, M, n_.shape[2], _stream()), "usip_desc_pairmin_f32")
+        loss = torch.empty_like(dpos); active = torch.empty((B,), dtype=torch.float32, device=dev)
+        _lib.check(lib.usip_desc_triplet(_p(dpos), _p(dneg), _p(anc_sigmas.contiguous().float()), float(self.opt.triple_loss_gamma),
+                                         float(self.opt.sigma_max), _p(loss), _p(active), B, M, _stream()), "usip_desc_triplet")
+        return loss, active
