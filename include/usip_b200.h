@@ -111,6 +111,8 @@ typedef struct usip_layer_desc {
   void* tc_workspace;                  /* precision 1: >= usip_layer_tc_workspace_bytes(Cin,Cout) bytes */
   int64_t tc_workspace_bytes;
   int32_t tc_weights_packed;           /* 1: tc_workspace already holds the packed weights of this W  */
+  int32_t debug_flags;                 /* profiling aid for the tcgen05 kernel (results are then WRONG): 1 = skip the epilogue
+                                          body, 2 = producers skip the X loads, 4 = no weight TMA, 8 = issue 1 of the 3 MMAs */
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);

@@ -132,7 +132,12 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       }
     };
     float4 x[8];
-    if ((uint32_t)grp < total_it) fetch((uint32_t)grp, x);
+    const bool dbg_noload = (d.debug_flags & 2) != 0, dbg_notma = (d.debug_flags & 4) != 0;
+    if (dbg_noload) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = make_float4(1.f, 2.f, 3.f, 4.f);
+    }
+    if ((uint32_t)grp < total_it && !dbg_noload) fetch((uint32_t)grp, x);
     for (uint32_t it = (uint32_t)grp; it < total_it; it += 2) {
       const int tile = (int)blockIdx.x + (int)(it / KC) * (int)gridDim.x;
       const int kc = (int)(it % KC);
@@ -146,9 +151,13 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
         const uint32_t a_lo = a_hi + TC_BM * 128;
         const uint32_t b_hi = a_hi + SM::A_STAGE;
         if (pt == 0) {
-          mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
-          const uint32_t* src = wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;
-          bulk_g2s(b_hi, src, SM::B_STAGE, full_bar(s));          // [hi | lo] contiguous
+          if (dbg_notma) {
+            mbar_arrive(full_bar(s));
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
+            const uint32_t* src = wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;
+            bulk_g2s(b_hi, src, SM::B_STAGE, full_bar(s));          // [hi | lo] contiguous
+          }
         }
         const int k = kc * TC_BK + c * 4;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -173,7 +182,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
-        if (it + 2 < total_it) fetch(it + 2, x);  // next tile of this group: in flight while we fence / arrive / wait
+        if (it + 2 < total_it && !dbg_noload) fetch(it + 2, x);  // next tile of this group: in flight while we fence / arrive / wait
         fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(full_bar(s));                  // every producer thread arrives after fencing its own stores
       }
@@ -201,8 +210,10 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
             const uint64_t dah = make_kmajor_sw128_desc(a_hi + ks * 32), dal = make_kmajor_sw128_desc(a_lo + ks * 32);
             const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ks * 32), dbl = make_kmajor_sw128_desc(b_lo + ks * 32);
             umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
-            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            if (!(d.debug_flags & 8)) {
+              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
           }
           umma_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
           if (kc == KC - 1) umma_commit(tfull_bar(buf));   // accumulator ready for the epilogue
@@ -237,7 +248,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int ch = half; ch < BN / 32; ch += 2) {
+      for (int ch = half; ch < ((d.debug_flags & 1) ? 0 : BN / 32); ch += 2) {
         const int cb = n0 + ch * 32;
         // TMEM read and the addend gather are issued back to back so their latencies overlap
         uint32_t raw[32];

@@ -152,7 +152,7 @@ def knn_nodes(pts, K):
 # ----------------------------------------------------------------------------- shared-MLP stack
 def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_shift=None, in_relu=False,
               addend=None, add_index=None, add_group=0, Y=None, ldy=None, stat_partial=None,
-              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False, w_transposed=False):
+              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False, w_transposed=False, debug_flags=0):
     d = LayerDesc()
     d.X = X.data_ptr(); d.ldx = X.stride(0) if ldx is None else ldx
     d.P = P; d.Cin = Cin; d.Cout = Cout
@@ -175,6 +175,7 @@ def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_sh
     d.garg_min = None if garg_min is None else garg_min.data_ptr()
     d.group = group
     d.precision = precision
+    d.debug_flags = debug_flags
     if precision in (1, 2, 3):
         if tc_ws is None:
             tc_ws = torch.empty((2 * Cin * Cout,), dtype=f32, device=X.device)
