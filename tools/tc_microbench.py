@@ -21,8 +21,7 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
         Q = P // group
         kw = dict(gmax=torch.empty(Q, Cout, device=dev), gmin=torch.empty(Q, Cout, device=dev), group=group)
     res = {}
-    for name, flags in [("full", 0), ("no_epilogue", 1), ("no_xload", 2), ("no_wtma", 4), ("one_mma_of_3", 8),
-                        ("no_epi+no_xload+no_wtma", 7), ("mma_only_1of3", 15)]:
+    for name, flags in [("full", 0), ("no_epilogue", 1), ("no_xload", 2), ("3xtf32 full", 16)]:
         def run(packed):
             ops.layer_fwd(X, W, b, P, Cin, Cout, in_scale=sc, in_shift=sh, in_relu=True, Y=Y, stat_partial=part,
                           precision=1, tc_ws=ws, tc_packed=packed, debug_flags=flags, **kw)
@@ -33,7 +32,21 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); run(True); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         res[name] = round(float(np.median(ts)) * 1e3, 1)
+    # per-role time attribution of the full kernel (clock64 accumulators, averaged over CTAs / warps of a role)
+    clk = torch.zeros(148 * 17 * 8, dtype=torch.int64, device=dev)
+    ops.layer_fwd(X, W, b, P, Cin, Cout, in_scale=sc, in_shift=sh, in_relu=True, Y=Y, stat_partial=part,
+                  precision=1, tc_ws=ws, tc_packed=True, debug_flags=0, debug_clocks=clk, **kw)
+    torch.cuda.synchronize()
+    c = clk.view(148, 17, 8).double().cpu().numpy()
+    tot = c[:, :, 7].mean()
+    def pct(role, names):
+        m = c[:, role, :].reshape(-1, 8).mean(0)
+        return {n: round(100 * m[i] / tot, 1) for i, n in enumerate(names) if n}
+    res["clk_total_kcycles"] = round(tot / 1e3, 1)
+    res["clk_epilogue_%"] = pct(slice(0, 8), ["wait_tfull", "tmem_ld+bias", "stage_sts", "y_store", "stats", "tail"])
+    res["clk_mma_%"] = pct(slice(8, 9), ["wait_tempty", "wait_full", "issue"])
+    res["clk_producer_%"] = pct(slice(9, 17), ["wait_empty", "tma+convert+sts", "fetch+fence+arrive", "loop"])
     flops = 2.0 * P * Cin * Cout
-    res["mma_floor_us_at_1965MHz"] = round(3 * flops / (148 * 2048 * 2 * 1.965e9) * 1e6, 1)
+    res["mma_floor_us_at_1965MHz"] = round(2 * flops / (148 * 2048 * 2 * 1.965e9) * 1e6, 1)
     out["%dx%d->%d%s" % (P, Cin, Cout, " g16 noY" if group else "")] = res
 print(json.dumps(out, indent=1))

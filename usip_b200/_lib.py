@@ -35,6 +35,7 @@ class LayerDesc(ctypes.Structure):
         ("tc_workspace_bytes", ctypes.c_int64),
         ("tc_weights_packed", ctypes.c_int32),
         ("debug_flags", ctypes.c_int32),
+        ("debug_clocks", ctypes.c_void_p),
     ]
 
 

@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, s)
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("USIP_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -339,7 +339,7 @@ extern "C" int usip_desc_pairmin_f32(const float* a, const float* b, float* min_
   USIP_REQUIRE(a && b && min_d && B > 0 && C > 0 && Ma > 0 && Nb > 0, "desc_pairmin: bad args");
   size_t smem = (size_t)C * (DP_Q + DP_J) * sizeof(float);
   USIP_REQUIRE(smem <= 200 * 1024, "desc_pairmin: C too large");
-  if (smem > 48 * 1024) cudaFuncSetAttribute(desc_pairmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 40 * 1024) cudaFuncSetAttribute(desc_pairmin_kernel   /* + 2 KB static */, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(cdiv(Ma, DP_Q), B);
   desc_pairmin_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, min_d, arg, C, Ma, Nb);
   return check_launch("desc_pairmin_kernel");

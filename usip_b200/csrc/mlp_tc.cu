@@ -8,58 +8,105 @@
 //
 // Persistent, warp-specialised CTA (one per SM), 17 warps:
 //   warps 0-7  : epilogue  (TMEM lanes 32*(w%4)..+31, two warps per quarter on alternating 32-column
-//                chunks): tcgen05.ld -> bias/addend -> Y, BN statistic partials and per-group max/min
-//                (+arg) of the raw output
-//   warp  8    : TMEM allocation, mbarrier init, single-thread tcgen05.mma issue
-//   warps 9-16 : A-operand producers, two groups of four warps on alternating K chunks: coalesced
-//                float4 loads of X, BN/ReLU prologue, hi/lo split, 128B-swizzled st.shared;
-//                one elected thread per chunk also issues the bulk-TMA (cp.async.bulk) copies of the
-//                pre-split, pre-swizzled weight tiles.
+//                chunks): tcgen05.ld -> (+addend) -> transpose through a swizzled 32x32 smem tile -> +bias ->
+//                coalesced Y stores, BN statistic partials and per-group max/min (+arg) of the raw output
+//   warps 8-15 : A-operand producers, two groups of four warps on alternating K chunks: coalesced
+//                float4 loads of X (register-prefetched one own-iteration ahead), BN/ReLU prologue, hi/lo
+//                split, 128B-swizzled st.shared; one thread per chunk also issues the bulk-TMA
+//                (cp.async.bulk) copy of the pre-split, pre-swizzled weight tile.
+//   warp  16   : TMEM allocation, mbarrier init, single-thread tcgen05.mma issue
+// Registers are re-split between the roles with setmaxnreg (producers 80, epilogue 112, launch 96).
 // Pipelines: smem full/empty ring (STAGES deep) between producers and MMA, TMEM full/empty (2
 // accumulators) between MMA and epilogue, static round-robin tile scheduler.
 //
 // Operand tiles are K-major, SWIZZLE_128B: row r (128 B = 32 tf32) at r*128, 16-byte chunk c stored at
 // chunk (c ^ (r & 7)); 8-row groups 1024 B apart (SBO).  One K chunk = 32 floats = 4 MMA k-steps of 8.
+//
+// Measured dead ends, kept out of the default path (tools/tc_microbench.py):
+//   * 16-float K chunks (SWIZZLE_64B) with twice the stages: 5-10% slower (per-stage barrier overhead);
+//   * TF32 main product + BF16 cross terms (debug_flags & 16): -33% tensor time, +2% speed -- the kernel is bound by
+//     the latency of its three software stages, not by the tensor pipe;
+//   * L2 bulk prefetch of X tiles ahead of the register prefetch: no change.
 #include "tc_common.cuh"
 
 namespace usip {
 
 constexpr int TC_EPI_WARPS = 8;            // two warps per TMEM lane quarter, on alternating 32-column chunks
-constexpr int TC_MMA_WARP = 8;
-constexpr int TC_PROD_WARP0 = 9;
+constexpr int TC_PROD_WARP0 = 8;           // warps 8-15: producers (warpgroups 2 and 3)
 constexpr int TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_PROD_WARP0 + TC_PROD_WARPS) * 32;   // 544
+constexpr int TC_MMA_WARP = 16;            // alone in warpgroup 4
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;                 // 544
+// Register split (setmaxnreg, per warpgroup): the kernel launches at 96 registers per thread -- the SM sub-partition
+// that hosts 5 of the 17 warps allows no more -- and the epilogue, which holds a 32-column accumulator slice per
+// thread, spilled at that size (ncu: ~25% of its stall samples were reloads of spilled values from L2, its stack
+// lines having been evicted by the streaming X traffic).  The producers give up 16 registers each, the epilogue takes them.
+constexpr int TC_REGS_PROD = 80, TC_REGS_EPI = 112;
 constexpr int TC_STAT_ROWS = 32;           // BN-statistic partials are emitted per 32-row warp slice
 
+// K-major SWIZZLE_64B shared-memory descriptor (cute::UMMA::SmemDescriptor, canonical layout
+// Swizzle<2,4,3> o ((8,m),(T,2)):((4T,SBO),(1,T))): SBO = 512 B between 8-row groups, layout type 4.
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {   // lo_elem at the lower address
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// offset (bytes) of the 8-byte group holding k = 4c..4c+3 of row r in a [rows x 32] BF16 tile, K-major SWIZZLE_64B
+__device__ __forceinline__ uint32_t bf16_tile_off(int r, int c) {
+  return (uint32_t)r * 64u + (uint32_t)((((c >> 1) ^ ((r >> 1) & 3)) << 4) + ((c & 1) << 3));
+}
+
 // ------------------------------------------------------------------------------------------------
-// weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk): [hi | lo] blocks of BN x 128 B,
-// already 128B-swizzled, so a tile is one contiguous bulk copy.
+// weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk) one contiguous, pre-swizzled block, so a
+// stage's B operand is a single bulk copy.
+//   mixed == 0 (CTA-pair kernel, 3xTF32): [w_hi | w_lo], TF32, BN x 128 B each, SWIZZLE_128B
+//   mixed == 1 (this kernel):             [w_hi TF32, BN x 128 B, SWIZZLE_128B | bf16(w_hi), BN x 64 B, SWIZZLE_64B |
+//                                          bf16(w - w_hi), BN x 64 B, SWIZZLE_64B]          (same 256 B per row)
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int transposed, int Cout, int Cin, int BN,
-                                       uint32_t* __restrict__ out) {
+                                       int mixed, uint32_t* __restrict__ out) {
   const int KC = Cin / TC_BK;
-  const int total = Cout * (Cin / 4);                 // one thread per 16-byte chunk
+  const int total = Cout * (Cin / 4);                 // one thread per 4 consecutive k
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int n = t / (Cin / 4), k4 = t - n * (Cin / 4);
-  const int kc = k4 / 8, c = k4 & 7;                  // chunk c of K chunk kc
+  const int kc = k4 / 8, c = k4 & 7;                  // 16-byte chunk c of K chunk kc
   const int nt = n / BN, r = n - nt * BN;
+  float w[4];
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float w = transposed ? W[(size_t)(k4 * 4 + j) * ldw + n] : W[(size_t)n * ldw + k4 * 4 + j];
-    split_tf32(w, hi[j], lo[j]);
+    w[j] = transposed ? W[(size_t)(k4 * 4 + j) * ldw + n] : W[(size_t)n * ldw + k4 * 4 + j];
+    split_tf32(w[j], hi[j], lo[j]);
   }
   const size_t blk = ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;     // in 32-bit words
   const size_t off = (size_t)r * TC_BK + (size_t)((c ^ (r & 7)) * 4);
   *reinterpret_cast<uint4*>(out + blk + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(out + blk + (size_t)BN * TC_BK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  if (!mixed) {
+    *reinterpret_cast<uint4*>(out + blk + (size_t)BN * TC_BK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  } else {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = __uint_as_float(hi[j]); l[j] = w[j] - h[j]; }
+    uint8_t* base = reinterpret_cast<uint8_t*>(out + blk + (size_t)BN * TC_BK);
+    const uint32_t o = bf16_tile_off(r, c);
+    *reinterpret_cast<uint2*>(base + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(base + (size_t)BN * 64 + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool COMBINE>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 struct TcSmem {
-  static constexpr int A_STAGE = 2 * TC_BM * 128;                 // hi + lo
+  static constexpr int A_STAGE = 2 * TC_BM * 128;                 // 3xTF32: hi + lo;  mixed: hi (128 B rows) + 2 BF16 tiles (64 B rows)
   static constexpr int B_STAGE = 2 * BN * 128;
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int TRANS = TC_EPI_WARPS * 32 * 32 * 4;       // per-warp 32x32 staging tile, XOR-swizzled 16B chunks
@@ -68,10 +115,13 @@ struct TcSmem {
   static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + BARS + 1024;   // +1024 alignment slack
 };
 
-template <int BN, int STAGES, bool COMBINE>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack) {
-  using SM = TcSmem<BN, STAGES, COMBINE>;
+  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
+  constexpr int BK = TC_BK;                          // 32 floats per K chunk
+  constexpr int CPR = BK / 4;                        // 16-byte chunks per fp32 operand row
+  constexpr int DEPTH = 1;                           // register-prefetched X chunks per producer thread
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024-B alignment
   uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -88,7 +138,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = d.P, Cin = d.Cin, Cout = d.Cout;
-  const int KC = Cin / TC_BK;
+  const int KC = Cin / BK;
   const int m_tiles = (P + TC_BM - 1) / TC_BM, n_tiles = Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
@@ -106,85 +156,147 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // optional per-warp time attribution, compiled in with -DUSIP_TC_PROF (USIP_NVCC_EXTRA=-DUSIP_TC_PROF python -m
+  // usip_b200.build -f): acc[k] += clock64 delta at each TICK(k), written to d.debug_clocks.  Off by default: the
+  // accumulators cost registers this kernel does not have (measured +15% run time).
+#ifdef USIP_TC_PROF
+  const bool prof = d.debug_clocks != nullptr;
+  unsigned long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = prof ? clock64() : 0;
+  const long long tstart = tprev;
+#define TICK(k) do { if (prof) { const long long tn_ = clock64(); acc[k] += (unsigned long long)(tn_ - tprev); tprev = tn_; } } while (0)
+#else
+#define TICK(k) do { } while (0)
+#endif
 
-  if (warp >= TC_PROD_WARP0) {
+  if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_PROD_WARPS) {
     // =============================== A producers (+ weight bulk copies) ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
     const int pw = warp - TC_PROD_WARP0;            // 0..7
     const int grp = pw >> 2;                        // K chunks with (it & 1) == grp
     const int pt = (pw & 3) * 32 + lane;            // 0..127 inside the group
-    const int c = pt & 7;                           // 16-byte chunk (4 floats) of the 128-byte row
-    const int r0 = pt >> 3;                         // rows r0 + 16*j
+    const int c = pt % CPR;                         // 16-byte chunk (4 floats) of the operand row
+    const int r0 = pt / CPR;                        // rows r0 + (128/CPR)*j
+    constexpr int RSTEP = 128 / CPR;
     const bool has_aff = d.in_scale != nullptr;
-    // flat iteration space over (tile, K chunk); this group handles every other iteration.  The X tile of the NEXT
-    // iteration is fetched into registers before waiting for the stage to be freed, so the global-load latency
-    // (1-2 us under load) overlaps the tensor core working on the other stage(s).
+    const float relu_floor = d.in_relu ? 0.f : -INFINITY;
+    // flat iteration space over (tile, K chunk); this group handles every other iteration.  X tiles are fetched into
+    // registers DEPTH own-iterations ahead, so the global-load latency (1-2 us under load) overlaps the tensor core
+    // working on the other stages.
     const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t total_it = (uint32_t)max(my_tiles, 0) * (uint32_t)KC;
-    auto fetch = [&](uint32_t it2, float4 (&x)[8]) {
+    struct XT { float4 x[CPR]; float4 sc, sh; };    // one prefetched A chunk of this thread + its BN affine
+    const bool dbg_noload = (d.debug_flags & 2) != 0, dbg_notma = (d.debug_flags & 4) != 0;
+    auto fetch = [&](uint32_t it2, XT& t) {
+      if (it2 >= total_it || dbg_noload) return;
       const int tile2 = (int)blockIdx.x + (int)(it2 / KC) * (int)gridDim.x;
       const int kc2 = (int)(it2 % KC);
       const int row02 = (tile2 / n_tiles) * TC_BM;
-      const int k2 = kc2 * TC_BK + c * 4;
+      const int k2 = kc2 * BK + c * 4;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int row = row02 + r0 + 16 * j;
-        x[j] = row < P ? __ldg(reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + k2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < CPR; ++j) {
+        const int row = row02 + r0 + RSTEP * j;     // rows past P: zeros in, garbage accumulator rows the epilogue never reads
+        t.x[j] = row < P ? __ldg(reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + k2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (has_aff) {                                // the folded BN affine of these 4 input channels travels with the tile
+        t.sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + k2));
+        t.sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + k2));
       }
     };
-    float4 x[8];
-    const bool dbg_noload = (d.debug_flags & 2) != 0, dbg_notma = (d.debug_flags & 4) != 0;
-    if (dbg_noload) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = make_float4(1.f, 2.f, 3.f, 4.f);
-    }
-    if ((uint32_t)grp < total_it && !dbg_noload) fetch((uint32_t)grp, x);
-    for (uint32_t it = (uint32_t)grp; it < total_it; it += 2) {
+    // hi = rna_tf32(v), lo = rna_tf32(v - hi) in 4 integer/float ops per element: (bits + 0x1000) & ~0x1fff IS
+    // cvt.rna.tf32.f32 for finite inputs (round to nearest, ties away, on the magnitude); for lo only the +0x1000 is
+    // issued and then masked the same way.  (nvcc expands the cvt into ~4 instructions with an inf/nan guard; the
+    // producers are issue-bound -- tools/tc_microbench.py -- so the guard is dropped: activations here are finite.)
+    auto split4 = [&](float v, uint32_t& hi, uint32_t& lo) {
+      hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+      lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+    };
+    // L2 prefetch of whole X row tiles a few tiles ahead (one 16B-granular bulk prefetch per row, no registers or
+    // shared memory held): measured, the register prefetch alone keeps only ~16 KB per SM in flight, which at DRAM
+    // latency under load (~2 us) caps the X stream at ~1.2 TB/s for every layer shape (tools/tc_microbench.py).
+    const int pf_dist = min(8, max(1, (192 * 1024) / (TC_BM * Cin * 4)));
+    const bool pf_on = !(d.debug_flags & 128) && grp == 0;
+    auto prefetch_tile = [&](int tile_i) {
+      const long long tile_p = (long long)blockIdx.x + (long long)tile_i * (long long)gridDim.x;
+      if (tile_p >= num_tiles) return;
+      const int row = (int)(tile_p / n_tiles) * TC_BM + pt;
+      if (row < P)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(d.X + (size_t)row * d.ldx), "r"(Cin * 4) : "memory");
+    };
+    if (pf_on) for (int i = 1; i < pf_dist; ++i) prefetch_tile(i);
+    auto produce = [&](uint32_t it, const XT& t) {
       const int tile = (int)blockIdx.x + (int)(it / KC) * (int)gridDim.x;
       const int kc = (int)(it % KC);
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int row0 = mt * TC_BM;
-      {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t a_hi = stage_base + s * SM::STAGE;
-        const uint32_t a_lo = a_hi + TC_BM * 128;
-        const uint32_t b_hi = a_hi + SM::A_STAGE;
-        if (pt == 0) {
-          if (dbg_notma) {
-            mbar_arrive(full_bar(s));
-          } else {
-            mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
-            const uint32_t* src = wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * TC_BK;
-            bulk_g2s(b_hi, src, SM::B_STAGE, full_bar(s));          // [hi | lo] contiguous
-          }
+      const int nt = tile % n_tiles;
+      if (pf_on && kc == 0) prefetch_tile((int)(it / KC) + pf_dist);
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      TICK(3);
+      mbar_wait(empty_bar(s), ph ^ 1);
+      TICK(0);
+      const uint32_t a_hi = stage_base + s * SM::STAGE;
+      const uint32_t a_lo = a_hi + TC_BM * 128;      // 3xTF32: lo tile;  mixed: bf16(hi) tile, bf16(lo) tile 8 KB further
+      const uint32_t b_hi = a_hi + SM::A_STAGE;
+      if (pt == 0) {
+        if (dbg_notma) {
+          mbar_arrive(full_bar(s));
+        } else {
+          mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
+          const uint32_t* src = wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * BK;
+          bulk_g2s(b_hi, src, SM::B_STAGE, full_bar(s));          // [hi | lo] contiguous
         }
-        const int k = kc * TC_BK + c * 4;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_aff) {
-          sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + k));
-          sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + k));
-        }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = r0 + 16 * j;
-          float v[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
-          if (has_aff) {
-            v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y);
-            v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+      for (int j = 0; j < CPR; ++j) {
+        const int r = r0 + RSTEP * j;
+        float v[4] = {t.x[j].x, t.x[j].y, t.x[j].z, t.x[j].w};
+        v[0] = fmaxf(fmaf(v[0], t.sc.x, t.sh.x), relu_floor); v[1] = fmaxf(fmaf(v[1], t.sc.y, t.sh.y), relu_floor);
+        v[2] = fmaxf(fmaf(v[2], t.sc.z, t.sh.z), relu_floor); v[3] = fmaxf(fmaf(v[3], t.sc.w, t.sh.w), relu_floor);
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        if (MIXED) {
+          // hi = rna_tf32(v) for the TF32 main product; the two cross terms only need ~8 bits: bf16(hi), bf16(v - hi)
+          uint32_t hi[4]; float h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hi[q] = (__float_as_uint(v[q]) + 0x1000u) & 0xffffe000u;
+            h[q] = __uint_as_float(hi[q]); l[q] = v[q] - h[q];
           }
-          if (d.in_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          if (row0 + r >= P) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+          const uint32_t ob = bf16_tile_off(r, c);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + ob), "r"(pack_bf16x2(h[0], h[1])), "r"(pack_bf16x2(h[2], h[3])) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + TC_BM * 64 + ob), "r"(pack_bf16x2(l[0], l[1])), "r"(pack_bf16x2(l[2], l[3])) : "memory");
+        } else {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32(v[q], hi[q], lo[q]);
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+          for (int q = 0; q < 4; ++q) split4(v[q], hi[q], lo[q]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
-        if (it + 2 < total_it && !dbg_noload) fetch(it + 2, x);  // next tile of this group: in flight while we fence / arrive / wait
-        fence_proxy_async_smem();                  // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(full_bar(s));                  // every producer thread arrives after fencing its own stores
+      }
+      TICK(1);
+    };
+    auto publish = [&](uint32_t it) {
+      fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(full_bar(it % STAGES));          // every producer thread arrives after fencing its own stores
+      TICK(2);
+    };
+    XT t[DEPTH];
+#pragma unroll
+    for (int dd = 0; dd < DEPTH; ++dd) {
+      t[dd].sc = make_float4(1.f, 1.f, 1.f, 1.f); t[dd].sh = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < CPR; ++j) t[dd].x[j] = make_float4(1.f, 2.f, 3.f, 4.f);
+      fetch((uint32_t)grp + 2 * dd, t[dd]);
+    }
+    for (uint32_t it = (uint32_t)grp; it < total_it; it += 2 * DEPTH) {
+#pragma unroll
+      for (int dd = 0; dd < DEPTH; ++dd) {
+        const uint32_t i2 = it + 2 * dd;
+        if (i2 < total_it) {
+          produce(i2, t[dd]);
+          fetch(i2 + 2 * DEPTH, t[dd]);
+          publish(i2);
+        }
       }
     }
   } else if (warp == TC_MMA_WARP) {
@@ -193,26 +305,48 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const uint32_t buf = tcount & 1;
+      TICK(2);
       mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);
+      TICK(0);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + buf * BN;
       for (int kc = 0; kc < KC; ++kc, ++it) {
         const int s = it % STAGES;
+        TICK(2);
         mbar_wait(full_bar(s), (it / STAGES) & 1);
+        TICK(1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = stage_base + s * SM::STAGE;
           const uint32_t a_lo = a_hi + TC_BM * 128;
           const uint32_t b_hi = a_hi + SM::A_STAGE;
           const uint32_t b_lo = b_hi + BN * 128;
+          if (MIXED) {
+            // a*w ~= tf32(a_hi*w_hi) + bf16(a_lo)*bf16(w_hi) + bf16(a_hi)*bf16(w_lo): the cross terms are 2^-11 of the
+            // product, so 8 mantissa bits leave ~2^-19 relative error -- fp32-sgemm level (tools/tc_precision.py) --
+            // at 2/3 of the tensor time and shared-memory operand traffic of 3xTF32.
+            constexpr uint32_t idesc_b = make_idesc_bf16(TC_BM, BN);
+            const uint32_t a_hb = a_lo, a_lb = a_lo + TC_BM * 64, b_hb = b_lo, b_lb = b_lo + BN * 64;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t dah = make_kmajor_sw128_desc(a_hi + ks * 32), dal = make_kmajor_sw128_desc(a_lo + ks * 32);
-            const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ks * 32), dbl = make_kmajor_sw128_desc(b_lo + ks * 32);
-            umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32(tmem_d, make_kmajor_sw128_desc(a_hi + ks * 32), make_kmajor_sw128_desc(b_hi + ks * 32), idesc, (kc | ks) != 0);
             if (!(d.debug_flags & 8)) {
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb) {
+                umma_bf16(tmem_d, make_kmajor_sw64_desc(a_lb + kb * 32), make_kmajor_sw64_desc(b_hb + kb * 32), idesc_b, 1u);
+                umma_bf16(tmem_d, make_kmajor_sw64_desc(a_hb + kb * 32), make_kmajor_sw64_desc(b_lb + kb * 32), idesc_b, 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t dah = make_kmajor_sw128_desc(a_hi + ks * 32), dal = make_kmajor_sw128_desc(a_lo + ks * 32);
+              const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ks * 32), dbl = make_kmajor_sw128_desc(b_lo + ks * 32);
+              umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
+              if (!(d.debug_flags & 8)) {
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+              }
             }
           }
           umma_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
@@ -223,6 +357,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
     }
   } else {
     // =============================== epilogue warps 0..7 ========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
     const int q = warp & 3;                           // TMEM lane quarter
     const int half = warp >> 2;                       // handles chunks with (ch & 1) == half
     float* tw = trans + warp * (32 * 32);
@@ -244,7 +379,9 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
         const int gi = d.add_index ? __ldg(d.add_index + row) : row / d.add_group;
         addp = d.addend + (size_t)gi * d.ld_add + n0;
       }
+      TICK(5);
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      TICK(0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -258,52 +395,58 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
 #pragma unroll
           for (int j = 0; j < 8; ++j) a4[j] = __ldg(reinterpret_cast<const float4*>(addp + ch * 32) + j);
         }
+        // the bias is added AFTER the transpose, where a lane needs 4 (row view) / 1 (column view) values of it instead
+        // of all 32: two coalesced loads per chunk, in flight across the TMEM wait
+        const int l8 = lane & 7, rsub = lane >> 3;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float biasc = 0.f;
+        if (d.bias) {
+          bias4 = __ldg(reinterpret_cast<const float4*>(d.bias + cb) + l8);
+          biasc = __ldg(d.bias + cb + lane);
+        }
         tmem_ld_wait(raw);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (d.bias) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(d.bias + cb) + j);
-            v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-          }
-        }
         if (addp) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { v[4 * j] += a4[j].x; v[4 * j + 1] += a4[j].y; v[4 * j + 2] += a4[j].z; v[4 * j + 3] += a4[j].w; }
         }
+        TICK(1);
         // stage the 32x32 chunk in shared memory: row = lane, 16-byte chunk j stored at chunk (j ^ (lane & 7))
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(tw + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
-        if (d.Y) {
+        TICK(2);
+        if (d.Y && !(d.debug_flags & 32)) {
           // coalesced stores: 8 lanes cover one 128-byte row segment, a warp instruction writes 4 full lines
-          const int l8 = lane & 7, rsub = lane >> 3;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = 4 * i + rsub;
             if (r < nvalid) {
-              const float4 o = *reinterpret_cast<const float4*>(tw + r * 32 + ((l8 ^ (r & 7)) << 2));
+              float4 o = *reinterpret_cast<const float4*>(tw + r * 32 + ((l8 ^ (r & 7)) << 2));
+              o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
               *reinterpret_cast<float4*>(d.Y + (size_t)(wrow0 + r) * d.ldy + cb + l8 * 4) = o;
             }
           }
         }
+        TICK(3);
         // column view: lane owns column cb + lane; element (r, lane) at r*32 + (((lane>>2) ^ (r&7))<<2) + (lane&3)
         const int cl = ch * 32 + lane;                // column inside the tile
         const int csub = lane & 3, cchunk = lane >> 2;
-        if (want_stats && !want_grp) {
+        if (d.debug_flags & 64) {
+        } else if (want_stats && !want_grp) {
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
           if (nvalid == 32) {
 #pragma unroll
             for (int r = 0; r < 32; r += 2) {
-              const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub];
-              const float x1 = tw[(r + 1) * 32 + ((cchunk ^ ((r + 1) & 7)) << 2) + csub];
+              const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;
+              const float x1 = tw[(r + 1) * 32 + ((cchunk ^ ((r + 1) & 7)) << 2) + csub] + biasc;
               s0 += x0; q0 = fmaf(x0, x0, q0); s1 += x1; q1 = fmaf(x1, x1, q1);
             }
           } else {
-            for (int r = 0; r < nvalid; ++r) { const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub]; s0 += x0; q0 = fmaf(x0, x0, q0); }
+            for (int r = 0; r < nvalid; ++r) { const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc; s0 += x0; q0 = fmaf(x0, x0, q0); }
           }
           if (nvalid > 0) {                          // slices entirely past P have no partial row
             const size_t st = (size_t)(mt * 4 + q);
@@ -317,7 +460,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           const int hrows = (g == 16) ? 16 : 32;      // rows per in-warp group segment
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const float x = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub];
+            const float x = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;
             const bool ok = r < nvalid;
             if (ok) { s += x; ss = fmaf(x, x, ss); }
             if (r < hrows) {
@@ -362,6 +505,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           }
         }
         __syncwarp();                                   // tw is rewritten by the next chunk
+        TICK(4);
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -391,6 +535,15 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
     }
   }
 
+#ifdef USIP_TC_PROF
+  if (prof && lane == 0) {
+    acc[7] = (unsigned long long)(clock64() - tstart);
+    unsigned long long* o = d.debug_clocks + ((size_t)blockIdx.x * (TC_THREADS / 32) + warp) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+  }
+#endif
+#undef TICK
   // ---------------------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
@@ -400,21 +553,21 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   }
 }
 
-template <int BN, int STAGES, bool COMBINE>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
-  using SM = TcSmem<BN, STAGES, COMBINE>;
+  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
   static_assert(SM::BYTES <= 232448, "shared memory budget");
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
     if (e != cudaSuccess) { sm_count = 0; set_last_error("layer_fwd_tc smem attr"); return (int)e; }
   }
   const int m_tiles = cdiv(d.P, TC_BM), n_tiles = d.Cout / BN;
   const int grid = min(sm_count, m_tiles * n_tiles);
-  layer_fwd_tc_kernel<BN, STAGES, COMBINE><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
+  layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
   return check_launch("layer_fwd_tc_kernel");
 }
 
@@ -440,21 +593,30 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
   // precision 2 opts into the CTA-pair (cta_group::2) kernel for wide layers with enough tiles.  Measured on B200 it
   // is ~10-25% SLOWER than the single-CTA kernel with register prefetch, so it is not the default.
+  // default: pure 3xTF32.  debug_flags & 16 selects TF32 + 2 BF16 cross terms: measured on B200 it buys 2% (the kernel is
+  // not tensor-bound) and costs ~8x in error (still fp32-sgemm level, tools/tc_precision.py), so it stays an experiment.
+  const bool x3 = (d.debug_flags & 16) == 0;
   const bool pair = d.precision == 2 && d.Cout % 256 == 0 && tc2_eligible(d);
   if (pair) BN = 256;
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {
     const int total = d.Cout * (d.Cin / 4);
-    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.w_transposed, d.Cout, d.Cin, BN, wpack);
+    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.w_transposed, d.Cout, d.Cin, BN, (pair || x3) ? 0 : 1, wpack);
     int e = check_launch("tc_pack_weights_kernel");
     if (e) return e;
   }
   if (pair) return launch_tc2(d, wpack, st);
   const bool combine = (d.gmax || d.gmin) && d.group > 32;
-  if (combine) return BN == 128 ? launch_tc<128, 2, true>(d, wpack, st) : launch_tc<64, 3, true>(d, wpack, st);
-  if (BN == 256) return launch_tc<256, 2, false>(d, wpack, st);
-  if (BN == 128) return launch_tc<128, 3, false>(d, wpack, st);
-  return launch_tc<64, 4, false>(d, wpack, st);
+  if (x3) {
+    if (combine) return BN == 128 ? launch_tc<128, 2, true, false>(d, wpack, st) : launch_tc<64, 3, true, false>(d, wpack, st);
+    if (BN == 256) return launch_tc<256, 2, false, false>(d, wpack, st);
+    if (BN == 128) return launch_tc<128, 3, false, false>(d, wpack, st);
+    return launch_tc<64, 4, false, false>(d, wpack, st);
+  }
+  if (combine) return BN == 128 ? launch_tc<128, 2, true, true>(d, wpack, st) : launch_tc<64, 3, true, true>(d, wpack, st);
+  if (BN == 256) return launch_tc<256, 2, false, true>(d, wpack, st);
+  if (BN == 128) return launch_tc<128, 3, false, true>(d, wpack, st);
+  return launch_tc<64, 4, false, true>(d, wpack, st);
 }
 
 }  // namespace usip

@@ -1,6 +1,7 @@
 // tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (mbarrier, TMA bulk copy, TMEM, UMMA descriptors).
 #pragma once
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace usip {
 
@@ -63,6 +64,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 with BF16 operands, fp32 accumulate, M=128, N from idesc, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = TMEM lane).  The load is asynchronous: the
 // destination registers may only be read after tmem_ld_wait(), which also ties the registers ("+r") so the compiler
 // cannot hoist their uses above the wait.
@@ -111,6 +123,9 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32(1)@4, a=TF32(2)@7, b=TF32(2)@10,
 // a/b K-major (0), N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {   // c=F32(1)@4, a=BF16(1)@7, b=BF16(1)@10
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

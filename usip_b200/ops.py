@@ -152,7 +152,7 @@ def knn_nodes(pts, K):
 # ----------------------------------------------------------------------------- shared-MLP stack
 def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_shift=None, in_relu=False,
               addend=None, add_index=None, add_group=0, Y=None, ldy=None, stat_partial=None,
-              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False, w_transposed=False, debug_flags=0):
+              gmax=None, gmin=None, garg_max=None, garg_min=None, group=0, precision=0, tc_ws=None, tc_packed=False, w_transposed=False, debug_flags=0, debug_clocks=None):
     d = LayerDesc()
     d.X = X.data_ptr(); d.ldx = X.stride(0) if ldx is None else ldx
     d.P = P; d.Cin = Cin; d.Cout = Cout
@@ -176,6 +176,7 @@ def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_sh
     d.group = group
     d.precision = precision
     d.debug_flags = debug_flags
+    d.debug_clocks = debug_clocks.data_ptr() if debug_clocks is not None else None
     if precision in (1, 2, 3):
         if tc_ws is None:
             tc_ws = torch.empty((2 * Cin * Cout,), dtype=f32, device=X.device)
