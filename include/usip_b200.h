@@ -102,7 +102,7 @@ typedef struct usip_layer_desc {
   const int32_t* add_index;            /* row -> g  (NULL: g = row / add_group)                       */
   int32_t add_group;
   float* Y; int32_t ldy;               /* [P,Cout] output (NULL: not written)                         */
-  float* stat_partial;                 /* [nstat,2,Cout] per-slice (sum, sumsq) or NULL (see stat_rows) */
+  float* stat_partial;                 /* [usip_layer_stat_slots(desc),2,Cout] partial (sum, sumsq) rows, or NULL */
   float* gmax; float* gmin;            /* [P/group,Cout] per-group max / min of Y, or NULL            */
   int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
   int32_t group;
@@ -118,9 +118,11 @@ typedef struct usip_layer_desc {
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);
-/* rows per BN-statistic partial: stat_partial is [ceil(P / usip_layer_stat_rows(precision)), 2, Cout] */
+/* number of [2,Cout] partial rows usip_layer_fwd writes into stat_partial for this descriptor (P, Cout, precision,
+   group and whether group outputs are requested must already be filled in): one per 128-row tile for the SIMT kernel,
+   one per (CTA, 32-lane quarter) for the persistent tcgen05 kernel.  usip_bn_finalize sums them in a fixed order. */
+int usip_layer_stat_slots(const usip_layer_desc* desc);
 int usip_layer_tile_rows(void);
-int usip_layer_stat_rows(int precision);
 /* bytes of tc_workspace (hi/lo TF32 split of W, pre-swizzled into tcgen05 operand tiles) */
 int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout);
 

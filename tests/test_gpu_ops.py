@@ -211,8 +211,9 @@ def test_layer_fwd(P, Cin, Cout, group, precision):
     add_idx = rng.integers(0, G, size=P).astype(np.int32)
     Xd = cu(X)
     Y = torch.empty((P, Cout), device=dev())
-    tile = ops.stat_rows(precision); nt = (P + tile - 1) // tile
-    part = torch.zeros((nt, 2, Cout), device=dev())
+    want_grp = bool(group and P % group == 0)
+    nt = ops.stat_slots(P, Cout, precision, group if want_grp else 0, want_grp)
+    part = torch.full((nt, 2, Cout), float("nan"), device=dev())     # every slot must be written
     kw = {}
     if group and P % group == 0:
         Q = P // group

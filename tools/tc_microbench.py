@@ -13,8 +13,7 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
     X = torch.randn(P, Cin, device=dev); W = torch.randn(Cout, Cin, device=dev) / Cin ** 0.5
     b = torch.randn(Cout, device=dev); sc = torch.rand(Cin, device=dev) + 0.5; sh = torch.randn(Cin, device=dev)
     Y = torch.empty(P, Cout, device=dev) if write_y else None
-    nt = (P + 31) // 32
-    part = torch.empty(nt, 2, Cout, device=dev)
+    part = torch.empty(ops.stat_slots(P, Cout, 1, group, bool(group)), 2, Cout, device=dev)
     ws = torch.empty(2 * Cin * Cout, device=dev)
     kw = {}
     if group:

@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 X = torch.randn(P, Cin, device=dev); W = torch.randn(Cout, Cin, device=dev) / Cin ** 0.5
 b = torch.randn(Cout, device=dev); sc = torch.rand(Cin, device=dev) + 0.5; sh = torch.randn(Cin, device=dev)
 Y = None if group else torch.empty(P, Cout, device=dev)
-part = torch.empty((P + 31) // 32, 2, Cout, device=dev)
+part = torch.empty(ops.stat_slots(P, Cout, 1, group, bool(group)), 2, Cout, device=dev)
 ws = torch.empty(2 * Cin * Cout, device=dev)
 kw = dict(gmax=torch.empty(P // group, Cout, device=dev), gmin=torch.empty(P // group, Cout, device=dev), group=group) if group else {}
 for i in range(4):

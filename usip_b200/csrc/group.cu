@@ -9,9 +9,11 @@ namespace usip {
 // ------------------------------------------------------------------------------------------------
 // som_assign: brute-force nearest node, node tile broadcast from shared memory, PTS points / thread.
 // ------------------------------------------------------------------------------------------------
-constexpr int ASSIGN_THREADS = 256;
-constexpr int ASSIGN_PTS = 4;
-constexpr int ASSIGN_NODE_CHUNK = 2048;  // float4 per node -> 32 KB static-ish chunk
+// 128 threads x 2 points: at the KITTI shape (16 clouds x 16384 points) that is 1024 CTAs, ~6.9 per SM -- 256 CTAs of
+// 1024 points left 40 SMs with twice the work of the rest.
+constexpr int ASSIGN_THREADS = 128;
+constexpr int ASSIGN_PTS = 2;
+constexpr int ASSIGN_NODE_CHUNK = 1024;  // float4 per node -> 16 KB
 
 __global__ void __launch_bounds__(ASSIGN_THREADS)
 som_assign_kernel(const float* __restrict__ xyz, const float* __restrict__ node,

@@ -254,40 +254,46 @@ layer_fwd_simt_kernel(const usip_layer_desc d) {
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int BNF_C = 8;       // channels per CTA: one 32-byte sector per partial row, C/8 CTAs
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int C,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var,
                    float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  // block = 32 channels x 32 tile slices; every thread keeps 8 independent loads in flight per batch so the
-  // reduction is bandwidth- not latency-bound (the partial buffer has up to thousands of rows)
-  __shared__ double sh[2][32][33];
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
+  // block = 8 channels x 128 partial-row slices; every thread keeps 8 independent loads in flight per batch so the
+  // reduction is bandwidth- not latency-bound
+  constexpr int SL = 1024 / BNF_C;
+  __shared__ double sh[2][SL][BNF_C + 1];
+  const int cl = threadIdx.x % BNF_C, sl = threadIdx.x / BNF_C;
+  const int c = blockIdx.x * BNF_C + cl;
   double s = 0.0, ss = 0.0;
   if (c < C) {
     int t = sl;
-    for (; t + 7 * 32 < ntiles; t += 8 * 32) {
+    for (; t + 7 * SL < ntiles; t += 8 * SL) {
       float a[8], b[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        a[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 0) * C + c);
-        b[u] = __ldg(part + ((size_t)(t + u * 32) * 2 + 1) * C + c);
+        a[u] = __ldg(part + ((size_t)(t + u * SL) * 2 + 0) * C + c);
+        b[u] = __ldg(part + ((size_t)(t + u * SL) * 2 + 1) * C + c);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
     }
-    for (; t < ntiles; t += 32) {
+    for (; t < ntiles; t += SL) {
       s += (double)part[((size_t)t * 2 + 0) * C + c];
       ss += (double)part[((size_t)t * 2 + 1) * C + c];
     }
   }
   sh[0][sl][cl] = s; sh[1][sl][cl] = ss;
   __syncthreads();
+  // tree over the 128 slices (fixed order -> deterministic)
+  for (int off = SL / 2; off > 0; off >>= 1) {
+    if (sl < off) { sh[0][sl][cl] += sh[0][sl + off][cl]; sh[1][sl][cl] += sh[1][sl + off][cl]; }
+    __syncthreads();
+  }
   if (sl == 0 && c < C) {
-    double S = 0.0, SS = 0.0;
-    for (int t = 0; t < 32; ++t) { S += sh[0][t][cl]; SS += sh[1][t][cl]; }
+    const double S = sh[0][0][cl], SS = sh[1][0][cl];
     double mean = S / count;
     double var = SS / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -462,14 +468,17 @@ static int launch_layer_simt(const usip_layer_desc& d, cudaStream_t st) {
 }
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st);   // mlp_tc.cu
-int tc_stat_rows();
+int tc_stat_slots(const usip_layer_desc& d);
 
 }  // namespace usip
 
 using namespace usip;
 
 extern "C" int usip_layer_tile_rows(void) { return L_BM; }
-extern "C" int usip_layer_stat_rows(int precision) { return precision != 0 ? tc_stat_rows() : L_BM; }
+extern "C" int usip_layer_stat_slots(const usip_layer_desc* dp) {
+  if (!dp || dp->P <= 0 || dp->Cout <= 0) return 0;
+  return dp->precision != 0 ? tc_stat_slots(*dp) : cdiv(dp->P, L_BM);
+}
 extern "C" int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout) { return (int64_t)2 * Cin * Cout * 4; }
 
 extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
@@ -500,7 +509,7 @@ extern "C" int usip_bn_finalize(const float* stat_partial, int ntiles, int64_t c
                                 float* running_var, float* scale, float* shift, float* save_mean,
                                 float* save_invstd, void* stream) {
   USIP_REQUIRE(stat_partial && scale && shift && ntiles > 0 && count > 0 && C > 0, "bn_finalize: bad args");
-  bn_finalize_kernel<<<cdiv(C, 32), 1024, 0, (cudaStream_t)stream>>>(stat_partial, ntiles, (double)count, C, gamma,
+  bn_finalize_kernel<<<cdiv(C, BNF_C), 1024, 0, (cudaStream_t)stream>>>(stat_partial, ntiles, (double)count, C, gamma,
                                                                     beta, eps, momentum, running_mean, running_var,
                                                                     scale, shift, save_mean, save_invstd);
   return check_launch("bn_finalize_kernel");

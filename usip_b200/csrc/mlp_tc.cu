@@ -366,6 +366,17 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
     const bool want_grp = (d.gmax != nullptr) || (d.gmin != nullptr);
     // staging tile addressing: element (r, c) lives at r*32 + (((c>>2) ^ (r&7))<<2) + (c&3)
     uint32_t tcount = 0;
+    // BN statistics: ONE partial row per (CTA, lane quarter), accumulated over the CTA's tiles.  The grid is a multiple
+    // of n_tiles, so a CTA always works on the same column tile and column (slot, c) belongs to exactly one lane of one
+    // warp for the whole kernel: a plain read-modify-write of an L2-resident float, first tile stores.  (Per-32-row
+    // partials were 1/16 of the bytes of Y and made usip_bn_finalize the #2 kernel of the step.)
+    float* stat_row = want_stats ? d.stat_partial + ((size_t)(blockIdx.x / n_tiles) * 4 + q) * 2 * Cout : nullptr;
+    auto stat_accumulate = [&](int col, float s, float ss) {
+      float* ps = stat_row + col;
+      float* pq = stat_row + Cout + col;
+      if (tcount != 0) { s += *ps; ss += *pq; }
+      *ps = s; *pq = ss;
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int row0 = mt * TC_BM, n0 = nt * BN;
@@ -448,11 +459,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           } else {
             for (int r = 0; r < nvalid; ++r) { const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc; s0 += x0; q0 = fmaf(x0, x0, q0); }
           }
-          if (nvalid > 0) {                          // slices entirely past P have no partial row
-            const size_t st = (size_t)(mt * 4 + q);
-            d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s0 + s1;
-            d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = q0 + q1;
-          }
+          stat_accumulate(cb + lane, s0 + s1, q0 + q1);
         } else if (want_grp) {
           float s = 0.f, ss = 0.f;
           float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
@@ -471,11 +478,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
               if (ok && x < mn1) { mn1 = x; an1 = r; }
             }
           }
-          if (want_stats && nvalid > 0) {
-            const size_t st = (size_t)(mt * 4 + q);
-            d.stat_partial[(st * 2 + 0) * Cout + cb + lane] = s;
-            d.stat_partial[(st * 2 + 1) * Cout + cb + lane] = ss;
-          }
+          if (want_stats) stat_accumulate(cb + lane, s, ss);
           if (g == 16) {
             const int grow = wrow0 / 16;
             if (nvalid > 0) {
@@ -553,20 +556,35 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   }
 }
 
-template <int BN, int STAGES, bool COMBINE, bool MIXED>
-static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
-  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
-  static_assert(SM::BYTES <= 232448, "shared memory budget");
+// persistent grid: one CTA per SM, rounded down to a multiple of the column-tile count so that a CTA keeps its column
+// tile (weights stay hot, BN-statistic slots are per CTA)
+static int tc_grid(int P, int Cout, int BN, int sm_count) {
+  const int m_tiles = cdiv(P, TC_BM), n_tiles = Cout / BN;
+  const int g = min(sm_count, m_tiles * n_tiles);
+  return max(n_tiles, g / n_tiles * n_tiles);
+}
+static int tc_sm_count() {
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
-    if (e != cudaSuccess) { sm_count = 0; set_last_error("layer_fwd_tc smem attr"); return (int)e; }
   }
-  const int m_tiles = cdiv(d.P, TC_BM), n_tiles = d.Cout / BN;
-  const int grid = min(sm_count, m_tiles * n_tiles);
+  return sm_count;
+}
+
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
+static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
+  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
+  static_assert(SM::BYTES <= 232448, "shared memory budget");
+  static bool attr_set = false;
+  const int sm_count = tc_sm_count();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    if (e != cudaSuccess) { set_last_error("layer_fwd_tc smem attr"); return (int)e; }
+    attr_set = true;
+  }
+  const int grid = tc_grid(d.P, d.Cout, BN, sm_count);
   layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
   return check_launch("layer_fwd_tc_kernel");
 }
@@ -575,7 +593,22 @@ bool tc2_eligible(const usip_layer_desc& d);                                   /
 int launch_tc2(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st);
 
 int tc_tile_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
-int tc_stat_rows() { return TC_STAT_ROWS; }
+
+// column-tile width the single-CTA kernel will use for this layer
+static int tc_pick_bn(const usip_layer_desc& d) {
+  int BN = tc_tile_n(d.Cout);
+  if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
+  // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
+  while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
+  return BN;
+}
+
+// number of [2, Cout] BN-statistic partial rows usip_layer_fwd writes for this descriptor (tensor-core precisions)
+int tc_stat_slots(const usip_layer_desc& d) {
+  if (d.precision == 2 && d.Cout % 256 == 0 && tc2_eligible(d)) return cdiv(d.P, TC_STAT_ROWS);   // pair kernel: per 32 rows
+  const int BN = tc_pick_bn(d);
+  return tc_grid(d.P, d.Cout, BN, tc_sm_count()) / (d.Cout / BN) * 4;
+}
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   USIP_REQUIRE(d.Cin % TC_BK == 0 && d.Cout % 64 == 0, "layer_fwd_tc: needs Cin%32==0 and Cout%64==0");
@@ -587,10 +620,7 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
                "layer_fwd_tc: scale/shift alignment");
   USIP_REQUIRE(d.tc_workspace && d.tc_workspace_bytes >= (int64_t)2 * d.Cout * d.Cin * 4, "layer_fwd_tc: workspace too small");
   if (d.gmax || d.gmin) USIP_REQUIRE(d.group == 16 || d.group == 32 || d.group == 64 || d.group == 128, "layer_fwd_tc: group must be 16/32/64/128");
-  int BN = tc_tile_n(d.Cout);
-  if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
-  // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
-  while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
+  int BN = tc_pick_bn(d);
   // precision 2 opts into the CTA-pair (cta_group::2) kernel for wide layers with enough tiles.  Measured on B200 it
   // is ~10-25% SLOWER than the single-CTA kernel with register prefetch, so it is not the default.
   // default: pure 3xTF32.  debug_flags & 16 selects TF32 + 2 BF16 cross terms: measured on B200 it buys 2% (the kernel is

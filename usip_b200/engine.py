@@ -110,7 +110,6 @@ class LayerRunner:
         self.use_tc = use_tc
         self.dev = dev
         self.tile = ops.tile_rows()
-        self.stat_rows = {0: ops.stat_rows(0), 1: ops.stat_rows(1), 2: ops.stat_rows(2), 3: ops.stat_rows(3)}
 
     def bn_state(self, norm, part, ntiles, count, momentum):
         C = norm.weight.numel()
@@ -129,9 +128,8 @@ class LayerRunner:
                                st.scale, st.shift)
         return st
 
-    def partials(self, P, Cout, prec=0):
-        rows = self.stat_rows[prec]
-        ntiles = (P + rows - 1) // rows
+    def partials(self, P, Cout, prec=0, group=0, want_group=False):
+        ntiles = ops.stat_slots(P, Cout, prec, group, want_group)
         if not self.training:
             return None, ntiles
         return torch.empty((ntiles, 2, Cout), dtype=f32, device=self.dev), ntiles
@@ -143,7 +141,7 @@ class LayerRunner:
         if Y is None and write_y:
             Y = torch.empty((P, Cout), dtype=f32, device=self.dev)
         prec = _precision_for(P, Cin, Cout, self.use_tc)
-        part, ntiles = self.partials(P, Cout, prec) if norm is not None else (None, 0)
+        part, ntiles = self.partials(P, Cout, prec, group, want_group) if norm is not None else (None, 0)
         grp = None
         if want_group:
             Q = P // group

@@ -72,8 +72,7 @@ def _standalone_layer_forward(layer, x, epoch):
     dev = x.device
     Y = torch.empty((P, Cout), dtype=torch.float32, device=dev)
     has_bn = layer.normalization == "batch"
-    tile = ops.stat_rows(0)
-    nt = (P + tile - 1) // tile
+    nt = ops.stat_slots(P, Cout, 0)
     part = torch.empty((nt, 2, Cout), dtype=torch.float32, device=dev) if (has_bn and layer.training) else None
     ops.layer_fwd(rows, W, layer.conv.bias.detach(), P, C, Cout, Y=Y, stat_partial=part)
     relu = layer.activation == "relu"

@@ -33,8 +33,12 @@ def tile_rows():
     return _lib.load().usip_layer_tile_rows()
 
 
-def stat_rows(precision):
-    return _lib.load().usip_layer_stat_rows(int(precision))
+def stat_slots(P, Cout, precision=0, group=0, want_group=False):
+    """Rows of the [slots, 2, Cout] BN-statistic partial buffer usip_layer_fwd fills for this layer shape."""
+    d = _lib.LayerDesc()
+    d.P, d.Cout, d.precision, d.group = int(P), int(Cout), int(precision), int(group)
+    d.gmax = 1 if want_group else None          # only tested for NULL-ness by the query
+    return _lib.load().usip_layer_stat_slots(ctypes.byref(d))
 
 
 # ----------------------------------------------------------------------------- reference operators
