@@ -53,6 +53,10 @@ int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
 int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
                         int32_t* out_idx, float* out_group, float* out_rows, int ld_rows,
                         void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);
+/* profiling aid: clock64() stamps of CTA 0 of the last single-kernel (cluster) usip_ball_group_f32 launch on the current
+   device -- start, points loaded, grid known, histogram done, cursors final, cell-sorted array done, queries done, exit.
+   Synchronises (cudaMemcpyFromSymbol). */
+int usip_ball_group_phase_clocks(unsigned long long* out8);
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 
 /* operations.knn_gather_by_indexing                         models/operations.py:271-287

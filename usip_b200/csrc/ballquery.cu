@@ -6,6 +6,7 @@
 // Both keep the reference's order-dependent semantics: FIRST K hits in ascending point index,
 // `<=` on the sqrt distance, 0 hits -> zeros, u<K hits -> cyclic repeat out[u+i] = out[i % u].
 #include "common.cuh"
+#include <cstdlib>
 
 namespace usip {
 
@@ -120,115 +121,13 @@ constexpr int BG_CAP = 256;
 
 struct BgGrid { float ox, oy, oz, inv_h; int nx, ny, nz, ok; };
 
-__global__ void __launch_bounds__(1024)
-bg_bbox_kernel(const float* __restrict__ xyz, float radius, BgGrid* __restrict__ grids, int N) {
-  __shared__ float smin[3][32], smax[3][32];
-  const int b = blockIdx.x;
-  const float* p = xyz + (size_t)b * 3 * N;
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  bool bad = false;
-  for (int n = threadIdx.x; n < N; n += 1024)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float v = p[(size_t)c * N + n];
-      bad |= !(fabsf(v) <= 1e30f);
-      mn[c] = fminf(mn[c], v); mx[c] = fmaxf(mx[c], v);
-    }
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned anybad = __ballot_sync(0xffffffffu, bad);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
-      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
-    }
-    if (lane == 0) { smin[c][w] = anybad ? NAN : mn[c]; smax[c][w] = mx[c]; }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    BgGrid g; g.ok = 1;
-    float lo[3], hi[3];
-    for (int c = 0; c < 3; ++c) {
-      lo[c] = INFINITY; hi[c] = -INFINITY;
-      for (int i = 0; i < 32; ++i) { if (smin[c][i] != smin[c][i]) g.ok = 0; lo[c] = fminf(lo[c], smin[c][i]); hi[c] = fmaxf(hi[c], smax[c][i]); }
-    }
-    if (!(radius >= 0.f) || !(radius <= 1e30f)) g.ok = 0;
-    float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-    float h = fmaxf(fmaxf(radius * 1.001f, ext * (1.0f / 126.0f)), 1e-6f);
-    int nx = 1, ny = 1, nz = 1;
-    if (g.ok) {
-      for (int it = 0; it < 64; ++it) {
-        nx = (int)floorf((hi[0] - lo[0]) / h) + 1; ny = (int)floorf((hi[1] - lo[1]) / h) + 1; nz = (int)floorf((hi[2] - lo[2]) / h) + 1;
-        if ((long long)nx * ny * nz <= BG_MAX_CELLS) break;
-        h *= 1.26f;
-      }
-      if ((long long)nx * ny * nz > BG_MAX_CELLS) g.ok = 0;
-    }
-    g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = 1.0f / h; g.nx = nx; g.ny = ny; g.nz = nz;
-    grids[b] = g;
-  }
-}
-
 __device__ __forceinline__ int bg_cell1(float v, float o, float inv_h, int n) {
   int c = (int)floorf((v - o) * inv_h);
   return min(max(c, 0), n - 1);
 }
 
-// per point: cell id + histogram; also writes the 32-byte AoS record (x,y,z,feat...) used by the gather
-__global__ void __launch_bounds__(256)
-bg_count_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const BgGrid* __restrict__ grids,
-                int32_t* __restrict__ cell_of, int32_t* __restrict__ cell_cnt, float* __restrict__ rec, int S, int N) {
-  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= N) return;
-  const BgGrid g = grids[b];
-  const float* p = xyz + (size_t)b * 3 * N;
-  const float x = p[n], y = p[N + n], z = p[2 * N + n];
-  float r[8] = {x, y, z, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < S && c < 5; ++c) r[3 + c] = feat[((size_t)b * S + c) * N + n];
-  float4* rp = reinterpret_cast<float4*>(rec + ((size_t)b * N + n) * 8);
-  rp[0] = make_float4(r[0], r[1], r[2], r[3]); rp[1] = make_float4(r[4], r[5], r[6], r[7]);
-  if (!g.ok) return;
-  const int cell = (bg_cell1(z, g.oz, g.inv_h, g.nz) * g.ny + bg_cell1(y, g.oy, g.inv_h, g.ny)) * g.nx + bg_cell1(x, g.ox, g.inv_h, g.nx);
-  cell_of[(size_t)b * N + n] = cell;
-  atomicAdd(&cell_cnt[(size_t)b * (BG_MAX_CELLS + 1) + cell], 1);
-}
-
-// exclusive scan of the cell histogram (one CTA per cloud); cell_cnt becomes cell_start, fill cursor zeroed
-__global__ void __launch_bounds__(1024)
-bg_scan_kernel(int32_t* __restrict__ cell_cnt, int32_t* __restrict__ cell_fill, const BgGrid* __restrict__ grids) {
-  __shared__ int part[1024];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const BgGrid g = grids[b];
-  if (!g.ok) return;
-  const int cells = g.nx * g.ny * g.nz;
-  int32_t* cnt = cell_cnt + (size_t)b * (BG_MAX_CELLS + 1);
-  int32_t* fill = cell_fill + (size_t)b * BG_MAX_CELLS;
-  const int per = (cells + 1023) / 1024, lo = min(tid * per, cells), hi = min(lo + per, cells);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += cnt[i];
-  part[tid] = s;
-  __syncthreads();
-  if (tid == 0) { int run = 0; for (int t = 0; t < 1024; ++t) { int v = part[t]; part[t] = run; run += v; } cnt[cells] = run; }
-  __syncthreads();
-  int run = part[tid];
-  for (int i = lo; i < hi; ++i) { int v = cnt[i]; cnt[i] = run; fill[i] = 0; run += v; }
-}
-
-__global__ void __launch_bounds__(256)
-bg_fill_kernel(const float* __restrict__ xyz, const BgGrid* __restrict__ grids, const int32_t* __restrict__ cell_of,
-               const int32_t* __restrict__ cell_start, int32_t* __restrict__ cell_fill, float4* __restrict__ sorted, int N) {
-  const int b = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
-  if (n >= N || !grids[b].ok) return;
-  const int cell = cell_of[(size_t)b * N + n];
-  const int pos = cell_start[(size_t)b * (BG_MAX_CELLS + 1) + cell] + atomicAdd(&cell_fill[(size_t)b * BG_MAX_CELLS + cell], 1);
-  const float* p = xyz + (size_t)b * 3 * N;
-  sorted[(size_t)b * N + pos] = make_float4(p[n], p[N + n], p[2 * N + n], __int_as_float(n));
-}
-
 // Fused per-cloud preparation (one CTA per cloud): bounding box -> grid -> shared-memory cell histogram -> exclusive
-// scan -> cell-sorted point array + 32-byte AoS records.  Replaces bbox/count/scan/fill (4 launches + memset) when
-// the grid fits in shared memory.
+// scan -> cell-sorted point array + 32-byte AoS records.  Used for clouds too large for the single-kernel cluster path (ballgroup_cluster.cu).
 constexpr int BG_PREP_CELLS = 49152;      // int32 counters in dynamic shared memory (192 KB)
 
 __global__ void __launch_bounds__(1024)
@@ -462,9 +361,21 @@ static float radius_to_tmax(float radius) {
   return t;
 }
 
+bool bg_cluster_eligible(int S, int N, int K);                                         // ballgroup_cluster.cu
+int launch_bg_cluster(const float* xyz, const float* feat, const float* centers, float radius, float t_max,
+                      int32_t* out_idx, float* out_group, float* out_rows, int ld_rows, int B, int S, int N, int M, int K,
+                      cudaStream_t st);
+
+int bg_cluster_phase_clocks(unsigned long long* host8);
+
 }  // namespace usip
 
 using namespace usip;
+
+extern "C" int usip_ball_group_phase_clocks(unsigned long long* out8) {
+  USIP_REQUIRE(out8, "ball_group_phase_clocks: null");
+  return bg_cluster_phase_clocks(out8);
+}
 
 extern "C" int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
                                         int B, int M, int N, int K, void* stream) {
@@ -476,17 +387,15 @@ extern "C" int usip_ball_query_dist_f32(const float* dist, float radius, int32_t
 
 static size_t bg_align(size_t x) { return (x + 255) & ~(size_t)255; }
 struct BgScratch {
-  BgGrid* grids; int32_t* cell_cnt; int32_t* cell_fill; int32_t* cell_of; float4* sorted; float* rec; size_t total;
+  BgGrid* grids; int32_t* cell_cnt; float4* sorted; float* rec; size_t total;
   BgScratch(void* base, int B, int N) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += bg_align(bytes); return o; };
     size_t o_g = take(sizeof(BgGrid) * B), o_c = take(sizeof(int32_t) * (size_t)B * (BG_MAX_CELLS + 1));
-    size_t o_f = take(sizeof(int32_t) * (size_t)B * BG_MAX_CELLS), o_o = take(sizeof(int32_t) * (size_t)B * N);
     size_t o_s = take(sizeof(float4) * (size_t)B * N), o_r = take(sizeof(float) * 8 * (size_t)B * N);
     total = off;
     char* p = (char*)base;
-    grids = (BgGrid*)(p + o_g); cell_cnt = (int32_t*)(p + o_c); cell_fill = (int32_t*)(p + o_f);
-    cell_of = (int32_t*)(p + o_o); sorted = (float4*)(p + o_s); rec = (float*)(p + o_r);
+    grids = (BgGrid*)(p + o_g); cell_cnt = (int32_t*)(p + o_c); sorted = (float4*)(p + o_s); rec = (float*)(p + o_r);
   }
 };
 
@@ -505,6 +414,11 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const float t_max = radius_to_tmax(radius);
   const int rows = B * M;
+  // single-kernel path: one 8-CTA cluster per cloud, everything in distributed shared memory (no scratch needed).
+  // USIP_BG_NO_CLUSTER=1 forces the older two-kernel grid path (A/B measurements only).
+  static const bool no_cluster = getenv("USIP_BG_NO_CLUSTER") != nullptr;
+  if (!no_cluster && bg_cluster_eligible(S, N, K) && (!out_rows || (reinterpret_cast<uintptr_t>(out_rows) % 16) == 0))
+    return launch_bg_cluster(xyz, feat, centers, radius, t_max, out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, st);
   const bool grid_ok = scratch && S <= 5 && (reinterpret_cast<uintptr_t>(scratch) % 256) == 0 &&
                        scratch_bytes >= usip_ball_group_scratch_bytes(B, S, N, M, K) - 256 &&
                        (!out_rows || (reinterpret_cast<uintptr_t>(out_rows) % 16) == 0);
