@@ -49,14 +49,11 @@ int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
  *   out_idx (B,M,K) i32      (bit-identical to ball_query on torch.norm(centers-xyz))
  *   out_group (B,3+S,M,K) f32 = x_aug gathered, xyz channels minus the centre  (`x_features`) (or NULL)
  *   out_rows  [B*M*K, ld_rows] f32: the same group as point-major rows for the MLP stack (or NULL)
- * scratch_i32: B*(N + 2*cells+2) + ... see usip_ball_group_scratch_bytes(). */
+ * scratch: usip_ball_group_scratch_bytes() bytes, 256-byte aligned (cell table, cell-sorted 32-byte records); without it
+ * (or for S > 4) the brute-force single-kernel path runs. */
 int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
                         int32_t* out_idx, float* out_group, float* out_rows, int ld_rows,
                         void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);
-/* profiling aid: clock64() stamps of CTA 0 of the last single-kernel (cluster) usip_ball_group_f32 launch on the current
-   device -- start, points loaded, grid known, histogram done, cursors final, cell-sorted array done, queries done, exit.
-   Synchronises (cudaMemcpyFromSymbol). */
-int usip_ball_group_phase_clocks(unsigned long long* out8);
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 
 /* operations.knn_gather_by_indexing                         models/operations.py:271-287

@@ -56,7 +56,6 @@ SIGNATURES = {
                                            c_int, c_int, c_int, c_int, c_ptr]),
     "usip_layer_fwd": (c_int, [ctypes.POINTER(LayerDesc), c_ptr]),
     "usip_layer_tile_rows": (c_int, []),
-    "usip_ball_group_phase_clocks": (c_int, [c_ptr]),
     "usip_layer_stat_slots": (c_int, [ctypes.POINTER(LayerDesc)]),
     "usip_layer_tc_workspace_bytes": (c_i64, [c_int, c_int]),
     "usip_bn_finalize": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr,
@@ -125,7 +124,7 @@ def load():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-KERNELS_PER_CALL = {"usip_cluster_sort": 3, "usip_pairwise_min_f32": 3, "usip_layer_fwd_tc": 2, "usip_ball_group_f32": 2}
+KERNELS_PER_CALL = {"usip_cluster_sort": 3, "usip_pairwise_min_f32": 3, "usip_layer_fwd_tc": 2, "usip_ball_group_f32": 4}
 LAUNCHES = [0]
 
 
