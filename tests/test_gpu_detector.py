@@ -173,6 +173,32 @@ def test_forward_loss_cuda_graph_matches_eager():
         assert torch.equal(torch.cat([md.src_sigmas, md.dst_sigmas]), eager[2])
 
 
+def test_prefetch_input_matches_set_input():
+    """prefetch_input() stages the next batch on a copy stream; set_input() with the same tensors adopts it, with other
+    tensors it copies as usual.  The loss must be the one of the batch passed to set_input either way."""
+    g, d, P, md = _setup("detector_kitti_small.npz", True)
+    keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
+    d2 = orc.synth_pair(2, 2048, 64, 4, kind="lidar", seed=999)
+    a = [torch.from_numpy(d[k]).pin_memory() for k in keys]
+    b = [torch.from_numpy(d2[k]).pin_memory() for k in keys]
+    sd0 = {k: v.clone() for k, v in md.detector.state_dict().items()}
+    ref = []
+    for batch in (a, b):
+        md.detector.load_state_dict(sd0)
+        md.set_input(*batch); md.forward_loss(epoch=0, train_bn=True, graph=False); ref.append(md.loss.item())
+    assert ref[0] != ref[1]
+    md.detector.load_state_dict(sd0)
+    md.prefetch_input(*a); md.set_input(*a)                    # adopted
+    assert md._staged is None
+    md.prefetch_input(*b)                                      # staged while step a runs
+    md.forward_loss(epoch=0, train_bn=True, graph=False); assert md.loss.item() == ref[0]
+    md.detector.load_state_dict(sd0)
+    md.set_input(*b); md.forward_loss(epoch=0, train_bn=True, graph=False); assert md.loss.item() == ref[1]
+    md.detector.load_state_dict(sd0)
+    md.prefetch_input(*b); md.set_input(*a)                    # different tensors: plain copy, the stale stage is dropped later
+    md.forward_loss(epoch=0, train_bn=True, graph=False); assert md.loss.item() == ref[0]
+
+
 @pytest.mark.parametrize("use_tc", [False, True])
 def test_detector_ragged_sizes_vs_oracle(use_tc):
     """Sizes that are not multiples of any tile: N=3001 points (what random point dropout produces), M=50 nodes, B'=6 clouds,

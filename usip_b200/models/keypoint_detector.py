@@ -69,19 +69,38 @@ class ModelDetector():
             self._dp.allreduce_mean()
 
     # ------------------------------------------------------------------ reference API
+    _INPUT_FIELDS = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "src_R_dst", "src_scale_dst", "src_shift_dst")
+
     def set_input(self, src_pc, src_sn, src_node, dst_pc, dst_sn, dst_node, src_R_dst, src_scale_dst, src_shift_dst):
+        """keypoint_detector.py:120-134.  If the same host tensors were staged by prefetch_input(), the staged device
+        copies are adopted with a stream-side wait instead of nine copies and a host synchronisation."""
+        args = (src_pc, src_sn, src_node, dst_pc, dst_sn, dst_node, src_R_dst, src_scale_dst, src_shift_dst)
+        st = getattr(self, "_staged", None)
+        if st is not None and len(st[0]) == len(args) and all(a is b for a, b in zip(st[0], args)):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(st[2])
+            for k, v in zip(self._INPUT_FIELDS, st[1]):
+                v.record_stream(cur)                                  # allocated on the copy stream, consumed here
+                setattr(self, k, v)
+            self._staged = None
+            return
         dev = self.opt.device
-        nb = True
-        self.src_pc = src_pc.float().to(dev, non_blocking=nb).detach()
-        self.src_sn = src_sn.float().to(dev, non_blocking=nb).detach()
-        self.src_node = src_node.float().to(dev, non_blocking=nb).detach()
-        self.dst_pc = dst_pc.float().to(dev, non_blocking=nb).detach()
-        self.dst_sn = dst_sn.float().to(dev, non_blocking=nb).detach()
-        self.dst_node = dst_node.float().to(dev, non_blocking=nb).detach()
-        self.src_R_dst = src_R_dst.float().to(dev, non_blocking=nb).detach()
-        self.src_scale_dst = src_scale_dst.float().to(dev, non_blocking=nb).detach()
-        self.src_shift_dst = src_shift_dst.float().to(dev, non_blocking=nb).detach()
+        for k, a in zip(self._INPUT_FIELDS, args):
+            setattr(self, k, a.float().to(dev, non_blocking=True).detach())
         torch.cuda.synchronize()                                  # keypoint_detector.py:134
+
+    def prefetch_input(self, *args):
+        """Not in the reference: stage the NEXT batch (same nine tensors as set_input, ideally pinned) with asynchronous
+        host-to-device copies on a dedicated stream, so that the transfer overlaps the step that is running.  The
+        following set_input() with the same tensor objects adopts the staged copies."""
+        dev = self.opt.device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            staged = [a.float().to(dev, non_blocking=True).detach() for a in args]
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (tuple(args), staged, ev)
 
     def forward(self, pc, sn, node, is_train=False, epoch=None):
         with torch.cuda.device(pc.get_device()):
