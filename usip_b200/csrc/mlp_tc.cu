@@ -465,17 +465,32 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
           int ax0 = 0, an0 = 0, ax1 = 0, an1 = 0;
           const int hrows = (g == 16) ? 16 : 32;      // rows per in-warp group segment
+          if (nvalid == 32 && !d.garg_max && !d.garg_min) {
+            // forward-only fast path (full slice, no arg outputs): 4 instructions per element instead of ~12
+            float s1 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const float x0 = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;
+              const float x1 = tw[(r + 16) * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;       // (r + 16) & 7 == r & 7
+              s += x0; ss = fmaf(x0, x0, ss); s1 += x1; q1 = fmaf(x1, x1, q1);
+              mx0 = fmaxf(mx0, x0); mn0 = fminf(mn0, x0);
+              if (hrows == 16) { mx1 = fmaxf(mx1, x1); mn1 = fminf(mn1, x1); }
+              else { mx0 = fmaxf(mx0, x1); mn0 = fminf(mn0, x1); }
+            }
+            s += s1; ss += q1;
+          } else {
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const float x = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;
-            const bool ok = r < nvalid;
-            if (ok) { s += x; ss = fmaf(x, x, ss); }
-            if (r < hrows) {
-              if (ok && x > mx0) { mx0 = x; ax0 = r; }
-              if (ok && x < mn0) { mn0 = x; an0 = r; }
-            } else {
-              if (ok && x > mx1) { mx1 = x; ax1 = r; }
-              if (ok && x < mn1) { mn1 = x; an1 = r; }
+            for (int r = 0; r < 32; ++r) {
+              const float x = tw[r * 32 + ((cchunk ^ (r & 7)) << 2) + csub] + biasc;
+              const bool ok = r < nvalid;
+              if (ok) { s += x; ss = fmaf(x, x, ss); }
+              if (r < hrows) {
+                if (ok && x > mx0) { mx0 = x; ax0 = r; }
+                if (ok && x < mn0) { mn0 = x; an0 = r; }
+              } else {
+                if (ok && x > mx1) { mx1 = x; ax1 = r; }
+                if (ok && x < mn1) { mn1 = x; an1 = r; }
+              }
             }
           }
           if (want_stats) stat_accumulate(cb + lane, s, ss);
