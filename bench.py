@@ -298,6 +298,18 @@ def main():
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel_ms": rec["ms"],
                     "kernel_share_of_step": rec["ms"] / step_ms, "note": pk["source"]}
         roof["per_op_ms"] = {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+        # dram bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/, tools/gpu_profile.sh)
+        import glob
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_top_kernel_traffic.json")), reverse=True):
+            t = json.load(open(f))
+            if t.get("kernel", "").split(" ")[0] == roof["kernel"]:
+                roof["traffic"] = t["traffic"]
+                import re
+                m = re.match(r".*\[(\d+)x(\d+)->(\d+)\]", roof["kernel"])
+                P_, Ci_, Co_ = (int(x) for x in m.groups())
+                roof["traffic_source"] = "%s: dram read %.0f MB + write %.0f MB per launch; compulsory: X %.0f MB read, group max/min %.0f MB written" % (
+                    os.path.basename(f), t["dram_bytes_read"] / 1e6, t["dram_bytes_write"] / 1e6, 4e-6 * P_ * Ci_, 8e-6 * (P_ // 16) * Co_)
+                break
 
     train = None
     if args.train:

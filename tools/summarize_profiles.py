@@ -73,7 +73,27 @@ def bench():
                     o.write(txt[-1] + "\n")
 
 
-launches(); full(); bench()
+def traffic():
+    """dram bytes of the dominant kernel (first launch in the full capture) -> profiles/TAG_top_kernel_traffic.json,
+    which bench.py reports as roofline.traffic"""
+    rep = os.path.join(G, "prof_tc_%s.ncu-rep" % TAG)
+    if not os.path.isfile(rep):
+        return
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+    idx = {h: i for i, h in enumerate(hdr)}
+    def b(k):
+        v = float(r[idx[k]].replace(",", "")); u = units[idx[k]].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    out = {"kernel": "knn_a1[131072x512->512] (tools/tc_one.py 131072 512 512 16)", "source": "prof_tc_%s.ncu-rep, ncu --set full" % TAG,
+           "dram_bytes_read": b("dram__bytes_read.sum"), "dram_bytes_write": b("dram__bytes_write.sum"),
+           "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * (1e-3 if units[idx["gpu__time_duration.sum"]] in ("ns", "nsecond") else 1.0)}
+    out["traffic"] = out["dram_bytes_read"] + out["dram_bytes_write"]
+    json.dump(out, open(os.path.join(OUT, "%s_top_kernel_traffic.json" % TAG), "w"), indent=1)
+
+
+launches(); full(); bench(); traffic()
 sass = subprocess.run("cuobjdump -sass %s | grep -oE 'UTC[A-Z0-9.]*|LDTM[A-Z0-9.]*|UBLKCP[A-Z0-9.]*|UTCBAR[A-Z0-9.]*|SYNCS[A-Z0-9.]*' | sort | uniq -c | sort -rn"
                       % os.path.join(ROOT, "usip_b200", "lib", "libusip_b200.so"), shell=True, capture_output=True, text=True).stdout
 open(os.path.join(OUT, "sass_tcgen05_evidence.txt"), "w").write(
