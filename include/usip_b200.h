@@ -56,6 +56,13 @@ int usip_ball_group_f32(const float* xyz, const float* feat, const float* center
                         void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 
+/* Farthest point sampling of the SOM nodes          data/kitti_detector_loader.py:68-83 (FarthestSampler.sample), :144-145
+ * pts (B, Ns, 3) f32 row-major (the numpy subset the reference samples from), start (B,) i32 = index of the first node
+ * (the reference draws it with np.random.randint) -> out_idx (B, k) i32 in selection order, out_nodes (B, 3, k) f32 (or
+ * NULL).  Bit-identical to the numpy code: float64 running distances, first arg-max.  Ns <= 8192. */
+int usip_fps_f32(const float* pts, const int32_t* start, int32_t* out_idx, float* out_nodes, int B, int Ns, int k,
+                 void* stream);
+
 /* operations.knn_gather_by_indexing                         models/operations.py:271-287
  * src (B,C,N), idx (B,M,K) i32 -> out (B,C,M,K): out[b,c,m,k] = src[b,c,idx[b,m,k]]. */
 int usip_knn_gather_f32(const float* src, const int32_t* idx, float* out,

@@ -134,3 +134,25 @@ void orc_knn(const float* query, const float* db, int32_t* knn_i, float* knn_d, 
   }
   free(d); free(used);
 }
+
+/* data/kitti_detector_loader.py:68-83 (FarthestSampler.sample): the chosen set starts with pts[start]; the running
+ * squared distance to the set is kept in float64 -- (p0 - pts)**2 summed over xyz left to right, p0 a float64 copy of a
+ * float32 point -- and every further node is the FIRST arg-max of it (np.argmax).  pts (Ns,3) row-major. */
+void orc_fps(const float* pts, int start, int32_t* out_idx, int Ns, int k) {
+  double* dist = (double*)malloc(sizeof(double) * (size_t)Ns);
+  int sel = start;
+  for (int it = 0; it < k; ++it) {
+    out_idx[it] = sel;
+    if (it == k - 1) break;
+    const double sx = pts[3 * sel], sy = pts[3 * sel + 1], sz = pts[3 * sel + 2];
+    int best = 0;
+    for (int n = 0; n < Ns; ++n) {
+      const double dx = sx - (double)pts[3 * n], dy = sy - (double)pts[3 * n + 1], dz = sz - (double)pts[3 * n + 2];
+      const double d = (dx * dx + dy * dy) + dz * dz;
+      dist[n] = (it == 0 || d < dist[n]) ? d : dist[n];
+      if (dist[n] > dist[best]) best = n;
+    }
+    sel = best;
+  }
+  free(dist);
+}

@@ -100,6 +100,14 @@ def pairwise_min(a, b):
     return d, arg
 
 
+def fps(pts, start, k):
+    """FarthestSampler.sample (data/kitti_detector_loader.py:68-83) given the first index: pts (Ns,3) f32 -> idx (k,) i32."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.empty(int(k), np.int32)
+    _lib().orc_fps(_fp(pts), int(start), _ip(out), int(pts.shape[0]), int(k))
+    return out
+
+
 def knn(query, db, K):
     """models/layers.py:417-421: topk(K, largest=False, sorted=True) of torch.norm distances."""
     query = _c32(query); db = _c32(db)

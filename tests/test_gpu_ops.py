@@ -355,3 +355,32 @@ def test_wgrad(P, Cout, Cin, precision):
     ref = GY.astype(np.float64).T @ A
     e = rel_err(gW.cpu().numpy(), ref)
     assert e < 2e-5, e
+
+
+def test_fps_vs_reference_golden_and_oracle():
+    """GPU farthest point sampling: the reference's FarthestSampler outputs (golden), the oracle at the KITTI node shape
+    (16 clouds x 5461 candidates x 512 nodes) bit for bit, and the drop-in class incl. its RNG consumption."""
+    from usip_b200 import ops
+    from usip_b200.data.kitti_detector_loader import FarthestSampler
+    g = golden("fps.npz")
+    fs = FarthestSampler(dev())
+    for name in ("lidar", "dup", "few"):
+        pts, k = g["pts_" + name], int(g["k_" + name])
+        np.random.seed(77)
+        nodes = fs.sample(pts, k)
+        assert nodes.dtype == np.float64 and np.array_equal(nodes, g["nodes_" + name]), name
+        np.random.seed(77); np.random.randint(len(pts))
+        after = np.random.randint(1 << 30)
+        np.random.seed(77); fs.sample(pts, k)
+        assert np.random.randint(1 << 30) == after                       # exactly one draw consumed
+    rng = np.random.default_rng(5)
+    B, Ns, k = 16, 5461, 512
+    pts = (rng.uniform(-40, 40, (B, Ns, 3)) * np.array([1, 0.05, 1])).astype(np.float32)
+    pts[3, 100:200] = pts[3, 0:100]                                      # exact duplicates
+    start = rng.integers(0, Ns, B).astype(np.int32)
+    idx, nodes = ops.fps(cu(pts), cu(start), k)
+    idx = idx.cpu().numpy(); nodes = nodes.cpu().numpy()
+    for b in range(B):
+        ref = orc.fps(pts[b], int(start[b]), k)
+        assert np.array_equal(idx[b], ref), b
+        assert np.array_equal(nodes[b], pts[b][ref].T)

@@ -185,6 +185,28 @@ def golden_desc_loss(ref):
                         gamma=np.float32(opt.triple_loss_gamma), sigma_max=np.float32(opt.sigma_max))
 
 
+def golden_fps(ref):
+    """FarthestSampler of the reference's KITTI loader (float64 distances, np.argmax) on three small clouds: lidar-like,
+    a cloud with duplicated points (exact ties) and k larger than the number of distinct points."""
+    import importlib
+    loader = importlib.import_module("data.kitti_detector_loader")
+    fs = loader.FarthestSampler()
+    out = {}
+    rng = np.random.default_rng(31)
+    clouds = dict(lidar=(rng.uniform(-40, 40, (700, 3)) * np.array([1, 0.05, 1])).astype(np.float32),
+                  dup=np.repeat(rng.normal(size=(60, 3)).astype(np.float32), 5, axis=0),
+                  few=np.repeat(rng.normal(size=(5, 3)).astype(np.float32), 4, axis=0))
+    for name, pts in clouds.items():
+        k = dict(lidar=64, dup=48, few=12)[name]
+        np.random.seed(77)
+        nodes = fs.sample(pts, k)                       # consumes np.random.randint(len(pts)) for the first node
+        np.random.seed(77)
+        start = np.random.randint(len(pts))
+        out["pts_" + name] = pts; out["k_" + name] = np.int32(k); out["start_" + name] = np.int32(start)
+        out["nodes_" + name] = nodes
+    np.savez_compressed(os.path.join(OUT, "fps.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -197,6 +219,7 @@ def main():
     detector_case(ref, "lite_small", B=2, N=1024, M=32, S=4, Kn=16, kind="lidar", seed=1238, scene="indoor")
     golden_descriptor(ref)
     golden_desc_loss(ref)
+    golden_fps(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KB")
 

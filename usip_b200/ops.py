@@ -89,6 +89,17 @@ def ball_group(xyz, feat, centers, radius, K, want_group=True, rows_ld=0):
     return idx, grp
 
 
+def fps(pts, start, k, want_nodes=True):
+    """Farthest point sampling.  pts (B,Ns,3) f32, start (B,) i32 -> (idx (B,k) i32, nodes (B,3,k) f32 or None)."""
+    _req(pts, f32, "pts"); _req(start, i32, "start")
+    B, Ns, _ = pts.shape
+    idx = torch.empty((B, int(k)), dtype=i32, device=pts.device)
+    nodes = torch.empty((B, 3, int(k)), dtype=f32, device=pts.device) if want_nodes else None
+    with torch.cuda.device(pts.device):
+        check(_lib.load().usip_fps_f32(_p(pts), _p(start), _p(idx), _p(nodes), B, Ns, int(k), _stream()), "usip_fps_f32")
+    return idx, nodes
+
+
 def knn_gather(src, idx):
     _req(src, f32, "som_node"); _req(idx, i32, "som_node_knn_I")
     B, C, N = src.shape
