@@ -63,6 +63,13 @@ int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 int usip_fps_f32(const float* pts, const int32_t* start, int32_t* out_idx, float* out_nodes, int B, int Ns, int k,
                  void* stream);
 
+/* Radius non-maximum suppression of the detected keypoints     evaluation/save_keypoints.py:180-216 (nms)
+ * keypoints (B,3,M) f32, sigmas (B,M) f32 -> out_idx (B,M) i32: original indices of the kept keypoints in the order the
+ * reference emits them (ascending sigma, ties by index), padded with -1; out_count (B,) i32.  radius < 0.01: pass-through
+ * (0..M-1, count M) like the reference. */
+int usip_nms_f32(const float* keypoints, const float* sigmas, float radius, int32_t* out_idx, int32_t* out_count,
+                 int B, int M, void* stream);
+
 /* operations.knn_gather_by_indexing                         models/operations.py:271-287
  * src (B,C,N), idx (B,M,K) i32 -> out (B,C,M,K): out[b,c,m,k] = src[b,c,idx[b,m,k]]. */
 int usip_knn_gather_f32(const float* src, const int32_t* idx, float* out,

@@ -108,6 +108,15 @@ def fps(pts, start, k):
     return out
 
 
+def nms(kp, sigma, radius):
+    """save_keypoints.py:180-216: kp (M,3) f32, sigma (M,) f32 -> original indices of the kept keypoints, emission order."""
+    kp = np.ascontiguousarray(kp, np.float32); sigma = np.ascontiguousarray(sigma, np.float32)
+    out = np.empty(kp.shape[0], np.int32)
+    lib = _lib(); lib.orc_nms.restype = ctypes.c_int
+    n = lib.orc_nms(_fp(kp), _fp(sigma), ctypes.c_float(radius), _ip(out), int(kp.shape[0]))
+    return out[:n].copy()
+
+
 def knn(query, db, K):
     """models/layers.py:417-421: topk(K, largest=False, sorted=True) of torch.norm distances."""
     query = _c32(query); db = _c32(db)

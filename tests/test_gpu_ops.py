@@ -384,3 +384,33 @@ def test_fps_vs_reference_golden_and_oracle():
         ref = orc.fps(pts[b], int(start[b]), k)
         assert np.array_equal(idx[b], ref), b
         assert np.array_equal(nodes[b], pts[b][ref].T)
+
+
+def test_nms_vs_reference_golden_and_oracle(tmp_path):
+    """GPU radius NMS: the reference's own nms() outputs (golden), the oracle on a batch at the detector's shape, the
+    batched select_keypoints() and the .bin wire format."""
+    from usip_b200 import ops
+    from usip_b200.evaluation import save_keypoints as sk
+    g = golden("nms.npz")
+    for name in ("lidar", "dense", "ties", "off"):
+        kp, sg, r = g["kp_" + name], g["sigma_" + name], float(g["radius_" + name])
+        vk, vs = sk.nms(kp, sg, r, device=dev())
+        assert np.array_equal(vk, g["valid_kp_" + name]) and np.array_equal(vs, g["valid_sigma_" + name]), name
+    rng = np.random.default_rng(9)
+    B, M = 16, 512
+    kp = (rng.uniform(-40, 40, (B, 3, M)) * np.array([1, 0.05, 1]).reshape(1, 3, 1)).astype(np.float32)
+    sg = rng.uniform(0.01, 2.0, (B, M)).astype(np.float32)
+    sg[2, ::7] = sg[2, 0]                                                # equal sigmas: ties by index
+    idx, cnt = ops.nms(cu(kp), cu(sg), 3.0)
+    idx = idx.cpu().numpy(); cnt = cnt.cpu().numpy()
+    sel = sk.select_keypoints(cu(kp), cu(sg), 3.0, desired_keypoint_num=128)
+    for b in range(B):
+        ref = orc.nms(kp[b].T.copy(), sg[b], 3.0)
+        assert cnt[b] == len(ref) and np.array_equal(idx[b, :cnt[b]], ref) and np.all(idx[b, cnt[b]:] == -1), b
+        assert np.array_equal(sel[b].cpu().numpy(), kp[b].T[ref[:128]])
+    f = str(tmp_path / "kp.bin")
+    sk.write_keypoints_bin(f, sel[0])
+    assert np.array_equal(sk.read_keypoints_bin(f), sel[0].cpu().numpy())
+    a = rng.normal(size=(100, 8)).astype(np.float64); np.save(str(tmp_path / "pc.npy"), a)
+    pc, sn = sk.read_pointcloud_npy(str(tmp_path / "pc.npy"))
+    assert pc.dtype == np.float32 and pc.shape == (100, 3) and np.array_equal(sn, a[:, 3:7].astype(np.float32))

@@ -207,6 +207,38 @@ def golden_fps(ref):
     np.savez_compressed(os.path.join(OUT, "fps.npz"), **out)
 
 
+def _reference_function(relpath, name):
+    """The reference's own, unmodified source of one top-level function, executed here (its module cannot be imported:
+    evaluation/save_keypoints.py is a script with hard-coded dataset paths and GUI / visdom imports)."""
+    import ast
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, relpath)).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), relpath, "exec"), ns)
+    return ns[name]
+
+
+def golden_nms(ref):
+    """evaluation/save_keypoints.py:180-216 nms() + the sigma-sorted top-k that follows it (:346-351)."""
+    nms = _reference_function("evaluation/save_keypoints.py", "nms")
+    rng = np.random.default_rng(41)
+    out = {}
+    cases = dict(lidar=(rng.uniform(-40, 40, (512, 3)) * np.array([1, 0.05, 1]), 2.0),
+                 dense=(rng.normal(size=(300, 3)) * 1.5, 1.0),
+                 ties=(np.round(rng.normal(size=(200, 3)) * 2) / 2, 0.5),       # duplicated positions, exact distance ties
+                 off=(rng.normal(size=(64, 3)), 0.0))                            # radius < 0.01: pass-through
+    for name, (kp, r) in cases.items():
+        kp = kp.astype(np.float32)
+        sg = (rng.uniform(0.01, 2.0, kp.shape[0])).astype(np.float32)
+        if name == "ties":
+            sg = np.round(sg * 4) / 4                                            # equal sigmas too
+            sg = sg.astype(np.float32)
+        vk, vs = nms(kp.copy(), sg.copy(), r)
+        out["kp_" + name] = kp; out["sigma_" + name] = sg; out["radius_" + name] = np.float32(r)
+        out["valid_kp_" + name] = vk; out["valid_sigma_" + name] = vs
+    np.savez_compressed(os.path.join(OUT, "nms.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -220,6 +252,7 @@ def main():
     golden_descriptor(ref)
     golden_desc_loss(ref)
     golden_fps(ref)
+    golden_nms(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KB")
 

@@ -100,6 +100,17 @@ def fps(pts, start, k, want_nodes=True):
     return idx, nodes
 
 
+def nms(keypoints, sigmas, radius):
+    """keypoints (B,3,M) f32, sigmas (B,M) f32 -> (idx (B,M) i32 kept indices in emission order, -1 padded; count (B,) i32)."""
+    _req(keypoints, f32, "keypoints"); _req(sigmas, f32, "sigmas")
+    B, _, M = keypoints.shape
+    idx = torch.empty((B, M), dtype=i32, device=keypoints.device)
+    cnt = torch.empty((B,), dtype=i32, device=keypoints.device)
+    with torch.cuda.device(keypoints.device):
+        check(_lib.load().usip_nms_f32(_p(keypoints), _p(sigmas), float(radius), _p(idx), _p(cnt), B, M, _stream()), "usip_nms_f32")
+    return idx, cnt
+
+
 def knn_gather(src, idx):
     _req(src, f32, "som_node"); _req(idx, i32, "som_node_knn_I")
     B, C, N = src.shape
