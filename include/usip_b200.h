@@ -206,6 +206,16 @@ int usip_desc_pairmin_f32(const float* a, const float* b, float* min_d, int32_t*
 int usip_desc_triplet(const float* dpos, const float* dneg, const float* sigma, float gamma, float sigma_max,
                       float* loss, float* active, int B, int M, void* stream);
 
+/* backward of DescPairScanLoss (losses.py:199-233) with upstream gradient g_loss (B,M): anc (B,C,M), pos (B,C,Mp),
+ * neg (B,C,Mn), saved (dpos, ipos, dneg, ineg) of usip_desc_pairmin_f32; g_anc / g_pos / g_neg are ACCUMULATED into
+ * (pre-zero them). */
+int usip_desc_triplet_bwd(const float* anc, const float* pos, const float* neg, const float* dpos, const int32_t* ipos,
+                          const float* dneg, const int32_t* ineg, const float* sigma, float gamma, float sigma_max,
+                          const float* g_loss, float* g_anc, float* g_pos, float* g_neg, int B, int C, int M, int Mp,
+                          int Mn, void* stream);
+/* backward of usip_l2norm_to_bcm: g (B,C,M), raw rows Y [B*M, C] -> GY [B*M, C]                     networks.py:383 */
+int usip_l2norm_bwd(const float* g, const float* Y, int ldy, float* GY, int ldg, int B, int M, int C, void* stream);
+
 /* ---- backward of the loss kernels (autograd of models/losses.py / keypoint_detector.py:182-184) ---- */
 /* grad of sum_i g_i*gscale*min_d_i: grad_a (B,3,Ma) overwritten, grad_b (B,3,Nb) ACCUMULATED (pre-zero) or NULL */
 int usip_pairwise_min_bwd(const float* a, const float* b, const float* min_d, const int32_t* arg,

@@ -436,3 +436,22 @@ def init_detector_params(S=4, seed=0, C1=128, C2=512, randomize_bn=False):
         for name, shp, bn in detector_param_shapes(S, C1, C2):
             P[name + ".conv.bias"] = rng.normal(0, 0.05, shp[0]).astype(np.float32)
     return P
+
+
+def desc_train_inputs(B, N, M, S, seed):
+    """Deterministic inputs of one descriptor train step: an anchor scan, its rigidly moved + jittered positive, keypoints
+    near cloud points in both frames, sigmas in [0, 4), a cyclic negative index.  Dense enough (x0.2 in x/z) that balls of
+    radius 1 hold 0 .. > K points."""
+    d = synth_pair(B, N, 16, S, kind="lidar", seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    sc = np.array([0.2, 1.0, 0.2], np.float32).reshape(1, 3, 1)
+    anc_pc = (d["src_pc"] * sc).astype(np.float32)
+    pos_pc = (d["dst_pc"] * sc).astype(np.float32)
+    sel = np.stack([rng.choice(N, M, replace=False) for _ in range(B)])
+    anc_kp = np.stack([anc_pc[b][:, sel[b]] for b in range(B)]) + rng.normal(0, 0.05, (B, 3, M))
+    pos_kp = np.stack([pos_pc[b][:, sel[b]] for b in range(B)]) + rng.normal(0, 0.05, (B, 3, M))
+    return dict(anc_pc=anc_pc, anc_sn=d["src_sn"], anc_kp=anc_kp.astype(np.float32),
+                anc_sigma=rng.uniform(0, 4, (B, M)).astype(np.float32),
+                pos_pc=pos_pc, pos_sn=d["dst_sn"], pos_kp=pos_kp.astype(np.float32),
+                pos_sigma=rng.uniform(0, 4, (B, M)).astype(np.float32),
+                neg_idx=((np.arange(B) + 1) % B).astype(np.int64))

@@ -154,6 +154,57 @@ def test_descriptor_forward_vs_reference_golden():
             assert e < REL, (mode, use_tc, e)
 
 
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_descriptor_train_step_vs_reference_golden(use_tc):
+    """One full ModelDescriptor.optimize() (train-mode forward of the siamese batch, DescPairScanLoss, backward, Adam)
+    against the reference's own loss, descriptors, gradients and post-step parameters (tools/make_golden.py)."""
+    from usip_b200.models.keypoint_descriptor import ModelDescriptor
+    g = golden("descriptor_train.npz")
+    B, N, M, S, K, seed = [int(v) for v in g["cfg"]]
+    d = orc.desc_train_inputs(B, N, M, S, seed)
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K,
+                   descriptor_len=128, random_pc_dropout_lower_limit=1.0, use_tensor_cores=use_tc)
+    md = ModelDescriptor(opt)
+    load_params(md.descriptor, {k[len("param/"):]: g[k] for k in g.files if k.startswith("param/")})
+    md.set_input(*[torch.from_numpy(d[k]) for k in ("anc_pc", "anc_sn", "anc_kp", "anc_sigma", "pos_pc", "pos_sn", "pos_kp", "pos_sigma")],
+                 torch.from_numpy(d["neg_idx"]))
+    np.random.seed(seed)                                       # the forward draws np.random.permutation(N)
+    md.optimize(epoch=0)
+    torch.cuda.synchronize()
+    assert abs(md.loss.item() - float(g["loss"])) <= REL * abs(float(g["loss"])), (md.loss.item(), float(g["loss"]))
+    assert abs(md.active_percentage.item() - float(g["active"])) < 1e-6
+    assert rel_err(md.anc_descriptors.detach().cpu().numpy(), g["anc_desc"]) < REL
+    assert rel_err(md.pos_descriptors.detach().cpu().numpy(), g["pos_desc"]) < REL
+    worst = 0.0
+    for k, p in md.descriptor.named_parameters():
+        ref = g["grad/" + k]
+        gr = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        absmax, norm = float(ref[2]), float(ref[3])
+        wnorm = float(g["grad/" + k.replace("bias", "weight")][3]) if k.endswith("conv.bias") else norm
+        if k.endswith("conv.bias") and norm < 1e-3 * max(wnorm, 1e-12):
+            assert np.linalg.norm(gr) < 1e-3 * max(wnorm, 1e-12), k    # bias in front of BN: true gradient is 0
+            continue
+        e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
+        e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
+        worst = max(worst, e_norm, e_el)
+        assert e_norm < 2e-3 and e_el < 5e-3, (k, e_norm, e_el)
+    sd = md.descriptor.state_dict()
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked") or k.endswith("running_mean") or k.endswith("running_var"):
+            continue
+        ref = g["after/" + k]
+        gref = g["grad/" + k][4:]
+        flat = v.cpu().numpy().reshape(-1)
+        n = min(24, flat.size)
+        diff = np.abs(flat[:n] - ref[3:3 + n])
+        assert diff.max() <= 2.2e-3, (k, diff.max())
+        if k.endswith("conv.bias") and float(g["grad/" + k][3]) < 1e-3 * max(float(g["grad/" + k.replace("bias", "weight")][3]), 1e-12):
+            continue
+        solid = np.abs(gref[:n]) > max(1e-5, 1e-2 * float(g["grad/" + k][2]))
+        assert np.all(diff[solid] <= 2e-5 + 2e-4 * np.abs(ref[3:3 + n][solid])), (k, diff, gref[:n])
+    print("worst gradient rel err", worst)
+
+
 def test_forward_loss_cuda_graph_matches_eager():
     """ModelDetector.forward_loss(graph=True) replays the captured launch sequence: results must equal the eager run
     bit for bit (all kernels on the fwd+loss path are deterministic), also after the inputs change."""

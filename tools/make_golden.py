@@ -171,6 +171,44 @@ def golden_descriptor(ref):
     np.savez_compressed(os.path.join(OUT, "descriptor.npz"), **out)
 
 
+def golden_descriptor_train(ref):
+    """One ModelDescriptor.optimize() of the reference (keypoint_descriptor.py:126-157) on CPU: loss, gradient
+    summaries, post-Adam parameter summaries.  Inputs are regenerated from the seed by the consumers."""
+    B, N, M, S, K = 3, 2048, 40, 4, 32
+    seed = 33
+    d = desc_train_inputs(B, N, M, S, seed)
+    opt = ref_shim.make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0,
+                            ball_nsamples=K, descriptor_len=128, random_pc_dropout_lower_limit=1.0)
+    torch.manual_seed(seed); np.random.seed(seed); random.seed(seed)
+    md = ref.keypoint_descriptor.ModelDescriptor(opt)
+    out = dict(cfg=np.array([B, N, M, S, K, seed], np.int64))
+    for k, v in md.descriptor.state_dict().items():
+        out["param/" + k] = v.detach().numpy().copy()
+    md.set_input(*[t(d[k]) for k in ("anc_pc", "anc_sn", "anc_kp", "anc_sigma", "pos_pc", "pos_sn", "pos_kp", "pos_sigma")],
+                 torch.from_numpy(d["neg_idx"]))
+    np.random.seed(seed)                                   # the forward consumes np.random.permutation(N)
+    md.optimize(epoch=0)
+    out["loss"] = np.float32(md.loss.item()); out["active"] = np.float32(md.active_percentage.item())
+    out["anc_desc"] = md.anc_descriptors.detach().numpy(); out["pos_desc"] = md.pos_descriptors.detach().numpy()
+    for k, p in md.descriptor.named_parameters():
+        g = p.grad.detach().numpy().reshape(-1).astype(np.float64)
+        out["grad/" + k] = np.concatenate([[g.mean(), g.std(), np.abs(g).max(), np.linalg.norm(g)], g[:24]]).astype(np.float32)
+    for k, v in md.descriptor.state_dict().items():
+        v = v.detach().numpy()
+        if k.endswith("num_batches_tracked"):
+            continue
+        flat = v.reshape(-1).astype(np.float64)
+        out["after/" + k] = np.concatenate([[flat.mean(), flat.std(), np.abs(flat).max()], flat[:24]]).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "descriptor_train.npz"), **out)
+    print("descriptor train loss", out["loss"], "active", out["active"])
+
+
+def desc_train_inputs(B, N, M, S, seed):
+    """Synthetic (anchor, positive) scan pair with keypoints + sigmas for the descriptor train step (shared with the
+    tests through oracle.usip_oracle.desc_train_inputs)."""
+    return orc.desc_train_inputs(B, N, M, S, seed)
+
+
 def golden_desc_loss(ref):
     torch.manual_seed(5)
     B, C, M = 3, 128, 40
@@ -251,6 +289,7 @@ def main():
     detector_case(ref, "lite_small", B=2, N=1024, M=32, S=4, Kn=16, kind="lidar", seed=1238, scene="indoor")
     golden_descriptor(ref)
     golden_desc_loss(ref)
+    golden_descriptor_train(ref)
     golden_fps(ref)
     golden_nms(ref)
     for f in sorted(os.listdir(OUT)):

@@ -389,6 +389,63 @@ wgrad_simt_kernel(const float* __restrict__ GY, int ldg, const float* __restrict
   }
 }
 
+
+// backward of descriptor / (||descriptor|| + 1e-5) (networks.py:383): g (B,C,M) reference layout, y raw rows [Q,C]
+//   out = y / (n + eps):  g_y = g / (n + eps) - y * (g . y) / (n * (n + eps)^2)      (n = 0: torch.norm's sub-gradient is 0)
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ Y, int ldy, float* __restrict__ GY, int ldg,
+                  int B, int M, int C) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * M) return;
+  const int b = w / M, m = w - b * M;
+  const float* y = Y + (size_t)w * ldy;
+  float ss = 0.f, gy = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float yv = y[c], gv = g[((size_t)b * C + c) * M + m];
+    ss = fmaf(yv, yv, ss); gy = fmaf(gv, yv, gy);
+  }
+  ss = warp_sum(ss); gy = warp_sum(gy);
+  const float n = sqrtf(ss), d = n + 1e-5f;
+  const float k = n > 0.f ? gy / (n * d * d) : 0.f;
+  for (int c = lane; c < C; c += 32) GY[(size_t)w * ldg + c] = g[((size_t)b * C + c) * M + m] / d - y[c] * k;
+}
+
+// backward of DescPairScanLoss (losses.py:199-233): loss[b,m] = w * clamp(dpos - dneg + gamma, 0) with upstream gradient
+// g_loss (B,M).  Thread block = one (b, m): coef = g_loss * w where the hinge is active; the anchor receives
+// coef * ((a - p)/dpos - (a - n)/dneg), the matched positive -coef*(a - p)/dpos and the matched negative +coef*(a - n)/dneg
+// (scattered with atomics: several anchors can share a match).  The weights are detached in the reference.
+__global__ void __launch_bounds__(128)
+desc_triplet_bwd_kernel(const float* __restrict__ anc, const float* __restrict__ pos, const float* __restrict__ neg,
+                        const float* __restrict__ dpos, const int32_t* __restrict__ ipos, const float* __restrict__ dneg,
+                        const int32_t* __restrict__ ineg, const float* __restrict__ sigma, float gamma, float sigma_max,
+                        const float* __restrict__ g_loss, float* __restrict__ g_anc, float* __restrict__ g_pos,
+                        float* __restrict__ g_neg, int C, int M, int Mp, int Mn) {
+  __shared__ float s_wmean;
+  __shared__ float sred[4];
+  const int b = blockIdx.y, m = blockIdx.x;
+  float ws = 0.f;
+  for (int t = threadIdx.x; t < M; t += blockDim.x) ws += fmaxf(sigma_max - sigma[(size_t)b * M + t], 0.f);
+  ws = warp_sum(ws);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ws;
+  __syncthreads();
+  if (threadIdx.x == 0) s_wmean = (sred[0] + sred[1] + sred[2] + sred[3]) / (float)M;
+  __syncthreads();
+  const size_t bm = (size_t)b * M + m;
+  const float dp = dpos[bm], dn = dneg[bm];
+  if (!(dp - dn + gamma > 0.f)) return;
+  const float coef = g_loss[bm] * (fmaxf(sigma_max - sigma[bm], 0.f) / s_wmean);
+  const int jp = ipos[bm], jn = ineg[bm];
+  const float ip = dp > 0.f ? coef / dp : 0.f, in = dn > 0.f ? coef / dn : 0.f;      // torch.norm: zero sub-gradient at 0
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float a = anc[((size_t)b * C + c) * M + m];
+    const float tp = (a - pos[((size_t)b * C + c) * Mp + jp]) * ip;
+    const float tn = (a - neg[((size_t)b * C + c) * Mn + jn]) * in;
+    atomicAdd(&g_anc[((size_t)b * C + c) * M + m], tp - tn);
+    atomicAdd(&g_pos[((size_t)b * C + c) * Mp + jp], -tp);
+    atomicAdd(&g_neg[((size_t)b * C + c) * Mn + jn], tn);
+  }
+}
+
 }  // namespace usip
 
 using namespace usip;
@@ -519,4 +576,21 @@ extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, con
   wgrad_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout,
                                                             Cin, rows);
   return check_launch("wgrad_simt_kernel");
+}
+
+extern "C" int usip_l2norm_bwd(const float* g, const float* Y, int ldy, float* GY, int ldg, int B, int M, int C, void* stream) {
+  USIP_REQUIRE(g && Y && GY && ldy >= C && ldg >= C, "l2norm_bwd: bad args");
+  l2norm_bwd_kernel<<<cdiv(B * M * 32, 256), 256, 0, (cudaStream_t)stream>>>(g, Y, ldy, GY, ldg, B, M, C);
+  return check_launch("l2norm_bwd_kernel");
+}
+
+extern "C" int usip_desc_triplet_bwd(const float* anc, const float* pos, const float* neg, const float* dpos,
+                                     const int32_t* ipos, const float* dneg, const int32_t* ineg, const float* sigma,
+                                     float gamma, float sigma_max, const float* g_loss, float* g_anc, float* g_pos,
+                                     float* g_neg, int B, int C, int M, int Mp, int Mn, void* stream) {
+  USIP_REQUIRE(anc && pos && neg && dpos && ipos && dneg && ineg && sigma && g_loss && g_anc && g_pos && g_neg,
+               "desc_triplet_bwd: bad args");
+  desc_triplet_bwd_kernel<<<dim3(M, B), 128, 0, (cudaStream_t)stream>>>(anc, pos, neg, dpos, ipos, dneg, ineg, sigma, gamma,
+                                                                       sigma_max, g_loss, g_anc, g_pos, g_neg, C, M, Mp, Mn);
+  return check_launch("desc_triplet_bwd_kernel");
 }

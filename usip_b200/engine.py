@@ -511,13 +511,13 @@ def detector_backward(net, ctx, g_kp, g_sig):
 
 def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):
     """DescriptorLiteOld.forward (models/networks.py:333-385) on the fused plan.
-    Returns (descriptor (B,C,M), x_features (B,3+S,M,K), ctx)."""
+    Returns (descriptor (B,C,M), x_features (B,3+S,M,K), ctx) -- ctx holds what descriptor_backward needs (keep=True)."""
     from . import _lib
     opt = net.opt
     dev = x.device
-    if keep:
-        raise NotImplementedError("descriptor backward plan is not built yet (SURVEY 8f-1 'next' row): run under "
-                                  "torch.no_grad() / freeze_model()")
+    if keep and not net.training:
+        raise NotImplementedError("gradients through eval-mode BatchNorm are not part of the hot path "
+                                  "(the reference only back-propagates in train mode, keypoint_descriptor.py:138)")
     Bp, _, N = x.shape
     M = keypoints.shape[2]
     K = opt.ball_nsamples
@@ -535,7 +535,7 @@ def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, k
     Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, _bn_mom(c1.norm, epoch), name="desc.conv1")
     Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, _bn_mom(c2.norm, epoch), prev=bn1, name="desc.conv2")
     Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, _bn_mom(c3.norm, epoch), prev=bn2,
-                          group=K, want_group=True, name="desc.conv3")
+                          group=K, want_group=True, want_arg=keep, name="desc.conv3")
     amax = torch.empty((Q, D), dtype=f32, device=dev)
     ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
     W4 = _w2d(c4.conv.weight)
@@ -543,12 +543,76 @@ def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, k
     Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, _bn_mom(c4.norm, epoch), prev=bn3, addend=U,
                        add_group=K, name="desc.conv4")
     _, _, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), prev=bn4, group=K, want_group=True,
-                       write_y=False, name="desc.conv5")
+                       want_arg=keep, write_y=False, name="desc.conv5")
     desc = torch.empty((Bp, D, M), dtype=f32, device=dev)
     _lib.check(_lib.load().usip_l2norm_to_bcm(ops._p(grp5["gmax"]), grp5["gmax"].stride(0), ops._p(desc), None, Bp, M, D,
                                               ops._stream()), "usip_l2norm_to_bcm")
-    return desc, feats, None
+    ctx = None
+    if keep:
+        ctx = dict(Bp=Bp, M=M, K=K, D=D, rows=rows, Y1=Y1, bn1=bn1, Y2=Y2, bn2=bn2, Y3=Y3, bn3=bn3, grp3=grp3, amax=amax,
+                   Y4=Y4, bn4=bn4, grp5=grp5, use_tc=use_tc)
+    return desc, feats, ctx
 
 
 def descriptor_backward(net, ctx, g_desc):
-    raise NotImplementedError("descriptor backward plan not built yet")
+    """Backward of descriptor_forward (points / keypoints carry no gradient): gradients of net.parameters() in order.
+
+    desc = l2norm(max_k conv5(a4)),  a4 = relu(bn4(a3 WA^T + (amax WB^T)[row/K])),  amax = max_k a3,
+    a3 = relu(bn3(conv3(a2))), a2 = relu(bn2(conv2(a1))), a1 = relu(bn1(conv1(rows)))      (networks.py:375-383)."""
+    dev = g_desc.device
+    Bp, M, K, D = ctx["Bp"], ctx["M"], ctx["K"], ctx["D"]
+    Q, G = Bp * M, Bp * M * K
+    bw = _Bwd(net, dev, ctx["use_tc"])
+    lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
+    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
+    grp5, grp3 = ctx["grp5"], ctx["grp3"]
+    # ---- l2 normalisation and the max over the ball (conv5 is linear: the max of the raw output routes to its arg row)
+    G_y = torch.empty((Q, D), dtype=f32, device=dev)
+    check(lib.usip_l2norm_bwd(p(g_desc.contiguous()), p(grp5["gmax"]), grp5["gmax"].stride(0), p(G_y), G_y.stride(0), Bp, M, D, s()),
+          "usip_l2norm_bwd")
+    GY5 = torch.zeros((G, D), dtype=f32, device=dev)
+    check(lib.usip_groupmax_scatter_add(p(GY5), GY5.stride(0), p(G_y), p(grp5["amax"]), K, Q, D, s()), "usip_groupmax_scatter_add")
+    W5 = _w2d(c5.conv.weight)
+    bw.wgrad(GY5, ctx["Y4"], bw.g2d(c5.conv.weight), G, D, W5.shape[1], prev=ctx["bn4"], name="wgrad_desc.conv5")
+    bw.colsum(GY5, bw.grads[c5.conv.bias], G, D)
+    G_a4 = bw.dgrad(GY5, W5, G, name="dgrad_desc.conv5")
+    del GY5
+    GY4 = bw.bn_bwd(G_a4, ctx["Y4"], ctx["bn4"], c4.norm, G, G_a4.shape[1], name="bn_bwd_desc.conv4")
+    del G_a4
+    # ---- conv4 on cat(y_first, broadcast max): Y4 = a3 WA^T + U[row/K] + b,  U = amax WB^T
+    W4 = _w2d(c4.conv.weight)
+    gW4 = bw.g2d(c4.conv.weight)
+    C4 = W4.shape[0]
+    bw.wgrad(GY4, ctx["Y3"], gW4[:, :D], G, C4, D, prev=ctx["bn3"], name="wgrad_desc.conv4")
+    G_a3 = bw.dgrad(GY4, _cols(W4, 0, D), G, name="dgrad_desc.conv4")                 # [G, D]
+    G_U = torch.empty((Q, C4), dtype=f32, device=dev)
+    check(lib.usip_group_sum(p(GY4), GY4.stride(0), p(G_U), G_U.stride(0), K, Q, C4, s()), "usip_group_sum")
+    del GY4
+    bw.wgrad(G_U, ctx["amax"], gW4[:, D:], Q, C4, D, name="wgrad_desc.conv4_node")
+    G_amax = bw.dgrad(G_U, _cols(W4, D), Q, name="dgrad_desc.conv4_node")             # [Q, D]
+    # the max path joins the dense gradient of a3 at the arg rows (the ReLU mask is applied by bn_bwd below)
+    gz = torch.empty((Q, D), dtype=f32, device=dev); arg3 = torch.empty((Q, D), dtype=i32, device=dev)
+    bn3 = ctx["bn3"]
+    check(lib.usip_groupmax_bwd_select(p(G_amax), G_amax.stride(0), p(grp3["gmax"]), p(grp3["gmin"]), p(grp3["amax"]),
+                                       p(grp3["amin"]), p(bn3.scale), p(bn3.shift), p(bn3.mean), p(bn3.invstd), p(gz), p(arg3),
+                                       None, Q, D, s()), "usip_groupmax_bwd_select")
+    check(lib.usip_groupmax_scatter_add(p(G_a3), G_a3.stride(0), p(G_amax), p(arg3), K, Q, D, s()), "usip_groupmax_scatter_add")
+    # ---- conv3, conv2, conv1
+    GY3 = bw.bn_bwd(G_a3, ctx["Y3"], bn3, c3.norm, G, D, name="bn_bwd_desc.conv3")
+    del G_a3
+    W3 = _w2d(c3.conv.weight)
+    bw.wgrad(GY3, ctx["Y2"], bw.g2d(c3.conv.weight), G, W3.shape[0], W3.shape[1], prev=ctx["bn2"], name="wgrad_desc.conv3")
+    G_a2 = bw.dgrad(GY3, W3, G, name="dgrad_desc.conv3")
+    del GY3
+    GY2 = bw.bn_bwd(G_a2, ctx["Y2"], ctx["bn2"], c2.norm, G, G_a2.shape[1], name="bn_bwd_desc.conv2")
+    del G_a2
+    W2 = _w2d(c2.conv.weight)
+    bw.wgrad(GY2, ctx["Y1"], bw.g2d(c2.conv.weight), G, W2.shape[0], W2.shape[1], prev=ctx["bn1"], name="wgrad_desc.conv2")
+    G_a1 = bw.dgrad(GY2, W2, G, name="dgrad_desc.conv2")
+    del GY2
+    GY1 = bw.bn_bwd(G_a1, ctx["Y1"], ctx["bn1"], c1.norm, G, G_a1.shape[1], name="bn_bwd_desc.conv1")
+    del G_a1
+    W1 = _w2d(c1.conv.weight)
+    bw.wgrad(GY1, ctx["rows"], bw.g2d(c1.conv.weight), G, W1.shape[0], W1.shape[1], name="wgrad_desc.conv1")
+    # conv1..conv4 biases sit in front of a train-mode BatchNorm: exactly zero gradient (left zero-initialised)
+    return [bw.grads[q] for q in net.parameters()]

@@ -152,26 +152,48 @@ class KeypointOnPCLoss(nn.Module):
         return self.single_side_chamfer(keypoint, pc)
 
 
+class _DescTripletFn(torch.autograd.Function):
+    """loss (B,M), active (B) of DescPairScanLoss; backward through the two descriptor-space nearest neighbours."""
+
+    @staticmethod
+    def forward(ctx, anc, pos, neg, sigmas, gamma, sigma_max):
+        lib = _lib.load()
+        a = anc.contiguous(); p_ = pos.contiguous(); n_ = neg.contiguous(); sg = sigmas.contiguous().float()
+        B, C, M = a.shape
+        dev = a.device
+        dpos = torch.empty((B, M), dtype=torch.float32, device=dev); dneg = torch.empty_like(dpos)
+        ipos = torch.empty((B, M), dtype=torch.int32, device=dev); ineg = torch.empty_like(ipos)
+        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(p_), _p(dpos), _p(ipos), B, C, M, p_.shape[2], _stream()), "usip_desc_pairmin_f32")
+        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(n_), _p(dneg), _p(ineg), B, C, M, n_.shape[2], _stream()), "usip_desc_pairmin_f32")
+        loss = torch.empty_like(dpos); active = torch.empty((B,), dtype=torch.float32, device=dev)
+        _lib.check(lib.usip_desc_triplet(_p(dpos), _p(dneg), _p(sg), float(gamma), float(sigma_max), _p(loss), _p(active),
+                                         B, M, _stream()), "usip_desc_triplet")
+        ctx.save_for_backward(a, p_, n_, sg, dpos, ipos, dneg, ineg)
+        ctx.gamma, ctx.sigma_max = float(gamma), float(sigma_max)
+        ctx.mark_non_differentiable(active)
+        return loss, active
+
+    @staticmethod
+    def backward(ctx, g_loss, g_active):
+        a, p_, n_, sg, dpos, ipos, dneg, ineg = ctx.saved_tensors
+        B, C, M = a.shape
+        g_a = torch.zeros_like(a); g_p = torch.zeros_like(p_); g_n = torch.zeros_like(n_)
+        _lib.check(_lib.load().usip_desc_triplet_bwd(_p(a), _p(p_), _p(n_), _p(dpos), _p(ipos), _p(dneg), _p(ineg), _p(sg),
+                                                     ctx.gamma, ctx.sigma_max, _p(g_loss.contiguous().float()), _p(g_a), _p(g_p),
+                                                     _p(g_n), B, C, M, p_.shape[2], n_.shape[2], _stream()),
+                   "usip_desc_triplet_bwd")
+        return g_a, g_p, g_n, None, None, None
+
+
 class DescPairScanLoss(nn.Module):
     """Triplet loss over scan pairs (models/losses.py:190-237): for every anchor keypoint the closest descriptor in
     the positive and in the negative scan (two fused C-dimensional pairwise-min kernels instead of two (B,C,M,M)
-    difference tensors), sigma-derived weights.  Forward only in this round (SURVEY 8f-1 'next' row)."""
+    difference tensors), sigma-derived (detached) weights; backward through the matched pairs."""
 
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
 
     def forward(self, anc_descriptors, pos_descriptors, neg_descriptors, anc_sigmas):
-        if torch.is_grad_enabled() and (anc_descriptors.requires_grad or pos_descriptors.requires_grad):
-            raise NotImplementedError("DescPairScanLoss backward is not built yet; evaluate under torch.no_grad()")
-        lib = _lib.load()
-        a = anc_descriptors.contiguous(); p_ = pos_descriptors.contiguous(); n_ = neg_descriptors.contiguous()
-        B, C, M = a.shape
-        dev = a.device
-        dpos = torch.empty((B, M), dtype=torch.float32, device=dev); dneg = torch.empty_like(dpos)
-        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(p_), _p(dpos), None, B, C, M, p_.shape[2], _stream()), "usip_desc_pairmin_f32")
-        _lib.check(lib.usip_desc_pairmin_f32(_p(a), _p(n_), _p(dneg), None, B, C, M, n_.shape[2], _stream()), "usip_desc_pairmin_f32")
-        loss = torch.empty_like(dpos); active = torch.empty((B,), dtype=torch.float32, device=dev)
-        _lib.check(lib.usip_desc_triplet(_p(dpos), _p(dneg), _p(anc_sigmas.contiguous().float()), float(self.opt.triple_loss_gamma),
-                                         float(self.opt.sigma_max), _p(loss), _p(active), B, M, _stream()), "usip_desc_triplet")
-        return loss, active
+        return _DescTripletFn.apply(anc_descriptors, pos_descriptors, neg_descriptors, anc_sigmas.detach(),
+                                    self.opt.triple_loss_gamma, self.opt.sigma_max)
