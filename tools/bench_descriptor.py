@@ -92,6 +92,16 @@ def main():
         with torch.no_grad():
             med_d, _ = time_ms(lambda: net(pc, sn, kp, mode == "train", None), iters=10, warm=3)
         out["descriptor_forward_" + mode] = {"ms": med_d, "clouds_per_s": B / (med_d * 1e-3)}
+    # --- descriptor train step (ModelDescriptor.optimize: siamese forward, DescPairScanLoss, backward, Adam), 8 pairs
+    from usip_b200.models.keypoint_descriptor import ModelDescriptor
+    opt.random_pc_dropout_lower_limit = 1.0
+    md = ModelDescriptor(opt)
+    h = B // 2
+    md.set_input(pc[:h], sn[:h], kp[:h], torch.rand(h, M) * 3, pc[h:], sn[h:], kp[h:], torch.rand(h, M) * 3,
+                 torch.tensor([(i + 1) % h for i in range(h)]))
+    med_t, _ = time_ms(lambda: md.optimize(epoch=0), iters=8, warm=3)
+    out["descriptor_train_step"] = {"ms": med_t, "clouds_per_s": B / (med_t * 1e-3), "pairs": h,
+                                    "includes": "fwd (train BN) + DescPairScanLoss + backward + Adam"}
     print(json.dumps(out))
 
 
