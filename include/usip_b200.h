@@ -216,6 +216,12 @@ int usip_desc_triplet_bwd(const float* anc, const float* pos, const float* neg, 
 /* backward of usip_l2norm_to_bcm: g (B,C,M), raw rows Y [B*M, C] -> GY [B*M, C]                     networks.py:383 */
 int usip_l2norm_bwd(const float* g, const float* Y, int ldy, float* GY, int ldg, int B, int M, int C, void* stream);
 
+/* PointOnSurfaceLoss                                                                   models/losses.py:146-183
+ * kp (B,3,M), pc (B,3,N), sn (B,S,N) (first 3 channels = normal), arg (B,M) = nearest point (usip_pairwise_min_f32).
+ * loss != NULL: loss (B,M) = (n . (kp-p)/(||kp-p|| + 1e-7))^2;  g_kp != NULL: g_kp (B,3,M) = g (B,M) * dloss/dkp. */
+int usip_point_on_surface(const float* kp, const float* pc, const float* sn, const int32_t* arg, const float* g,
+                          float* loss, float* g_kp, int B, int M, int N, int S, void* stream);
+
 /* ---- backward of the loss kernels (autograd of models/losses.py / keypoint_detector.py:182-184) ---- */
 /* grad of sum_i g_i*gscale*min_d_i: grad_a (B,3,Ma) overwritten, grad_b (B,3,Nb) ACCUMULATED (pre-zero) or NULL */
 int usip_pairwise_min_bwd(const float* a, const float* b, const float* min_d, const int32_t* arg,

@@ -279,6 +279,26 @@ def chamfer_prob(src, dst, sig_src, sig_dst):
     return np.float32(fwd + bwd), np.float32(pure), np.float32(weighted)
 
 
+def point_on_surface(kp, pc, sn, g=None):
+    """PointOnSurfaceLoss (models/losses.py:146-183): nearest cloud point per keypoint, then the squared cosine between its
+    normal (first three channels of sn) and the unit vector from it to the keypoint.  Returns loss (B,M) and, if an
+    upstream gradient g (B,M) is given, d(sum g*loss)/d kp (B,3,M) -- the arg-min is piecewise constant."""
+    kp = np.asarray(kp, np.float32); pc = np.asarray(pc, np.float32); sn = np.asarray(sn, np.float32)
+    _, arg = pairwise_min(kp, pc)
+    B, _, M = kp.shape
+    p = np.stack([pc[b][:, arg[b]] for b in range(B)]); n = np.stack([sn[b][:3, arg[b]] for b in range(B)])
+    d = (kp - p).astype(np.float64); n = n.astype(np.float64)
+    r = np.sqrt((d ** 2).sum(1)); e = r + 1e-7
+    s = (n * d).sum(1) / e
+    loss = (s ** 2).astype(np.float32)
+    if g is None:
+        return loss
+    nd = (n * d).sum(1)
+    c = np.where(r > 0, nd / np.maximum(r, 1e-300) / e ** 2, 0.0)
+    grad = (2 * s * np.asarray(g, np.float64))[:, None, :] * (n / e[:, None, :] - d * c[:, None, :])
+    return loss, grad.astype(np.float32)
+
+
 def single_side_chamfer(kp, pc):
     """SingleSideChamferLoss_Brute.forward (models/losses.py:125-143) -> (B,M)."""
     d, _ = pairwise_min(kp, pc)

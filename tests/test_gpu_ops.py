@@ -414,3 +414,17 @@ def test_nms_vs_reference_golden_and_oracle(tmp_path):
     a = rng.normal(size=(100, 8)).astype(np.float64); np.save(str(tmp_path / "pc.npy"), a)
     pc, sn = sk.read_pointcloud_npy(str(tmp_path / "pc.npy"))
     assert pc.dtype == np.float32 and pc.shape == (100, 3) and np.array_equal(sn, a[:, 3:7].astype(np.float32))
+
+
+def test_point_on_surface_loss_vs_reference_golden():
+    """KeypointOnPCLoss(keypoint, pc, sn) = PointOnSurfaceLoss ('point_to_plane'): value (B,M,1,1) and keypoint gradient
+    against the reference's autograd (golden), S=4 surface-normal channels."""
+    from usip_b200.models import losses
+    from tests.util_gpu import make_opt
+    g = golden("losses.npz")
+    kp = cu(g["kp"]).requires_grad_(True)
+    out = losses.KeypointOnPCLoss(make_opt())(kp, cu(g["pc"]), cu(g["sn4"]))
+    assert tuple(out.shape) == tuple(g["on_surface"].shape)
+    (out.mean() * 0.37).backward()
+    assert rel_err(out.detach().cpu().numpy(), g["on_surface"]) < 1e-4
+    assert rel_err(kp.grad.cpu().numpy(), g["g_kp_surface"]) < 1e-4

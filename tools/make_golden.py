@@ -90,6 +90,13 @@ def golden_losses(ref):
     ssc = ref.losses.SingleSideChamferLoss_Brute(opt)(kpg, pc)
     ssc.mean().backward()
     out.update(kp=kp.numpy(), pc=pc.numpy(), single=ssc.detach().numpy(), g_kp=kpg.grad.numpy())
+    # point_to_plane (PointOnSurfaceLoss through KeypointOnPCLoss): value + gradient w.r.t. the keypoints
+    sn = torch.nn.functional.normalize(torch.randn(B, 3, 700), dim=1)
+    sn4 = torch.cat([sn, torch.rand(B, 1, 700)], 1)              # S=4: only the first three channels are the normal
+    kpp = kp.clone().requires_grad_(True)
+    pos = ref.losses.KeypointOnPCLoss(opt)(kpp, pc, sn4)
+    (pos.mean() * 0.37).backward()
+    out.update(sn4=sn4.numpy(), on_surface=pos.detach().numpy(), g_kp_surface=kpp.grad.numpy())
     # no-sigma branch
     l2, p2, w2 = crit(src, dst)
     out.update(nosigma=l2.numpy())

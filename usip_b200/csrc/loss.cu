@@ -269,6 +269,34 @@ desc_triplet_kernel(const float* __restrict__ dpos, const float* __restrict__ dn
   }
 }
 
+
+// PointOnSurfaceLoss (losses.py:146-183) after the nearest-point search: p = pc[:, arg], n = sn[0:3, arg],
+//   u = (kp - p) / (||kp - p|| + 1e-7),  loss = (n . u)^2     (B,M); the arg-min is not differentiated.
+// backward (g given): d = kp - p, r = ||d||, e = r + 1e-7, s = n . u:
+//   dloss/dkp = 2 s * ( n / e - d * (n . d) / (r * e^2) )     (r = 0: torch.norm's sub-gradient is 0 -> only n / e, and s = 0)
+__global__ void point_on_surface_kernel(const float* __restrict__ kp, const float* __restrict__ pc, const float* __restrict__ sn,
+                                        const int32_t* __restrict__ arg, const float* __restrict__ g, float* __restrict__ loss,
+                                        float* __restrict__ g_kp, int B, int M, int N, int S) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * M) return;
+  const int b = t / M, m = t - b * M;
+  const int j = arg[t];
+  const float* k = kp + (size_t)b * 3 * M; const float* p = pc + (size_t)b * 3 * N; const float* n = sn + (size_t)b * S * N;
+  const float dx = k[m] - p[j], dy = k[M + m] - p[N + j], dz = k[2 * M + m] - p[2 * N + j];
+  const float nx = n[j], ny = n[N + j], nz = n[2 * N + j];
+  const float r = sqrtf(dx * dx + dy * dy + dz * dz), e = r + 1e-7f;
+  const float ux = dx / e, uy = dy / e, uz = dz / e;
+  const float s = nx * ux + ny * uy + nz * uz;
+  if (loss) loss[t] = s * s;
+  if (g_kp) {
+    const float nd = nx * dx + ny * dy + nz * dz;
+    const float c = r > 0.f ? nd / (r * e * e) : 0.f;
+    const float f = 2.f * s * g[t];
+    float* o = g_kp + (size_t)b * 3 * M;
+    o[m] = f * (nx / e - dx * c); o[M + m] = f * (ny / e - dy * c); o[2 * M + m] = f * (nz / e - dz * c);
+  }
+}
+
 }  // namespace usip
 
 using namespace usip;
@@ -350,4 +378,11 @@ extern "C" int usip_desc_triplet(const float* dpos, const float* dneg, const flo
   USIP_REQUIRE(dpos && dneg && sigma && loss && active, "desc_triplet: bad args");
   desc_triplet_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dpos, dneg, sigma, gamma, sigma_max, loss, active, M);
   return check_launch("desc_triplet_kernel");
+}
+
+extern "C" int usip_point_on_surface(const float* kp, const float* pc, const float* sn, const int32_t* arg, const float* g,
+                                     float* loss, float* g_kp, int B, int M, int N, int S, void* stream) {
+  USIP_REQUIRE(kp && pc && sn && arg && (loss || (g && g_kp)) && S >= 3, "point_on_surface: bad args");
+  point_on_surface_kernel<<<cdiv(B * M, 256), 256, 0, (cudaStream_t)stream>>>(kp, pc, sn, arg, g, loss, g_kp, B, M, N, S);
+  return check_launch("point_on_surface_kernel");
 }

@@ -128,9 +128,13 @@ class ModelDetector():
                 self.keypoint_on_pc_criteria(self.src_keypoints, self.src_pc, None), self.opt.keypoint_on_pc_alpha)
             self.loss_keypoint_on_pc_dst = losses.mean_scale(
                 self.keypoint_on_pc_criteria(self.dst_keypoints, self.dst_pc, None), self.opt.keypoint_on_pc_alpha)
+        elif self.opt.keypoint_on_pc_type == 'point_to_plane':          # keypoint_detector.py:198-202
+            self.loss_keypoint_on_pc_src = losses.mean_scale(
+                self.keypoint_on_pc_criteria(self.src_keypoints, self.src_pc, self.src_sn), self.opt.keypoint_on_pc_alpha)
+            self.loss_keypoint_on_pc_dst = losses.mean_scale(
+                self.keypoint_on_pc_criteria(self.dst_keypoints, self.dst_pc, self.dst_sn), self.opt.keypoint_on_pc_alpha)
         else:
-            raise NotImplementedError("keypoint_on_pc_type=%r: only 'point_to_point' is on the B200 hot path"
-                                      % self.opt.keypoint_on_pc_type)
+            raise NotImplementedError("keypoint_on_pc_type=%r" % self.opt.keypoint_on_pc_type)
         self.loss = self.loss_chamfer + self.loss_keypoint_on_pc_src + self.loss_keypoint_on_pc_dst
 
     def _run_siamese(self, is_train, epoch):

@@ -139,17 +139,52 @@ class SingleSideChamferLoss_Brute(nn.Module):
         return _PairMinFn.apply(pc_src_input, pc_dst_input)
 
 
+class _PointOnSurfaceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, keypoint, pc, sn):
+        kp = keypoint.contiguous(); pc = pc.contiguous(); sn = sn.contiguous()
+        B, _, M = kp.shape
+        _, arg = ops.pairwise_min(kp, pc)                       # nearest cloud point of every keypoint (not differentiated)
+        loss = torch.empty((B, M), dtype=torch.float32, device=kp.device)
+        _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), None, _p(loss), None, B, M, pc.shape[2],
+                                                     sn.shape[1], _stream()), "usip_point_on_surface")
+        ctx.save_for_backward(kp, pc, sn, arg)
+        return loss.view(B, M, 1, 1)                            # the reference returns the (B,M,1,1) matmul result
+
+    @staticmethod
+    def backward(ctx, g):
+        kp, pc, sn, arg = ctx.saved_tensors
+        B, _, M = kp.shape
+        g_kp = torch.empty_like(kp)
+        _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), _p(g.reshape(B, M).contiguous().float()),
+                                                     None, _p(g_kp), B, M, pc.shape[2], sn.shape[1], _stream()),
+                   "usip_point_on_surface")
+        return g_kp, None, None
+
+
+class PointOnSurfaceLoss(nn.Module):
+    """models/losses.py:146-183 ('point_to_plane'): squared cosine between the surface normal of the nearest cloud point
+    and the direction from that point to the keypoint; gradient w.r.t. the keypoint only."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+
+    def forward(self, keypoint, pc, sn):
+        return _PointOnSurfaceFn.apply(keypoint, pc.detach(), sn.detach())
+
+
 class KeypointOnPCLoss(nn.Module):
     def __init__(self, opt):
         super().__init__()
         self.opt = opt
         self.single_side_chamfer = SingleSideChamferLoss_Brute(opt)
+        self.keypoint_on_surface = PointOnSurfaceLoss(opt)
 
     def forward(self, keypoint, pc, sn=None):
-        if sn is not None:
-            raise NotImplementedError("point_to_plane (PointOnSurfaceLoss, losses.py:146-183) is a non-default "
-                                      "option outside the B200 hot path; use keypoint_on_pc_type='point_to_point'")
-        return self.single_side_chamfer(keypoint, pc)
+        if sn is None:
+            return self.single_side_chamfer(keypoint, pc)
+        return self.keypoint_on_surface(keypoint, pc, sn)
 
 
 class _DescTripletFn(torch.autograd.Function):
