@@ -307,3 +307,50 @@ def test_desc_pair_scan_loss_and_model_descriptor_api():
     md.optimize(epoch=0)                                        # the train step itself is pinned by the golden test above
     assert np.isfinite(md.get_current_errors()["O_loss"])
     assert any(not torch.equal(v, before[k]) for k, v in md.descriptor.state_dict().items() if k.endswith("conv.weight"))
+
+
+@pytest.mark.parametrize("name,B,N,M,S,Kn,kind,lb,alpha", [
+    ("modelnet", 24, 5000, 512, 3, 32, "object", 1e-4, 1.0),           # BASELINE configs[1]
+    ("kitti", 8, 16384, 512, 4, 16, "lidar", 1e-3, 0.01),              # BASELINE configs[2] (the bench workload)
+])
+def test_full_size_baseline_configs(name, B, N, M, S, Kn, kind, lb, alpha):
+    """BASELINE.json's full-size detector configurations through size-independent checks: the node assignment is
+    bit-identical to the C oracle, the tcgen05 (3xTF32) and the fp32 SIMT layer paths agree to 1e-4 on keypoints /
+    sigmas / loss, CUDA-graph replay equals eager, and one full optimize() step runs and moves the parameters."""
+    from usip_b200 import ops
+    from usip_b200.models.keypoint_detector import ModelDetector
+    d = orc.synth_pair(B, N, M, S, kind=kind, seed=4321)
+    P = orc.init_detector_params(S=S, seed=7, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
+    x = np.concatenate([d["src_pc"], d["dst_pc"]]); node = np.concatenate([d["src_node"], d["dst_node"]])
+    min_idx, _ = ops.som_assign(cu(x), cu(node))
+    assert np.array_equal(min_idx.cpu().numpy(), orc.som_assign(x, node))
+    res = {}
+    for use_tc in (True, False):
+        opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn,
+                       loss_sigma_lower_bound=lb, keypoint_on_pc_alpha=alpha, use_tensor_cores=use_tc)
+        md = ModelDetector(opt)
+        load_params(md.detector, P)
+        md.set_input(*[torch.from_numpy(d[k]) for k in keys])
+        sd0 = {k: v.clone() for k, v in md.detector.state_dict().items()}
+        md.forward_loss(epoch=0, train_bn=True, graph=False)
+        res[use_tc] = (torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy(),
+                       torch.cat([md.src_sigmas, md.dst_sigmas]).cpu().numpy(), md.loss.item())
+        assert np.isfinite(res[use_tc][2]) and md.loss_keypoint_on_pc_src.item() >= 0
+        if use_tc:
+            md.detector.load_state_dict(sd0)
+            md.forward_loss(epoch=0, train_bn=True, graph=True)
+            assert md.loss.item() == res[True][2]
+            assert np.array_equal(torch.cat([md.src_keypoints, md.dst_keypoints]).cpu().numpy(), res[True][0])
+            md.detector.load_state_dict(sd0)
+            md.optimize(epoch=0)
+            torch.cuda.synchronize()
+            assert np.isfinite(md.loss.item())
+            assert abs(md.loss.item() - res[True][2]) <= 1e-4 * abs(res[True][2])      # same forward, autograd path
+            w = md.detector.state_dict()["mlp1.conv.weight"]
+            assert not torch.equal(w, sd0["mlp1.conv.weight"]) and bool(torch.isfinite(w).all())
+        del md
+        torch.cuda.empty_cache()
+    assert rel_err(res[True][0], res[False][0]) < REL and rel_err(res[True][1], res[False][1]) < REL
+    assert abs(res[True][2] - res[False][2]) <= REL * abs(res[False][2])
