@@ -20,7 +20,8 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
         Q = P // group
         kw = dict(gmax=torch.empty(Q, Cout, device=dev), gmin=torch.empty(Q, Cout, device=dev), group=group)
     res = {}
-    for name, flags in [("full", 0), ("no_epilogue", 1), ("no_xload", 2), ("3xtf32 full", 16)]:
+    for name, flags in [("full", 0), ("no_epilogue", 1), ("no_xload", 2), ("no_wtma", 4), ("no_Ystore", 32), ("no_stats_loop", 64),
+                        ("no_epi+no_xload+no_wtma", 7), ("tf32+2xbf16 cross terms", 16)]:
         def run(packed):
             ops.layer_fwd(X, W, b, P, Cin, Cout, in_scale=sc, in_shift=sh, in_relu=True, Y=Y, stat_partial=part,
                           precision=1, tc_ws=ws, tc_packed=packed, debug_flags=flags, **kw)
@@ -46,6 +47,6 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
     res["clk_mma_%"] = pct(slice(8, 9), ["wait_tempty", "wait_full", "issue"])
     res["clk_producer_%"] = pct(slice(9, 17), ["wait_empty", "tma+convert+sts", "fetch+fence+arrive", "loop"])
     flops = 2.0 * P * Cin * Cout
-    res["mma_floor_us_at_1965MHz"] = round(2 * flops / (148 * 2048 * 2 * 1.965e9) * 1e6, 1)
+    res["mma_floor_us_at_1965MHz"] = round(3 * flops / (148 * 2048 * 2 * 1.965e9) * 1e6, 1)
     out["%dx%d->%d%s" % (P, Cin, Cout, " g16 noY" if group else "")] = res
 print(json.dumps(out, indent=1))
