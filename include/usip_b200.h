@@ -126,10 +126,15 @@ typedef struct usip_layer_desc {
   void* tc_workspace;                  /* precision 1: >= usip_layer_tc_workspace_bytes(Cin,Cout) bytes */
   int64_t tc_workspace_bytes;
   int32_t tc_weights_packed;           /* 1: tc_workspace already holds the packed weights of this W  */
-  int32_t debug_flags;                 /* profiling aid for the tcgen05 kernel (results are then WRONG): 1 = skip the epilogue
-                                          body, 2 = producers skip the X loads, 4 = no weight TMA, 8 = issue 1 of the 3 MMAs; 32 = no Y stores, 128 (correct) = no L2 prefetch of X, 64 = no statistics / group pass; 16 (correct, ~1e-6 rel. error) = TF32 + 2 BF16 cross terms instead of 3xTF32 */
-  unsigned long long* debug_clocks;    /* optional [grid][17 warps][8] clock64() accumulators written by the tcgen05 kernel
-                                          (lane 0 of each warp): where each warp role spends its time; NULL = off */
+  int32_t debug_flags;                 /* profiling aids of the tcgen05 kernel, 0 in production (tools/tc_microbench.py).
+                                          Results become WRONG with: 1 = skip the epilogue body, 2 = producers skip the X
+                                          loads, 4 = no weight TMA, 8 = issue 1 of the 3 MMAs, 32 = no Y stores, 64 = no
+                                          statistics / group pass.  Results stay correct with: 16 = TF32 main product + two
+                                          BF16 cross terms instead of 3xTF32 (~1e-6 relative error), 128 = also prefetch X
+                                          tiles into L2 */
+  unsigned long long* debug_clocks;    /* [grid][17 warps][8] clock64() accumulators (lane 0 of each warp): where each warp
+                                          role spends its time.  Only written by a library built with -DUSIP_TC_PROF
+                                          (USIP_NVCC_EXTRA); NULL = off */
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);

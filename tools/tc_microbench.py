@@ -21,7 +21,7 @@ for (P, Cin, Cout, group, write_y) in [(131072, 512, 512, 16, False), (131072, 2
         kw = dict(gmax=torch.empty(Q, Cout, device=dev), gmin=torch.empty(Q, Cout, device=dev), group=group)
     res = {}
     for name, flags in [("full", 0), ("no_epilogue", 1), ("no_xload", 2), ("no_wtma", 4), ("no_Ystore", 32), ("no_stats_loop", 64),
-                        ("no_epi+no_xload+no_wtma", 7), ("tf32+2xbf16 cross terms", 16)]:
+                        ("no_epi+no_xload+no_wtma", 7), ("tf32+2xbf16 cross terms", 16), ("with L2 prefetch of X", 128)]:
         def run(packed):
             ops.layer_fwd(X, W, b, P, Cin, Cout, in_scale=sc, in_shift=sh, in_relu=True, Y=Y, stat_partial=part,
                           precision=1, tc_ws=ws, tc_packed=packed, debug_flags=flags, **kw)

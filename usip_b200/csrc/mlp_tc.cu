@@ -211,11 +211,10 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
       hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
       lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
     };
-    // L2 prefetch of whole X row tiles a few tiles ahead (one 16B-granular bulk prefetch per row, no registers or
-    // shared memory held): measured, the register prefetch alone keeps only ~16 KB per SM in flight, which at DRAM
-    // latency under load (~2 us) caps the X stream at ~1.2 TB/s for every layer shape (tools/tc_microbench.py).
+    // optional L2 prefetch of whole X row tiles a few tiles ahead (one 16B-granular bulk prefetch per row, no registers
+    // or shared memory held).  Measured: no change in run time -- the X stream is not DRAM-latency bound.
     const int pf_dist = min(8, max(1, (192 * 1024) / (TC_BM * Cin * 4)));
-    const bool pf_on = !(d.debug_flags & 128) && grp == 0;
+    const bool pf_on = (d.debug_flags & 128) && grp == 0;   // experiment only: measured no gain, off by default
     auto prefetch_tile = [&](int tile_i) {
       const long long tile_p = (long long)blockIdx.x + (long long)tile_i * (long long)gridDim.x;
       if (tile_p >= num_tiles) return;
