@@ -274,31 +274,29 @@ segmax_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 knn_nodes_kernel(const float* __restrict__ pts, int32_t* __restrict__ knn_idx, int B, int M, int K) {
-  extern __shared__ float sdist[];                 // 8 warps x M
+  extern __shared__ unsigned long long skey[];     // 8 warps x M packed keys (distance bits << 32 | index), built once
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * 8 + wib;
   if (w >= B * M) return;
   const int b = w / M, m = w - b * M;
   const float* p = pts + (size_t)b * 3 * M;
-  float* d = sdist + (size_t)wib * M;
+  unsigned long long* d = skey + (size_t)wib * M;
   const float qx = p[m], qy = p[M + m], qz = p[2 * M + m];
-  for (int j = lane; j < M; j += 32) d[j] = __fsqrt_rn(sqdist_rn(qx, qy, qz, p[j], p[M + j], p[2 * M + j]));
+  for (int j = lane; j < M; j += 32)
+    d[j] = ((unsigned long long)__float_as_uint(__fsqrt_rn(sqdist_rn(qx, qy, qz, p[j], p[M + j], p[2 * M + j]))) << 32) | (unsigned)j;
   __syncwarp();
   for (int k = 0; k < K; ++k) {
     unsigned long long best = ~0ull;
-    for (int j = lane; j < M; j += 32) {
-      unsigned long long key = ((unsigned long long)__float_as_uint(d[j]) << 32) | (unsigned)j;
-      best = key < best ? key : best;
-    }
+    for (int j = lane; j < M; j += 32) { const unsigned long long key = d[j]; best = key < best ? key : best; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
       best = other < best ? other : best;
     }
     int j = (int)(best & 0xffffffffu);
     if (k >= M) j = 0;                             // K > M: undefined in the reference (topk would throw)
     if (lane == 0) knn_idx[(size_t)w * K + k] = j;
-    if (lane == (j & 31) && k < M) d[j] = __uint_as_float(0xffffffffu);   // NaN bit pattern: max key
+    if (lane == (j & 31) && k < M) d[j] = ~0ull;   // taken: the largest key
     __syncwarp();
   }
 }
@@ -505,7 +503,7 @@ extern "C" int usip_segmax(const float* X, int ldx, const int32_t* seg_off, cons
 
 extern "C" int usip_knn_nodes(const float* pts, int32_t* knn_idx, int B, int M, int K, void* stream) {
   USIP_REQUIRE(pts && knn_idx && K > 0 && M > 0, "knn_nodes: bad args");
-  size_t smem = (size_t)8 * M * sizeof(float);
+  size_t smem = (size_t)8 * M * sizeof(unsigned long long);
   USIP_REQUIRE(smem <= 200 * 1024, "knn_nodes: M too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(knn_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   knn_nodes_kernel<<<cdiv(B * M, 8), 256, smem, (cudaStream_t)stream>>>(pts, knn_idx, B, M, K);

@@ -52,6 +52,44 @@ pairwise_min_kernel(const float* __restrict__ a, const float* __restrict__ b,
   }
 }
 
+// Small databases (Nb <= 2048: the keypoint <-> keypoint chamfer searches): one CTA owns PM_Q queries and walks ALL
+// database tiles, so no cross-CTA merge, no init / finish launches.  Same arithmetic and tie rule as above.
+__global__ void __launch_bounds__(PM_THREADS)
+pairwise_min_direct_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ min_d,
+                           int32_t* __restrict__ arg, int Ma, int Nb) {
+  __shared__ float4 sb[PM_TILE];
+  __shared__ float hbest[PM_Q]; __shared__ int hidx[PM_Q];
+  const int bb = blockIdx.y;
+  const int q = threadIdx.x & (PM_Q - 1), hf = threadIdx.x >> 7;
+  const int i = blockIdx.x * PM_Q + q;
+  const float* pa = a + (size_t)bb * 3 * Ma; const float* pb = b + (size_t)bb * 3 * Nb;
+  const bool ok = i < Ma;
+  const float ax = ok ? pa[i] : 0.f, ay = ok ? pa[Ma + i] : 0.f, az = ok ? pa[2 * Ma + i] : 0.f;
+  float best = INFINITY; int bj = 0;
+  for (int j0 = 0; j0 < Nb; j0 += PM_TILE) {
+    const int jc = min(PM_TILE, Nb - j0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < jc; t += PM_THREADS) sb[t] = make_float4(pb[j0 + t], pb[Nb + j0 + t], pb[2 * Nb + j0 + t], 0.f);
+    __syncthreads();
+    const int t0 = hf * (PM_TILE / 2), t1 = min(jc, t0 + PM_TILE / 2);
+    for (int t = t0; t < t1; ++t) {                 // ascending j inside a thread: '<' keeps the first minimum
+      const float4 p = sb[t];
+      const float d = sqdist_rn(ax, ay, az, p.x, p.y, p.z);
+      if (d < best) { best = d; bj = j0 + t; }
+    }
+  }
+  if (hf == 1) { hbest[q] = best; hidx[q] = bj; }
+  __syncthreads();
+  if (hf == 0 && ok) {
+    const float ob = hbest[q]; const int oj = hidx[q];
+    if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    const bool none = !(best == best) || !(best < INFINITY);
+    const size_t o = (size_t)bb * Ma + i;
+    if (min_d) min_d[o] = none ? INFINITY : __fsqrt_rn(best);
+    if (arg) arg[o] = none ? 0 : bj;
+  }
+}
+
 __global__ void pm_finish_kernel(const unsigned long long* __restrict__ packed, float* __restrict__ min_d,
                                  int32_t* __restrict__ arg, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,35 +113,41 @@ __device__ double block_sum(double v, double* sh) {
   return r;   // valid on thread 0
 }
 
-// losses.py:79-97.  Single CTA (sizes are B*M ~ 1e4).
+// losses.py:79-97.  Single CTA (sizes are B*M ~ 1e4).  Per-element arithmetic in fp32 like the reference (log, divide),
+// sums in fp64; the eight sums are reduced together (one barrier).
 __global__ void __launch_bounds__(1024)
 chamfer_prob_reduce_kernel(const float* __restrict__ d_sd, const int32_t* __restrict__ i_sd,
                            const float* __restrict__ d_ds, const int32_t* __restrict__ i_ds,
                            const float* __restrict__ sig_src, const float* __restrict__ sig_dst,
                            float* __restrict__ out3, int B, int M, int N) {
-  __shared__ double sh[32];
-  double f_loss = 0, f_d = 0, f_inv = 0, f_wd = 0;
+  __shared__ double sh[8][32];
+  double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // forward: loss, d, 1/s, d/s; backward: the same
   for (int t = threadIdx.x; t < B * M; t += blockDim.x) {
-    int b = t / M;
-    double s = 0.5 * ((double)sig_src[t] + (double)sig_dst[(size_t)b * N + i_sd[t]]);
-    double d = d_sd[t];
-    f_loss += log(s) + d / s; f_d += d; f_inv += 1.0 / s; f_wd += d / s;
+    const int b = t / M;
+    const float s = 0.5f * (sig_src[t] + sig_dst[(size_t)b * N + i_sd[t]]);
+    const float d = d_sd[t], ds = d / s;
+    r[0] += (double)(logf(s) + ds); r[1] += (double)d; r[2] += (double)(1.0f / s); r[3] += (double)ds;
   }
-  double b_loss = 0, b_d = 0, b_inv = 0, b_wd = 0;
   for (int t = threadIdx.x; t < B * N; t += blockDim.x) {
-    int b = t / N;
-    double s = 0.5 * ((double)sig_dst[t] + (double)sig_src[(size_t)b * M + i_ds[t]]);
-    double d = d_ds[t];
-    b_loss += log(s) + d / s; b_d += d; b_inv += 1.0 / s; b_wd += d / s;
+    const int b = t / N;
+    const float s = 0.5f * (sig_dst[t] + sig_src[(size_t)b * M + i_ds[t]]);
+    const float d = d_ds[t], ds = d / s;
+    r[4] += (double)(logf(s) + ds); r[5] += (double)d; r[6] += (double)(1.0f / s); r[7] += (double)ds;
   }
-  double r[8] = {f_loss, f_d, f_inv, f_wd, b_loss, b_d, b_inv, b_wd};
-  for (int q = 0; q < 8; ++q) r[q] = block_sum(r[q], sh);
-  if (threadIdx.x == 0) {
-    double nf = (double)B * M, nb = (double)B * N;
-    out3[0] = (float)(r[0] / nf + r[4] / nb);
-    out3[1] = (float)(r[1] / nf + r[5] / nb);
-    // mean(w*d), w = (1/s)/mean(1/s)  ==  mean(d/s) / mean(1/s)
-    out3[2] = (float)((r[3] / nf) / (r[2] / nf) + (r[7] / nb) / (r[6] / nb));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { r[q] = warp_sum_d(r[q]); if (lane == 0) sh[q][w] = r[q]; }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = warp_sum_d(lane < (int)(blockDim.x >> 5) ? sh[q][lane] : 0.0);
+    if (lane == 0) {
+      const double nf = (double)B * M, nb = (double)B * N;
+      out3[0] = (float)(r[0] / nf + r[4] / nb);
+      out3[1] = (float)(r[1] / nf + r[5] / nb);
+      // mean(w*d), w = (1/s)/mean(1/s)  ==  mean(d/s) / mean(1/s)
+      out3[2] = (float)((r[3] / nf) / (r[2] / nf) + (r[7] / nb) / (r[6] / nb));
+    }
   }
 }
 
@@ -305,6 +349,10 @@ extern "C" int usip_pairwise_min_f32(const float* a, const float* b, float* min_
                                      unsigned long long* packed, int B, int Ma, int Nb, void* stream) {
   USIP_REQUIRE(a && b && packed && B > 0 && Ma > 0 && Nb > 0, "pairwise_min: bad args");
   cudaStream_t st = (cudaStream_t)stream;
+  if (Nb <= 4 * PM_TILE) {
+    pairwise_min_direct_kernel<<<dim3(cdiv(Ma, PM_Q), B), PM_THREADS, 0, st>>>(a, b, min_d, arg, Ma, Nb);
+    return check_launch("pairwise_min_direct_kernel");
+  }
   size_t n = (size_t)B * Ma;
   pm_init_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(packed, n);
   dim3 grid(cdiv(Nb, PM_TILE), cdiv(Ma, PM_Q), B);
