@@ -52,38 +52,51 @@ pairwise_min_kernel(const float* __restrict__ a, const float* __restrict__ b,
   }
 }
 
-// Small databases (Nb <= 2048: the keypoint <-> keypoint chamfer searches): one CTA owns PM_Q queries and walks ALL
-// database tiles, so no cross-CTA merge, no init / finish launches.  Same arithmetic and tie rule as above.
+// Direct variant: one CTA owns Q queries (256 / Q threads per query, each on its slice of every tile) and walks ALL
+// database tiles, so there is no cross-CTA merge and no init / finish launch.  Q = 128 for small databases (the
+// keypoint <-> keypoint chamfer searches), Q = 32 for keypoints against a whole cloud (B * Ma / 32 CTAs).  Same
+// arithmetic and tie rule as above: smaller distance, then smaller index.
+template <int Q>
 __global__ void __launch_bounds__(PM_THREADS)
 pairwise_min_direct_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ min_d,
                            int32_t* __restrict__ arg, int Ma, int Nb) {
+  constexpr int SL = PM_THREADS / Q;               // slices per query
+  constexpr int SPAN = PM_TILE / SL;               // database points per slice and tile
   __shared__ float4 sb[PM_TILE];
-  __shared__ float hbest[PM_Q]; __shared__ int hidx[PM_Q];
+  __shared__ float hbest[SL][Q]; __shared__ int hidx[SL][Q];
   const int bb = blockIdx.y;
-  const int q = threadIdx.x & (PM_Q - 1), hf = threadIdx.x >> 7;
-  const int i = blockIdx.x * PM_Q + q;
+  const int q = threadIdx.x % Q, sl = threadIdx.x / Q;
+  const int i = blockIdx.x * Q + q;
   const float* pa = a + (size_t)bb * 3 * Ma; const float* pb = b + (size_t)bb * 3 * Nb;
   const bool ok = i < Ma;
   const float ax = ok ? pa[i] : 0.f, ay = ok ? pa[Ma + i] : 0.f, az = ok ? pa[2 * Ma + i] : 0.f;
-  float best = INFINITY; int bj = 0;
+  float best0 = INFINITY, best1 = INFINITY; int bj0 = 0, bj1 = 0;
   for (int j0 = 0; j0 < Nb; j0 += PM_TILE) {
     const int jc = min(PM_TILE, Nb - j0);
     __syncthreads();
     for (int t = threadIdx.x; t < jc; t += PM_THREADS) sb[t] = make_float4(pb[j0 + t], pb[Nb + j0 + t], pb[2 * Nb + j0 + t], 0.f);
     __syncthreads();
-    const int t0 = hf * (PM_TILE / 2), t1 = min(jc, t0 + PM_TILE / 2);
-    for (int t = t0; t < t1; ++t) {                 // ascending j inside a thread: '<' keeps the first minimum
-      const float4 p = sb[t];
-      const float d = sqdist_rn(ax, ay, az, p.x, p.y, p.z);
-      if (d < best) { best = d; bj = j0 + t; }
+    const int t0 = sl * SPAN, t1 = min(jc, t0 + SPAN);
+    int t = t0;
+    for (; t + 1 < t1; t += 2) {                   // two independent chains; ascending j inside each: '<' keeps the first minimum
+      const float4 p0 = sb[t], p1 = sb[t + 1];
+      const float d0 = sqdist_rn(ax, ay, az, p0.x, p0.y, p0.z), d1 = sqdist_rn(ax, ay, az, p1.x, p1.y, p1.z);
+      if (d0 < best0) { best0 = d0; bj0 = j0 + t; }
+      if (d1 < best1) { best1 = d1; bj1 = j0 + t + 1; }
     }
+    if (t < t1) { const float4 p0 = sb[t]; const float d0 = sqdist_rn(ax, ay, az, p0.x, p0.y, p0.z); if (d0 < best0) { best0 = d0; bj0 = j0 + t; } }
   }
-  if (hf == 1) { hbest[q] = best; hidx[q] = bj; }
+  float best = best0; int bj = bj0;
+  if (best1 < best || (best1 == best && bj1 < bj)) { best = best1; bj = bj1; }
+  hbest[sl][q] = best; hidx[sl][q] = bj;
   __syncthreads();
-  if (hf == 0 && ok) {
-    const float ob = hbest[q]; const int oj = hidx[q];
-    if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
-    const bool none = !(best == best) || !(best < INFINITY);
+  if (sl == 0 && ok) {
+#pragma unroll
+    for (int s2 = 1; s2 < SL; ++s2) {
+      const float ob = hbest[s2][q]; const int oj = hidx[s2][q];
+      if (ob < best || (ob == best && oj < bj)) { best = ob; bj = oj; }
+    }
+    const bool none = !(best < INFINITY);
     const size_t o = (size_t)bb * Ma + i;
     if (min_d) min_d[o] = none ? INFINITY : __fsqrt_rn(best);
     if (arg) arg[o] = none ? 0 : bj;
@@ -350,7 +363,11 @@ extern "C" int usip_pairwise_min_f32(const float* a, const float* b, float* min_
   USIP_REQUIRE(a && b && packed && B > 0 && Ma > 0 && Nb > 0, "pairwise_min: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   if (Nb <= 4 * PM_TILE) {
-    pairwise_min_direct_kernel<<<dim3(cdiv(Ma, PM_Q), B), PM_THREADS, 0, st>>>(a, b, min_d, arg, Ma, Nb);
+    pairwise_min_direct_kernel<128><<<dim3(cdiv(Ma, 128), B), PM_THREADS, 0, st>>>(a, b, min_d, arg, Ma, Nb);
+    return check_launch("pairwise_min_direct_kernel");
+  }
+  if ((long long)cdiv(Ma, 32) * B >= 96) {           // enough CTAs to fill the machine without splitting the database
+    pairwise_min_direct_kernel<32><<<dim3(cdiv(Ma, 32), B), PM_THREADS, 0, st>>>(a, b, min_d, arg, Ma, Nb);
     return check_launch("pairwise_min_direct_kernel");
   }
   size_t n = (size_t)B * Ma;
