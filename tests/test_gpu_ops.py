@@ -432,8 +432,8 @@ def test_point_on_surface_loss_vs_reference_golden():
 
 @pytest.mark.parametrize("B,Ma,Nb", [(2, 64, 700), (2, 100, 5000), (8, 512, 5000), (3, 33, 2049)])
 def test_pairwise_min_all_paths_vs_oracle(B, Ma, Nb):
-    """usip_pairwise_min_f32 picks one of three kernels by shape (direct with 128 / 32 queries per CTA, split database
-    with a 64-bit atomicMin merge): distances and first-index arg-min equal the oracle bit for bit, exact ties included."""
+    """usip_pairwise_min_f32 picks one of two kernels by database size (direct, or split database with a 64-bit atomicMin
+    merge): distances and first-index arg-min equal the oracle bit for bit, exact ties included."""
     from usip_b200 import ops
     rng = np.random.default_rng(B * 1000 + Ma)
     a = rng.normal(size=(B, 3, Ma)).astype(np.float32)

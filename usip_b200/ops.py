@@ -254,8 +254,8 @@ def pairwise_min(a, b):
     packed = torch.empty((B, Ma), dtype=torch.int64, device=a.device)
     check(_lib.load().usip_pairwise_min_f32(_p(a), _p(b), _p(d), _p(arg), _p(packed), B, Ma, Nb, _stream()),
           "usip_pairwise_min_f32")
-    if Nb <= 2048 or ((Ma + 31) // 32) * B >= 96:
-        _lib.LAUNCHES[0] -= 2          # single-kernel path (no init / finish launches), same rule as loss.cu
+    if Nb <= 2048:
+        _lib.LAUNCHES[0] -= 2          # small databases take the single-kernel path (no init / finish launches)
     return d, arg
 
 
