@@ -436,6 +436,71 @@ layer_fwd_rowwarp_kernel(const usip_layer_desc d) {
   }
 }
 
+// First layer of a point stack: Cin <= 8 input channels (xyz + surface normal), Cout in {32, 64}, raw input (no folded
+// BN), Y + BN statistics out.  HBM-bound (8 B in, 4*Cout B out per row); the generic 128x64x16 register tile pads K to
+// 16 and ran at 25 % of that roofline.  CTA = 128 rows, 4 warps x 32 rows; a lane owns channels lane (and lane + 32)
+// with their <= 8 weights in registers, so a row costs two broadcast shared loads, <= 16 FMAs and one / two coalesced
+// 128-byte stores.  One statistics partial per CTA = per 128-row tile, like the generic SIMT kernel.
+template <int NCH>                                   // channels per lane: Cout = 32 * NCH
+__global__ void __launch_bounds__(128)
+layer_fwd_narrow_kernel(const usip_layer_desc d) {
+  __shared__ float4 sx[128][2];
+  __shared__ float sred[4][2][32 * NCH];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int row0 = blockIdx.x * 128;
+  const int P = d.P, Cin = d.Cin, Cout = d.Cout;
+  {   // stage the 128 x 8 input tile (zero padded)
+    const int r = row0 + tid;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < P) {
+      const float* x = d.X + (size_t)r * d.ldx;
+      if (d.ldx >= 8 && (d.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(d.X) & 15) == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(x), b = *reinterpret_cast<const float4*>(x + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        for (int k = Cin; k < 8; ++k) v[k] = 0.f;
+      } else {
+        for (int k = 0; k < Cin; ++k) v[k] = x[k];
+      }
+    }
+    sx[tid][0] = make_float4(v[0], v[1], v[2], v[3]); sx[tid][1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  float wr[NCH][8], br[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int n = lane + 32 * c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[c][k] = k < Cin ? (d.w_transposed ? d.W[(size_t)k * d.ldw + n] : d.W[(size_t)n * d.ldw + k]) : 0.f;
+    br[c] = d.bias ? d.bias[n] : 0.f;
+  }
+  __syncthreads();
+  float s[NCH], q[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { s[c] = 0.f; q[c] = 0.f; }
+  const int nrows = min(32, max(0, P - (row0 + w * 32)));
+  for (int r = 0; r < nrows; ++r) {
+    const float4 a = sx[w * 32 + r][0], b = sx[w * 32 + r][1];
+    const size_t row = (size_t)row0 + w * 32 + r;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float y = br[c];
+      y = fmaf(a.x, wr[c][0], y); y = fmaf(a.y, wr[c][1], y); y = fmaf(a.z, wr[c][2], y); y = fmaf(a.w, wr[c][3], y);
+      y = fmaf(b.x, wr[c][4], y); y = fmaf(b.y, wr[c][5], y); y = fmaf(b.z, wr[c][6], y); y = fmaf(b.w, wr[c][7], y);
+      if (d.Y) d.Y[row * d.ldy + lane + 32 * c] = y;
+      s[c] += y; q[c] = fmaf(y, y, q[c]);
+    }
+  }
+  if (d.stat_partial) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) { sred[w][0][lane + 32 * c] = s[c]; sred[w][1][lane + 32 * c] = q[c]; }
+    __syncthreads();
+    for (int i = tid; i < 2 * Cout; i += 128) {
+      const int which = i / Cout, n = i - which * Cout;
+      d.stat_partial[((size_t)blockIdx.x * 2 + which) * Cout + n] =
+          (sred[0][which][n] + sred[1][which][n]) + (sred[2][which][n] + sred[3][which][n]);
+    }
+  }
+}
+
 // descriptor / (||descriptor||_2 + 1e-5) over channels, [Q,C] rows -> reference (B,C,M) layout (networks.py:383)
 __global__ void __launch_bounds__(256)
 l2norm_to_bcm_kernel(const float* __restrict__ X, int ldx, float* __restrict__ out, float* __restrict__ norm_out, int B,
@@ -499,6 +564,11 @@ extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
     const size_t smem = (size_t)(8 + 2) * d.Cin * sizeof(float);
     layer_fwd_rowwarp_kernel<8><<<cdiv(d.P, 8), 256, smem, st>>>(d);
     return check_launch("layer_fwd_rowwarp_kernel");
+  }
+  if (d.Cin <= 8 && (d.Cout == 32 || d.Cout == 64) && !d.in_scale && !d.in_relu && !d.addend && !d.gmax && !d.gmin) {
+    if (d.Cout == 64) layer_fwd_narrow_kernel<2><<<cdiv(d.P, 128), 128, 0, st>>>(d);
+    else layer_fwd_narrow_kernel<1><<<cdiv(d.P, 128), 128, 0, st>>>(d);
+    return check_launch("layer_fwd_narrow_kernel");
   }
   if (d.Cout <= 64) return launch_layer_simt<64>(d, st);
   return launch_layer_simt<128>(d, st);
