@@ -443,3 +443,18 @@ def test_pairwise_min_all_paths_vs_oracle(B, Ma, Nb):
     d, arg = ops.pairwise_min(cu(a), cu(b))
     rd, ra = orc.pairwise_min(a, b)
     assert np.array_equal(arg.cpu().numpy(), ra) and np.array_equal(d.cpu().numpy(), rd)
+
+
+def test_knn_gather_matches_reference_semantics():
+    """operations.knn_gather_by_indexing / knn_gather_wrapper (operations.py:243-287): out[b,c,n,k] = src[b,c,I[b,n,k]],
+    i.e. the expand + torch.gather of the reference, bit for bit (pure data movement)."""
+    from usip_b200.models import operations
+    torch.manual_seed(3)
+    B, C, N, K = 3, 5, 700, 9
+    src = torch.randn(B, C, N, device=dev())
+    idx = torch.randint(0, N, (B, N, K), device=dev())
+    out = operations.knn_gather_by_indexing(src, idx)
+    ref = torch.gather(src.unsqueeze(3).expand(B, C, N, K), 2, idx.unsqueeze(1).expand(B, C, N, K))
+    assert torch.equal(out, ref)
+    out3 = operations.knn_gather_wrapper(src[:, :3].contiguous(), idx)
+    assert torch.equal(out3, ref[:, :3])
