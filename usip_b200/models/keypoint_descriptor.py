@@ -4,13 +4,12 @@ DescPairScanLoss) on the fused B200 plan: `forward`, `forward_siamese`, `run_mod
 `ModelDescriptorIndoor` depends on a network that is
 broken in the reference itself (networks.py:447 calls a commented-out function) and is out of scope."""
 import os
-import random
 from collections import OrderedDict
 
-import numpy as np
 import torch
 
 from . import losses, networks
+from ._common import random_point_dropout
 
 
 class ModelDescriptor():
@@ -63,15 +62,8 @@ class ModelDescriptor():
         """keypoint_descriptor.py:126-157: optional random point dropout (same RNG streams), train-mode forward of the
         (anchor, positive) batch, triplet loss against the in-batch negatives, backward, Adam."""
         with torch.cuda.device(self.anc_pc.get_device()):
-            if self.opt.random_pc_dropout_lower_limit < 0.99:
-                dropout_keep_ratio = random.uniform(self.opt.random_pc_dropout_lower_limit, 1.0)
-                resulting_pc_num = round(dropout_keep_ratio * self.opt.input_pc_num)
-                chosen_indices = np.random.choice(self.opt.input_pc_num, resulting_pc_num, replace=False)
-                chosen_indices_tensor = torch.from_numpy(chosen_indices).to(self.opt.device)
-                self.anc_pc = torch.index_select(self.anc_pc, dim=2, index=chosen_indices_tensor)
-                self.anc_sn = torch.index_select(self.anc_sn, dim=2, index=chosen_indices_tensor)
-                self.pos_pc = torch.index_select(self.pos_pc, dim=2, index=chosen_indices_tensor)
-                self.pos_sn = torch.index_select(self.pos_sn, dim=2, index=chosen_indices_tensor)
+            self.anc_pc, self.anc_sn, self.pos_pc, self.pos_sn = random_point_dropout(
+                self.opt, self.anc_pc, self.anc_sn, self.pos_pc, self.pos_sn)
             self.descriptor.train()
             (self.anc_descriptors, self.pos_descriptors), _ = self.forward_siamese(
                 (self.anc_pc, self.pos_pc), (self.anc_sn, self.pos_sn), (self.anc_keypoints, self.pos_keypoints),

@@ -9,13 +9,12 @@ statistics stay per rank (the per-replica semantics DataParallel already has) an
 all-reduce of a flat fp32 gradient buffer (`enable_data_parallel()`), launched by `optimize()`.
 """
 import os
-import random
 from collections import OrderedDict
 
-import numpy as np
 import torch
 
 from . import losses, networks
+from ._common import random_point_dropout
 
 
 class ModelDetector():
@@ -148,15 +147,8 @@ class ModelDetector():
 
     def optimize(self, epoch=None):
         with torch.cuda.device(self.src_pc.get_device()):
-            if self.opt.random_pc_dropout_lower_limit < 0.99:      # keypoint_detector.py:161-169, same RNG streams
-                dropout_keep_ratio = random.uniform(self.opt.random_pc_dropout_lower_limit, 1.0)
-                resulting_pc_num = round(dropout_keep_ratio * self.opt.input_pc_num)
-                chosen_indices = np.random.choice(self.opt.input_pc_num, resulting_pc_num, replace=False)
-                chosen_indices_tensor = torch.from_numpy(chosen_indices).to(self.opt.device)
-                self.src_pc = torch.index_select(self.src_pc, dim=2, index=chosen_indices_tensor)
-                self.src_sn = torch.index_select(self.src_sn, dim=2, index=chosen_indices_tensor)
-                self.dst_pc = torch.index_select(self.dst_pc, dim=2, index=chosen_indices_tensor)
-                self.dst_sn = torch.index_select(self.dst_sn, dim=2, index=chosen_indices_tensor)
+            self.src_pc, self.src_sn, self.dst_pc, self.dst_sn = random_point_dropout(
+                self.opt, self.src_pc, self.src_sn, self.dst_pc, self.dst_sn)
             self.detector.train()
             self._run_siamese(is_train=True, epoch=epoch)
             if self._flat_grad is not None:
