@@ -2,13 +2,17 @@
 """bench.py -- clouds/sec of the USIP detector fwd+loss hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
-  python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (unmodified reference staged
+                                                           # under oracle/_ref/py + its C++ index_max; else the port)
 
 Workload (config.workload): BASELINE.json configs[2] "KITTI detector" -- per rank B=8 pairs = 16 clouds,
 N=16384 points, M=512 nodes, S=4, node kNN K=16, train-mode BatchNorm, probabilistic chamfer + 2x
 keypoint-on-pc loss.  A step = one fwd+loss pass over one synthetic batch.  Weak scaling: every rank processes its
-own batch; the fwd+loss path has no collective (the gradient all-reduce belongs to the train step, reported in
-`train_step`).  `value` = clouds of all ranks / max-over-ranks device time, inputs resident in HBM (a rotating set of
+own batch; the fwd+loss path has no collective; the gradient all-reduce belongs to the train step, which is timed in
+every run and reported in `train_step` (fwd+loss+backward+Adam, + the NCCL all-reduce when N>1).  At N=1 the line also
+carries `reference_gpu` (the UNMODIFIED reference's 1-GPU PyTorch path on the same tensors, same GPU: the ">=10x"
+denominator of BASELINE.json's north_star) and `descriptor` (Oxford descriptor path: fused ball-query+group roofline,
+descriptor forward).  `value` = clouds of all ranks / max-over-ranks device time, inputs resident in HBM (a rotating set of
 distinct batches larger than L2); `e2e` = same metric through ModelDetector.set_input() from pinned host tensors +
 loss.item() every step.
 """
@@ -96,33 +100,82 @@ def make_batches(nb, cfg, seed0):
 KEYS = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
 
 
+def _workload_config(cfg, world):
+    return {"workload": "KITTI detector fwd+loss (BASELINE configs[2]): per rank B=8 pairs (16 clouds), "
+                        "N=16384, M=512, S=4, node_knn_k=16, train-mode BN, chamfer + 2x keypoint-on-pc",
+            "global_pairs": cfg["B"] * world}
+
+
+def _ref_opt(ref_shim, cfg, B, **over):
+    return ref_shim.make_opt(batch_size=B, input_pc_num=cfg["N"], node_num=cfg["M"], surface_normal_len=cfg["S"],
+                             node_knn_k_1=cfg["Kn"], loss_sigma_lower_bound=cfg["lb"], keypoint_on_pc_alpha=cfg["alpha"], **over)
+
+
+def _ref_fwd_loss_train_bn(rmd):
+    """The reference's own fwd+loss code (ModelDetector.test_model, keypoint_detector.py:209-241) with train-mode
+    BatchNorm statistics -- the metric's definition -- under no_grad: test_model() begins with
+    self.detector.eval(); the instance attribute below turns that one call into a no-op so the detector stays in train()."""
+    import torch
+    rmd.detector.train()
+    rmd.detector.eval = lambda: rmd.detector
+    try:
+        with torch.no_grad():
+            rmd.test_model()
+    finally:
+        del rmd.detector.eval
+    return rmd.loss
+
+
 def cpu_reference_run(cfg, steps, warmup, threads=None):
-    """The reference algorithm's CPU path (oracle port: numpy + C restatement, validated against the real reference in
-    tests/golden) on a bounded sample: ONE pair (2 clouds) of the same workload per step."""
+    """The reference's CPU path on a bounded sample: ONE pair (2 clouds) of the same workload per step.
+    kind="reference": the unmodified reference (oracle/_ref/py, its own C++ index_max.forward_cpu) through oracle/ref_shim;
+    kind="port": the numpy/C oracle restatement, only when the reference is not staged."""
     from oracle import usip_oracle as orc
     import torch
     threads = threads or os.cpu_count()
-    try:
-        from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=threads)
-    except Exception:
-        limiter = None
+    torch.set_num_threads(threads)
     d = orc.synth_pair(1, cfg["N"], cfg["M"], cfg["S"], kind=cfg["kind"], seed=999)
     P = orc.init_detector_params(S=cfg["S"], seed=0)
+    kind = "port"
+    try:
+        from oracle import ref_shim
+        if ref_shim.reference_available():
+            ref = ref_shim.modules(mode="cpu")
+            from tests.util_gpu import load_params
+            rmd = ref.keypoint_detector.ModelDetector(_ref_opt(ref_shim, cfg, 1))
+            load_params(rmd.detector, P)
+            rmd.set_input(*[torch.from_numpy(d[k]) for k in KEYS])
+            kind = "reference"
+    except Exception as e:  # pragma: no cover
+        print("[bench] reference CPU path unavailable (%s); timing the oracle port" % e, file=sys.stderr)
+        kind = "port"
+    limiter = None
+    if kind == "port":
+        try:
+            from threadpoolctl import threadpool_limits
+            limiter = threadpool_limits(limits=threads)
+        except Exception:
+            pass
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc.detector_fwd_loss(P, d["src_pc"], d["src_sn"], d["src_node"], d["dst_pc"], d["dst_sn"], d["dst_node"],
-                              d["R"], d["scale"], d["shift"], node_knn_k=cfg["Kn"], sigma_lower_bound=cfg["lb"],
-                              alpha=cfg["alpha"], training=True)
+        if kind == "reference":
+            float(_ref_fwd_loss_train_bn(rmd))
+        else:
+            orc.detector_fwd_loss(P, d["src_pc"], d["src_sn"], d["src_node"], d["dst_pc"], d["dst_sn"], d["dst_node"],
+                                  d["R"], d["scale"], d["shift"], node_knn_k=cfg["Kn"], sigma_lower_bound=cfg["lb"],
+                                  alpha=cfg["alpha"], training=True)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     del limiter
     t = float(np.mean(times))
-    return dict(value=2.0 / t, unit="clouds/s", cores=int(threads), kind="port",
-                sample="%d x (1 pair = 2 clouds, N=%d, M=%d) fwd+loss, numpy/BLAS + C oracle port; %.2f s per pair"
-                       % (len(times), cfg["N"], cfg["M"], t)), t
+    what = ("unmodified reference ModelDetector (models/keypoint_detector.py:209-241, train-mode BN, no_grad) on CPU, "
+            "torch %d threads, its own C++ index_max.forward_cpu" % threads) if kind == "reference" else \
+           "numpy/BLAS + C oracle port"
+    return dict(value=2.0 / t, unit="clouds/s", cores=int(threads), kind=kind,
+                sample="%d x (1 pair = 2 clouds, N=%d, M=%d) fwd+loss, %s; %.2f s per pair"
+                       % (len(times), cfg["N"], cfg["M"], what, t)), t
 
 
 def run_reference_arm(args):
@@ -130,17 +183,74 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cfg = dict(KITTI)
-    steps = max(1, min(args.steps, 5)); warmup = min(args.warmup, 1)
+    steps = max(1, args.steps); warmup = max(0, args.warmup)
     cb, t = cpu_reference_run(cfg, steps, warmup)
+    conf = _workload_config(cfg, 1)
+    conf["reference_sample"] = "bounded sample of that workload: 1 pair (2 clouds) per step on the host cores"
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clouds/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "KITTI detector fwd+loss, bounded sample: 1 pair (2 clouds) per step", "B_pairs": 1,
-                       "N": cfg["N"], "M": cfg["M"], "S": cfg["S"], "node_knn_k": cfg["Kn"], "bn": "train"},
+            "config": conf,
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def reference_gpu_record(cfg, resident, P, dev, ours_ms, ours_train_ms, iters=20, warm=5):
+    """The UNMODIFIED reference's 1-GPU PyTorch path (oracle/_ref/py + its two CUDA extensions) on the same resident
+    tensors and parameters, CUDA-event timed on this GPU: `fwd_loss` = its own test_model() code with train-mode BN under
+    no_grad (the metric), `train_step` = its optimize().  Two precision settings: TF32 off (the fp32 arithmetic our
+    3xTF32 path is equivalent to) and PyTorch's defaults (cuDNN convolutions may use TF32)."""
+    import torch
+    from oracle import build_ref, ref_shim
+    if not (ref_shim.reference_available() and build_ref.have("index_max") and build_ref.have("ball_query")):
+        return {"unavailable": "oracle/_ref (staged reference tree + its two extensions) not built"}
+    from tests.util_gpu import load_params
+    ref = ref_shim.modules(mode="cuda")
+    rmd = ref.keypoint_detector.ModelDetector(_ref_opt(ref_shim, cfg, cfg["B"], device=dev, gpu_ids=[dev.index or 0]))
+    load_params(rmd.detector, P)
+    nb = len(resident)
+
+    def assign(i):
+        b = resident[i % nb]
+        rmd.src_pc, rmd.src_sn, rmd.src_node = b["src_pc"], b["src_sn"], b["src_node"]
+        rmd.dst_pc, rmd.dst_sn, rmd.dst_node = b["dst_pc"], b["dst_sn"], b["dst_node"]
+        rmd.src_R_dst, rmd.src_scale_dst, rmd.src_shift_dst = b["R"], b["scale"], b["shift"]
+
+    def timed(fn):
+        for i in range(warm):
+            assign(i); fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            assign(i); fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    clouds = 2 * cfg["B"]
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {"what": "unmodified lijx10/USIP ModelDetector on cuda:%d, same tensors/parameters, %d warm-up + %d timed "
+                   "iterations, CUDA events" % (dev.index or 0, warm, iters), "clouds_per_step": clouds}
+    try:
+        for tag, tf32 in (("tf32_off", False), ("torch_default", None)):
+            if tf32 is None:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+            else:
+                torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+            ms_f = timed(lambda: _ref_fwd_loss_train_bn(rmd))
+            ms_t = timed(lambda: rmd.optimize(epoch=0))
+            out[tag] = {"fwd_loss_ms": ms_f, "fwd_loss_clouds_per_s": clouds / (ms_f * 1e-3),
+                        "train_step_ms": ms_t, "train_step_clouds_per_s": clouds / (ms_t * 1e-3),
+                        "ours_speedup_fwd_loss": ms_f / ours_ms,
+                        "ours_speedup_train_step": None if ours_train_ms is None else ms_t / ours_train_ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["peak_mem_GB"] = torch.cuda.max_memory_allocated(dev) / 1e9
+    del rmd
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -151,7 +261,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT layers only")
-    ap.add_argument("--train", action="store_true", help="also time the full train step (fwd+loss+bwd+Adam)")
+    ap.add_argument("--train", action="store_true", help="(kept for compatibility: the train step is always timed)")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step record")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own GPU path (N=1 only)")
+    ap.add_argument("--no-descriptor", action="store_true", help="skip the descriptor-path sub-record (N=1 only)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     ap.add_argument("--nbatches", type=int, default=18, help="distinct resident input batches (18 x 7.3 MB > 126 MB L2)")
     args = ap.parse_args()
@@ -180,7 +293,8 @@ def main():
                    node_knn_k_1=cfg["Kn"], loss_sigma_lower_bound=cfg["lb"], keypoint_on_pc_alpha=cfg["alpha"],
                    use_tensor_cores=not args.no_tc, device=dev, gpu_ids=[local])
     md = ModelDetector(opt)
-    load_params(md.detector, orc.init_detector_params(S=cfg["S"], seed=0))     # same weights on every rank
+    P0 = orc.init_detector_params(S=cfg["S"], seed=0)
+    load_params(md.detector, P0)                                              # same weights on every rank
     nb = args.nbatches
     host = make_batches(nb, cfg, seed0=1234 + 2 + 1000 * rank)
     pinned = [{k: torch.from_numpy(b[k]).pin_memory() for k in KEYS} for b in host]
@@ -311,30 +425,47 @@ def main():
                     os.path.basename(f), t["dram_bytes_read"] / 1e6, t["dram_bytes_write"] / 1e6, 4e-6 * P_ * Ci_, 8e-6 * (P_ // 16) * Co_)
                 break
 
+    # ---- full train step (BASELINE configs[2] / [4]): fwd + loss + backward + Adam (+ NCCL gradient all-reduce, N>1)
     train = None
-    if args.train:
+    if not args.no_train:
         def step_train(i):
             assign(resident[i % nb])
             md.optimize(epoch=0)
         if world > 1:
             md.enable_data_parallel()
-        for i in range(3):
+        for i in range(W):
             step_train(i)
         ms_t, l_t = timed(step_train, K)
         train = {"value": clouds * K / (ms_t * 1e-3), "unit": "clouds/s", "ms_per_step": ms_t / K, "gpu_launches": l_t,
-                 "includes": "fwd+loss+backward+Adam" + ("+NCCL grad all-reduce" if world > 1 else "")}
+                 "includes": "fwd (train BN) + loss + backward + Adam" + (" + NCCL all-reduce of the flat 4.79 MB gradient buffer" if world > 1 else ""),
+                 "loss_after": float(md.loss)}
+        assert np.isfinite(train["loss_after"])
 
-    cb = None
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_reference_run(cfg, steps=3, warmup=1)
+    # ---- N=1 extras: the reference's own GPU path on the same tensors, the descriptor path, the CPU baseline
+    ref_gpu = desc = cb = None
+    if rank == 0 and world == 1:
+        if not args.no_descriptor:
+            from tools import bench_descriptor
+            desc = bench_descriptor.records(dev, pk if roof else peaks(), quick=True)
+        if not args.no_reference_gpu:
+            try:
+                ref_gpu = reference_gpu_record(cfg, resident, P0, dev, ms / K, None if train is None else train["ms_per_step"])
+            except Exception as e:                                  # the denominator is evidence, never a reason to lose the line
+                ref_gpu = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        if not args.no_cpu_baseline:
+            # own interpreter: the CPU shim of the reference patches torch.cuda.* and cannot share a process with the GPU arm
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                               capture_output=True, text=True, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+            try:
+                cb = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                cb = {"unavailable": (r.stderr or r.stdout)[-300:]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "KITTI detector fwd+loss (BASELINE configs[2]): per rank B=8 pairs (16 clouds), "
-                                       "N=16384, M=512, S=4, node_knn_k=16, train-mode BN, chamfer + 2x keypoint-on-pc",
-                           "global_pairs": cfg["B"] * world, "parallelism": "dp%d (independent ranks, no collective on fwd+loss)" % world,
+                "config": {**_workload_config(cfg, world), "parallelism": "dp%d (independent ranks, no collective on fwd+loss)" % world,
                            "l2": "inputs rotate over %d distinct resident batches (%.0f MB > 126 MB L2); activations per step ~1.5 GB" % (nb, nb * h2d_bytes / 1e6),
                            "matmul_precision": "fp32 SIMT" if args.no_tc else "3xTF32 tcgen05 (fp32-equivalent) + fp32 SIMT for narrow layers",
                            "launch": "CUDA-graph replay of the step (ModelDetector.forward_loss(graph=True))" if use_graph else "eager"},
@@ -345,6 +476,10 @@ def main():
             line["cpu_baseline"] = cb
         if train:
             line["train_step"] = train
+        if ref_gpu:
+            line["reference_gpu"] = ref_gpu
+        if desc:
+            line["descriptor"] = desc
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

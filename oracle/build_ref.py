@@ -75,12 +75,53 @@ def have(name):
     return os.path.isfile(_so_path(name))
 
 
+# The unmodified Python files of the reference's hot path.  They are STAGED (byte-for-byte, never edited) next to the two
+# compiled extensions under the git-ignored oracle/_ref/py/ so that the GPU box -- where /root/reference does not exist --
+# can run the reference itself: as the full-size floating-point oracle (tests/test_gpu_vs_reference.py) and as the
+# "reference 1-GPU PyTorch path" denominator of bench.py (`reference_gpu`).  Nothing staged is committed.
+PY_OUT = os.path.join(REF_OUT, "py")
+_PY_FILES = [
+    "models/keypoint_detector.py", "models/keypoint_descriptor.py", "models/networks.py", "models/layers.py",
+    "models/losses.py", "models/operations.py",
+    "util/__init__.py", "util/som.py", "util/potential_field.py", "util/vis_tools.py",
+    "data/augmentation.py",
+]
+
+
+def stage_py():
+    """Copy the hot-path .py files of the mounted reference into oracle/_ref/py/ (idempotent; returns the directory)."""
+    import shutil
+    for rel in _PY_FILES:
+        src = os.path.join(REFERENCE_ROOT, rel)
+        if not os.path.isfile(src):
+            raise FileNotFoundError(src)
+        dst = os.path.join(PY_OUT, rel)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        if not os.path.isfile(dst) or open(src, "rb").read() != open(dst, "rb").read():
+            shutil.copyfile(src, dst)
+    return PY_OUT
+
+
+def have_py():
+    return all(os.path.isfile(os.path.join(PY_OUT, rel)) for rel in _PY_FILES)
+
+
+def reference_py_root():
+    """Where the reference's Python tree can be imported from: the mount (build container) or the staged copy."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "models")):
+        return REFERENCE_ROOT
+    if have_py():
+        return PY_OUT
+    return None
+
+
 def build_all(verbose=False):
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "models")):
         return False
     for n in _EXTS:
         if not have(n):
             build(n, verbose=verbose)
+    stage_py()
     return True
 
 

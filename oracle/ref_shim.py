@@ -1,14 +1,17 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
-Import shim that lets the UNMODIFIED reference (lijx10/USIP, mounted read-only at
-/root/reference) run on CPU inside the build container, so that
+Import shim that lets the UNMODIFIED reference (lijx10/USIP) run as the checker / the baseline:
 
-  * the oracle restatement (oracle/usip_oracle.py, oracle/usip_oracle.c) can be pinned
-    against the real reference, and
-  * golden vectors can be generated for tests/golden/ (tools/make_golden.py).
+  * mode="cpu" (build container and `bench.py --impl reference`): the reference on the host cores, so that the
+    oracle restatement (oracle/usip_oracle.py, oracle/usip_oracle.c) can be pinned against it, golden vectors can be
+    generated for tests/golden/ (tools/make_golden.py) and the reference's own CPU path can be timed;
+  * mode="cuda" (GPU box): the reference's own 1-GPU PyTorch path with its own two CUDA extensions
+    (oracle/_ref/{index_max,ball_query}.so) -- the full-size floating-point oracle of tests/test_gpu_vs_reference.py
+    and the `reference_gpu` denominator of bench.py.
 
-/root/reference does not exist on the GPU box, therefore nothing in the `-m gpu` tests,
-smoke() or bench.py imports this file.
+The reference tree is imported from /root/reference where it is mounted (build container) and otherwise from the
+byte-identical staged copy oracle/_ref/py/ (oracle/build_ref.py: stage_py; git-ignored, travels with gpurun), so the
+GPU box never reads /root/reference.
 
 What the shim does (follows SURVEY.md Appendix B):
   1. empty stub modules for matplotlib / mpl_toolkits / h5py (imported but unused on the path),
@@ -26,13 +29,23 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("USIP_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_installed = False
+_installed = None          # None | "cpu" | "cuda"
+
+
+def reference_root():
+    from . import build_ref
+    return build_ref.reference_py_root()
+
+
+def build_ref_root():
+    """The mounted reference (files that are NOT staged, e.g. evaluation/save_keypoints.py, only exist there)."""
+    from . import build_ref
+    return build_ref.REFERENCE_ROOT
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+    return reference_root() is not None
 
 
 def _stub(name, **attrs):
@@ -49,13 +62,17 @@ def _ball_query_restatement(node_to_point_dist, radius, K):
     return torch.from_numpy(orc.ball_query_dist(d, float(radius), int(K)))
 
 
-def install(use_ref_ext: bool = True):
-    """Make `import models.networks` etc. resolve to the reference, runnable on CPU."""
+def install(use_ref_ext: bool = True, mode: str = "cpu"):
+    """Make `import models.networks` etc. resolve to the reference (CPU shims, or its own CUDA extensions)."""
     global _installed
-    if _installed:
+    if _installed is not None:
+        if _installed != mode:
+            raise RuntimeError("ref_shim already installed in %s mode; one mode per process" % _installed)
         return
-    if not reference_available():
-        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree neither mounted nor staged under oracle/_ref/py (run oracle/build_ref.py "
+                           "in the build container)")
 
     # 1. stubs
     mpl = _stub("matplotlib")
@@ -64,6 +81,14 @@ def install(use_ref_ext: bool = True):
     tk = _stub("mpl_toolkits")
     tk.mplot3d = _stub("mpl_toolkits.mplot3d", Axes3D=None)
     _stub("h5py")
+
+    if mode == "cuda":
+        # 2'. the reference's own CUDA extensions, compiled from its sources by oracle/build_ref.py
+        from . import build_ref
+        sys.modules["index_max"] = build_ref._load_so("index_max")
+        sys.modules["ball_query"] = build_ref._load_so("ball_query")
+        _finish(root, mode)
+        return
 
     # 2. operator modules
     ref_im = None
@@ -88,13 +113,19 @@ def install(use_ref_ext: bool = True):
     torch.cuda.synchronize = lambda *a, **k: None
     torch.Tensor.get_device = lambda self: 0
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    _finish(root, mode)
+
+
+def _finish(root, mode):
+    global _installed
+    if root in sys.path:
+        sys.path.remove(root)
+    sys.path.insert(0, root)
     # our own package also has a `models` mirror; make sure the reference wins under this shim
     for name in list(sys.modules):
-        if name == "models" or name.startswith("models.") or name == "util" or name.startswith("util."):
+        if name.split(".")[0] in ("models", "util", "data"):
             del sys.modules[name]
-    _installed = True
+    _installed = mode
 
 
 def make_opt(**over):
@@ -114,8 +145,8 @@ def make_opt(**over):
     return o
 
 
-def modules():
-    install()
+def modules(mode="cpu"):
+    install(mode=mode)
     networks = importlib.import_module("models.networks")
     losses = importlib.import_module("models.losses")
     layers = importlib.import_module("models.layers")

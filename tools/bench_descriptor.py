@@ -30,13 +30,12 @@ def time_ms(fn, iters=20, warm=3, flush=None):
     return float(np.median(ts)), float(np.min(ts))
 
 
-def main():
+def records(dev, pk, quick=False):
+    """All descriptor-path measurements as a dict.  quick=True (bench.py's default line) skips the slow reference-kernel
+    comparisons and the train step, and uses fewer iterations."""
     from usip_b200 import ops, index_max, ball_query
     from usip_b200.models import networks
     from tests.util_gpu import make_opt, ref_ext
-    import bench
-    dev = torch.device("cuda:0")
-    pk = bench.peaks()
     torch.manual_seed(1234 + 3)
     B, N, M, K, S = 16, 16384, 1024, 64, 4
     pc = torch.stack([torch.empty(B, N, device=dev).uniform_(-40, 40), torch.empty(B, N, device=dev).uniform_(-2, 2),
@@ -55,7 +54,7 @@ def main():
                                "frac": alg_bytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"],
                                "note": "4 launches (partial boxes, histogram + last-CTA scan, scatter to cell-sorted records, warp-per-keypoint query); L2 flushed between iterations"}
     # --- reference path for the same result: materialise (B,M,N) distances + reference ball_query kernel + gather
-    rb = ref_ext("ball_query")
+    rb = None if quick else ref_ext("ball_query")
     if rb is not None:
         def ref_path():
             dist = torch.norm(kp.unsqueeze(3) - pc.unsqueeze(2), p=2, dim=1, keepdim=False)
@@ -78,13 +77,13 @@ def main():
     rec = {"ours_ms": a, "bytes": data.numel() * 4 + index.numel() * 4 + 16 * 128 * 512 * 4}
     rec["ours_GBs"] = rec["bytes"] / (a * 1e-3) / 1e9
     rec["frac_hbm"] = rec["ours_GBs"] / pk["hbm_gbs"]
-    ri = ref_ext("index_max")
+    ri = None if quick else ref_ext("index_max")
     if ri is not None:
         b, _ = time_ms(lambda: ri.forward_cuda(data, index, 512), iters=5, warm=1, flush=flush)
         rec["reference_kernel_ms"] = b
     out["index_max_op"] = rec
     # --- descriptor forward (eval BN), clouds/s
-    opt = make_opt(batch_size=B // 2, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K,
+    opt = make_opt(device=dev, gpu_ids=[dev.index or 0], batch_size=B // 2, input_pc_num=N, node_num=M, surface_normal_len=S, ball_radius=1.0, ball_nsamples=K,
                    descriptor_len=128)
     net = networks.DescriptorLiteOld(opt).to(dev)
     for mode in ("eval", "train"):
@@ -92,6 +91,8 @@ def main():
         with torch.no_grad():
             med_d, _ = time_ms(lambda: net(pc, sn, kp, mode == "train", None), iters=10, warm=3)
         out["descriptor_forward_" + mode] = {"ms": med_d, "clouds_per_s": B / (med_d * 1e-3)}
+    if quick:
+        return out
     # --- descriptor train step (ModelDescriptor.optimize: siamese forward, DescPairScanLoss, backward, Adam), 8 pairs
     from usip_b200.models.keypoint_descriptor import ModelDescriptor
     opt.random_pc_dropout_lower_limit = 1.0
@@ -102,7 +103,12 @@ def main():
     med_t, _ = time_ms(lambda: md.optimize(epoch=0), iters=8, warm=3)
     out["descriptor_train_step"] = {"ms": med_t, "clouds_per_s": B / (med_t * 1e-3), "pairs": h,
                                     "includes": "fwd (train BN) + DescPairScanLoss + backward + Adam"}
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    import bench
+    print(json.dumps(records(torch.device("cuda:0"), bench.peaks())))
 
 
 if __name__ == "__main__":

@@ -256,7 +256,7 @@ def _reference_function(relpath, name):
     """The reference's own, unmodified source of one top-level function, executed here (its module cannot be imported:
     evaluation/save_keypoints.py is a script with hard-coded dataset paths and GUI / visdom imports)."""
     import ast
-    src = open(os.path.join(ref_shim.REFERENCE_ROOT, relpath)).read()
+    src = open(os.path.join(ref_shim.build_ref_root(), relpath)).read()
     node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
     ns = {"np": np}
     exec(compile(ast.Module(body=[node], type_ignores=[]), relpath, "exec"), ns)

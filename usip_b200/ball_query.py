@@ -4,7 +4,15 @@
 
 plus `forward_fused(xyz, feat, centers, radius, K)`, the B200 path that never builds the (B,M,N) distance
 matrix (replaces models/networks.py:355-373)."""
-from . import ops as _ops
+import os as _os
+import sys as _sys
+
+# importable both as `usip_b200.ball_query` and -- with <repo>/usip_b200 first on sys.path, the reference's own import style
+# (models/networks.py:9-18) -- as the bare top-level name: make the `usip_b200` package itself resolvable either way
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+if _ROOT not in _sys.path:
+    _sys.path.append(_ROOT)
+from usip_b200 import ops as _ops  # noqa: E402
 
 
 def forward_cuda_shared_mem(node_to_point_dist, radius, K):

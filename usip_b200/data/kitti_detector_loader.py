@@ -8,7 +8,7 @@ step of this repository, hence on the critical path once the step is ~1 ms.
 import numpy as np
 import torch
 
-from .. import ops
+from usip_b200 import ops
 
 
 class FarthestSampler:

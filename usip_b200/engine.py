@@ -93,11 +93,24 @@ def _tc_workspace(W, P, Cin, Cout, group, transposed):
     return ws, False
 
 
+def invalidate_packed_weights(module):
+    """Drop every cached packed (hi/lo TF32) weight tile of `module`'s parameters.  The cache key follows the autograd
+    version counter, which in-place writes through `.data` (legacy checkpoint loaders, EMA, weight clipping) do NOT bump:
+    call this after such a write.  load_state_dict(), train()/eval() switches and the optimizer step invalidate by
+    themselves (models/networks.py hooks; Adam bumps the version)."""
+    for p in module.parameters():
+        p.__dict__.pop("_usip_tc", None)
+
+
 import os as _os
 _TC_PREC = 2 if _os.environ.get("USIP_TC_PAIR") else 1     # A/B switch: opt into the CTA-pair kernel for wide layers
 
 
-def _precision_for(P, Cin, Cout, use_tc):
+def _precision_for(P, Cin, Cout, use_tc, group=0):
+    """Tensor-core kernel only for shapes it implements; everything else takes the fp32 SIMT kernel.  The tcgen05 group
+    epilogue handles groups of 16/32/64/128 rows (the SIMT kernel any multiple of 4 dividing 128)."""
+    if group and group not in (16, 32, 64, 128):
+        return 0
     return _TC_PREC if (use_tc and Cin % 32 == 0 and Cout % 64 == 0 and P >= 1024) else 0
 
 
@@ -140,7 +153,7 @@ class LayerRunner:
         Cout, Cin = W.shape
         if Y is None and write_y:
             Y = torch.empty((P, Cout), dtype=f32, device=self.dev)
-        prec = _precision_for(P, Cin, Cout, self.use_tc)
+        prec = _precision_for(P, Cin, Cout, self.use_tc, group if want_group else 0)
         part, ntiles = self.partials(P, Cout, prec, group, want_group) if norm is not None else (None, 0)
         grp = None
         if want_group:
@@ -532,15 +545,16 @@ def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, k
         idx, feats, rows = ops.ball_group(x, snp, kp, float(opt.ball_radius), K, want_group=True, rows_ld=8)
     c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
     D = c3.conv.weight.shape[0]
-    Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, _bn_mom(c1.norm, epoch), name="desc.conv1")
-    Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, _bn_mom(c2.norm, epoch), prev=bn1, name="desc.conv2")
-    Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, _bn_mom(c3.norm, epoch), prev=bn2,
+    # networks.py:375-379 calls conv1..conv4 WITHOUT epoch: the descriptor's BN momentum never decays
+    Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, c1.norm.momentum, name="desc.conv1")
+    Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, c2.norm.momentum, prev=bn1, name="desc.conv2")
+    Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, c3.norm.momentum, prev=bn2,
                           group=K, want_group=True, want_arg=keep, name="desc.conv3")
     amax = torch.empty((Q, D), dtype=f32, device=dev)
     ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
     W4 = _w2d(c4.conv.weight)
     U, _, _ = R.run(amax, Q, _cols(W4, D), None, relu_in=False, name="desc.conv4_node")        # cat(y_first, max): max is LAST
-    Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, _bn_mom(c4.norm, epoch), prev=bn3, addend=U,
+    Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, c4.norm.momentum, prev=bn3, addend=U,
                        add_group=K, name="desc.conv4")
     _, _, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), prev=bn4, group=K, want_group=True,
                        want_arg=keep, write_y=False, name="desc.conv5")

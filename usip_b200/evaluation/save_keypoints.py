@@ -10,7 +10,7 @@ checkpoints, plotting) is out of scope.
 import numpy as np
 import torch
 
-from .. import ops
+from usip_b200 import ops
 
 
 def nms(keypoints_np, sigmas_np, NMS_radius, device="cuda"):

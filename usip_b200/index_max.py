@@ -6,7 +6,15 @@ Both names run the same sm_100a kernel (usip_index_max_f32): the reference's two
 where the running max lives, and its shared-memory variant silently returns zeros once B*K > 12288
 (index_max_cuda.cu:92-96, no cudaFuncSetAttribute) -- that limit does not exist here.
 The CPU entry points are deliberately not provided: this build has no CPU path."""
-from . import ops as _ops
+import os as _os
+import sys as _sys
+
+# importable both as `usip_b200.index_max` and -- with <repo>/usip_b200 first on sys.path, the reference's own import style
+# (models/networks.py:9-18) -- as the bare top-level name: make the `usip_b200` package itself resolvable either way
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+if _ROOT not in _sys.path:
+    _sys.path.append(_ROOT)
+from usip_b200 import ops as _ops  # noqa: E402
 
 
 def forward_cuda_shared_mem(data, index, K):

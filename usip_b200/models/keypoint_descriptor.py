@@ -75,7 +75,7 @@ class ModelDescriptor():
 
     def test_model(self):
         self.descriptor.eval()
-        with torch.no_grad():
+        with torch.cuda.device(self.anc_pc.device), torch.no_grad():
             (self.anc_descriptors, self.pos_descriptors), _ = self.forward_siamese(
                 (self.anc_pc, self.pos_pc), (self.anc_sn, self.pos_sn), (self.anc_keypoints, self.pos_keypoints),
                 is_train=False, epoch=None)
@@ -87,7 +87,7 @@ class ModelDescriptor():
 
     def run_model(self, pc, sn, keypoints):
         self.descriptor.eval()
-        with torch.no_grad():
+        with torch.cuda.device(pc.device), torch.no_grad():
             descriptors, _ = self.descriptor(pc, sn, keypoints, False, None)
         return descriptors
 

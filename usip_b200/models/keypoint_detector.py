@@ -59,7 +59,7 @@ class ModelDetector():
     # ------------------------------------------------------------------ data parallel (one process / GPU)
     def enable_data_parallel(self, process_group=None):
         """Switch on the gradient all-reduce.  Call after torch.distributed.init_process_group."""
-        from ..dp import FlatGradAllReduce
+        from usip_b200.dp import FlatGradAllReduce
         self._dp = FlatGradAllReduce(self.detector.parameters(), process_group, buffers=list(self.detector.buffers()))
         self._flat_grad = self._dp.flat
 
@@ -162,7 +162,7 @@ class ModelDetector():
 
     def test_model(self):
         self.detector.eval()
-        with torch.no_grad():
+        with torch.cuda.device(self.src_pc.device), torch.no_grad():    # kernels launch on the inputs' device, whatever is current
             self._run_siamese(is_train=False, epoch=None)
             self._losses()
 
@@ -179,6 +179,10 @@ class ModelDetector():
         first time a given input shape / BN momentum / parameter version is seen, inputs are copied into the graph's
         static buffers, outputs (loss, keypoints, sigmas, ...) are the graph's static output tensors."""
         self.detector.train(train_bn)
+        with torch.cuda.device(self.src_pc.device):
+            return self._forward_loss(epoch, train_bn, graph)
+
+    def _forward_loss(self, epoch, train_bn, graph):
         if not graph:
             with torch.no_grad():
                 self._run_siamese(is_train=train_bn, epoch=epoch)
@@ -193,7 +197,7 @@ class ModelDetector():
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
-        from .. import _lib
+        from usip_b200 import _lib
         _lib.LAUNCHES[0] += self._graph_launches
         for k, v in zip(self._GRAPH_INPUTS, self._graph_in):
             setattr(self, k, v)
@@ -202,16 +206,21 @@ class ModelDetector():
         return self.loss
 
     def _capture_forward_loss(self, key, ins, epoch, train_bn):
-        from .. import _lib
+        from usip_b200 import _lib
         self._graph_in = [t.clone() for t in ins]
         for k, v in zip(self._GRAPH_INPUTS, self._graph_in):
             setattr(self, k, v)
+        # the warm-up passes must not count as training steps: BatchNorm running statistics (and num_batches_tracked)
+        # are restored afterwards, so a captured run leaves the same buffers behind as an eager one
+        bn_buffers = [(b, b.detach().clone()) for b in self.detector.buffers()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side), torch.no_grad():          # warm-up on a side stream (allocator, smem attributes,
             for _ in range(2):                                   # packed-weight cache) before capture
                 self._run_siamese(is_train=train_bn, epoch=epoch)
                 self._losses()
+            for b, saved in bn_buffers:
+                b.copy_(saved)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()

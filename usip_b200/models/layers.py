@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 from torch.nn.modules.batchnorm import _BatchNorm
 
-from .. import ops
+from usip_b200 import ops
 
 _SUPPORTED_ACT = (None, "relu")
 

@@ -12,8 +12,8 @@ import ctypes
 import torch
 import torch.nn as nn
 
-from .. import _lib, ops
-from ..ops import _p, _stream
+from usip_b200 import _lib, ops
+from usip_b200.ops import _p, _stream
 
 
 class _PairMinFn(torch.autograd.Function):
@@ -22,7 +22,7 @@ class _PairMinFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         a = a.contiguous(); b = b.contiguous()
-        from .. import engine
+        from usip_b200 import engine
         with engine._Prof("pairwise_min[%dx%dx%d]" % (a.shape[0], a.shape[2], b.shape[2])):
             d, arg = ops.pairwise_min(a, b)
         ctx.save_for_backward(a, b, d, arg)
@@ -45,7 +45,7 @@ class _ChamferProbFn(torch.autograd.Function):
     def forward(ctx, src, dst, sig_src, sig_dst):
         src = src.contiguous(); dst = dst.contiguous()
         sig_src = sig_src.contiguous(); sig_dst = sig_dst.contiguous()
-        from .. import engine
+        from usip_b200 import engine
         with engine._Prof("chamfer_prob"):
             d_sd, i_sd = ops.pairwise_min(src, dst)
             d_ds, i_ds = ops.pairwise_min(dst, src)

@@ -11,7 +11,31 @@ import torch
 import torch.nn as nn
 
 from .layers import EquivariantLayer, GeneralKNNFusionModule, MyConv2d, PointNet
-from .. import engine
+from usip_b200 import engine
+
+
+def _check_group(k, name):
+    """The fused group-max epilogues (usip_layer_fwd) take groups that are a multiple of 4 and divide 128."""
+    if k % 4 != 0 or 128 % k != 0:
+        raise NotImplementedError("%s=%d: the B200 plan supports group sizes 4, 8, 16, 32, 64, 128 "
+                                  "(every shipped configuration uses 16, 32 or 64)" % (name, k))
+
+
+class _PackedWeightHooks:
+    """Mixin: keeps the packed tensor-core weight cache (engine._tc_workspace) honest across the writes that do not bump
+    the parameters' autograd version -- load_state_dict and mode switches re-pack; `invalidate_packed_weights()` is the
+    explicit hook for in-place `.data` edits (EMA, clipping, legacy loaders)."""
+
+    def _install_weight_hooks(self):
+        self.register_load_state_dict_post_hook(lambda module, incompatible: engine.invalidate_packed_weights(module))
+
+    def invalidate_packed_weights(self):
+        engine.invalidate_packed_weights(self)
+
+    def train(self, mode=True):
+        if mode != self.training:
+            engine.invalidate_packed_weights(self)
+        return super().train(mode)
 
 
 class _DetectorFn(torch.autograd.Function):
@@ -39,7 +63,7 @@ class _DetectorFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(grads)
 
 
-class _RPNBase(nn.Module):
+class _RPNBase(_PackedWeightHooks, nn.Module):
     C1 = 128
     C2 = 512
 
@@ -53,6 +77,7 @@ class _RPNBase(nn.Module):
                                        activation=opt.activation, normalization=opt.normalization, **kw)
         self.second_pointnet = PointNet(C1, [C1, C1], activation=opt.activation, normalization=opt.normalization, **kw)
         assert self.opt.node_knn_k_1 >= 2
+        _check_group(self.opt.node_knn_k_1, "node_knn_k_1")
         self.knnlayer_1 = GeneralKNNFusionModule(3 + C1, (C2 // 2, C2 // 2, C2 // 2), (C2, C2),
                                                  activation=opt.activation, normalization=opt.normalization, **kw)
         self.mlp1 = EquivariantLayer(C1 + C2, 512, activation=opt.activation, normalization=opt.normalization, **kw)
@@ -64,6 +89,7 @@ class _RPNBase(nn.Module):
         self.use_tc = bool(getattr(opt, "use_tensor_cores", True))
         self._keep = False
         self._last_aux = None
+        self._install_weight_hooks()
         if opt.activation != "relu" or opt.normalization != "batch":
             raise NotImplementedError("the B200 plan implements activation='relu', normalization='batch'")
 
@@ -107,7 +133,7 @@ class _DescriptorFn(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(grads)
 
 
-class DescriptorLiteOld(nn.Module):
+class DescriptorLiteOld(_PackedWeightHooks, nn.Module):
     """models/networks.py:310-385.  forward(x, sn, keypoints, is_train, epoch) -> (descriptor (B,C,M),
     x_features (B,3+S,M,K))."""
 
@@ -124,8 +150,10 @@ class DescriptorLiteOld(nn.Module):
         self.conv3 = MyConv2d(D // 2, D, **kw)
         self.conv4 = MyConv2d(D * 2, D, **kw)
         self.conv5 = MyConv2d(D, D, kernel_size=(1, 1), stride=1, padding=0, bias=True, activation=None, normalization=None)
+        _check_group(opt.ball_nsamples, "ball_nsamples")
         self.use_tc = bool(getattr(opt, "use_tensor_cores", True))
         self._keep = False
+        self._install_weight_hooks()
 
     def forward(self, x, sn, keypoints, is_train=False, epoch=None):
         if not x.is_cuda:

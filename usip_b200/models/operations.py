@@ -6,7 +6,7 @@ Inside the fused detector plan the gather never materialises (B,C,N,K) (the cons
 these functions are the stand-alone entry points with the reference's signature."""
 import torch
 
-from .. import ops
+from usip_b200 import ops
 
 # generalized batch size / SOM size limits of the reference's shared-memory kernels (operations.py:16-18); kept for
 # attribute compatibility -- the B200 kernels have no such cap.

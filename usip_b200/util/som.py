@@ -9,7 +9,7 @@ network plan (usip_b200/engine.py) consumes min_idx / counts directly and never 
 The SOM / BatchSOM fitting classes (util/som.py:57-417) are not on the hot path and are not provided."""
 import torch
 
-from .. import ops
+from usip_b200 import ops
 
 
 def query_topk(node, x, M, k):
