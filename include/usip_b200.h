@@ -280,6 +280,14 @@ int usip_head_bwd(const float* g_kp, const float* g_sig, const float* out4, int 
 int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale, const float* in_shift,
                int in_relu, float* gW, int ldw, int P, int Cout, int Cin, int precision, void* stream);
 
+/* ---- parameter update (replaces torch.optim.Adam at models/keypoint_detector.py:42-45,207; keypoint_descriptor.py:32-35) ----
+ * Adam(betas, eps, weight_decay 0) over flat fp32 buffers of n elements (n % 4 == 0, 16-byte aligned).  `lr_dev` (1 float)
+ * and `step_dev` (1 int64, steps taken so far; incremented by the kernel) live in device memory so the launch can be part
+ * of a CUDA graph; `arrive` is a zero-initialised uint32 scratch word.  g is multiplied by grad_scale first (1/world for a
+ * summed data-parallel gradient). */
+int usip_adam_step(float* p, const float* g, float* m, float* v, const float* lr_dev, int64_t* step_dev, uint32_t* arrive,
+                   float beta1, float beta2, float eps, float grad_scale, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,11 +11,22 @@ import torch.distributed as dist
 
 
 class FlatGradAllReduce:
+    """`params` is either an iterable of parameters (a flat gradient buffer is built here) or a usip_b200.optim.FlatAdam,
+    whose flat parameter / gradient / moment buffers are used as they are (one broadcast each, one all-reduce per step)."""
+
     def __init__(self, params, process_group=None, broadcast_from=0, buffers=()):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = process_group if process_group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
+        self.avg_op = dist.get_backend(self.group) == "nccl"          # ncclAvg: sum and 1/world in the one collective
+        if hasattr(params, "flat_g") and hasattr(params, "flat_p"):  # FlatAdam
+            opt = params
+            self.params = list(opt._params)
+            self.flat = opt.flat_g
+            for t in [opt.flat_p, opt.exp_avg, opt.exp_avg_sq, opt.step_dev] + list(buffers):
+                dist.broadcast(t.data, src=broadcast_from, group=self.group)
+            return
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -34,8 +45,11 @@ class FlatGradAllReduce:
         self.flat.zero_()
 
     def allreduce_mean(self):
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / self.world)
+        if self.avg_op:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)
 
     def check_views(self):
         """True iff every .grad still aliases the flat buffer (guards against zero_grad(set_to_none=True))."""

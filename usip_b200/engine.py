@@ -14,7 +14,7 @@ All arithmetic happens in libusip_b200.so; torch only owns memory / streams / au
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 
 f32 = torch.float32
 i32 = torch.int32
@@ -84,7 +84,7 @@ def _tc_workspace(W, P, Cin, Cout, group, transposed):
         return torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device), False
     cache = owner.__dict__.setdefault("_usip_tc", {})  # lives and dies with the Parameter object
     key = (W.data_ptr() - owner.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32)
-    ver = owner._version
+    ver = (owner._version, _lib.WEIGHT_GEN[0])
     ent = cache.get(key)
     if ent is not None and ent[0] == ver and ent[2] == owner.data_ptr():
         return ent[1], True
@@ -332,7 +332,25 @@ class _Bwd:
         self.check = _lib.check
         self.dev = dev
         self.use_tc = use_tc
-        self.grads = {p: torch.zeros_like(p, memory_format=torch.contiguous_format) for p in net.parameters()}
+        params = list(net.parameters())
+        # usip_b200.optim.FlatAdam publishes a view of its flat gradient buffer on every parameter: accumulate straight
+        # into it (autograd's own semantics for an existing .grad) and hand autograd nothing to add.  Without it (a
+        # caller's own optimizer) the gradients are fresh tensors returned through autograd.
+        self.direct = all(getattr(p, "_usip_flat_grad", None) is not None for p in params)
+        if self.direct:
+            for p in params:
+                if p.grad is None or p.grad.data_ptr() != p._usip_flat_grad.data_ptr():   # module.zero_grad(set_to_none=True)
+                    p._usip_flat_grad.zero_()
+                    p.grad = p._usip_flat_grad
+            self.grads = {p: p._usip_flat_grad for p in params}
+        else:
+            self.grads = {p: torch.zeros_like(p, memory_format=torch.contiguous_format) for p in params}
+
+    def result(self, net):
+        """What the autograd Function returns for the parameters."""
+        if self.direct:
+            return [None for _ in net.parameters()]
+        return [self.grads[q] for q in net.parameters()]
 
     def g2d(self, w):
         g = self.grads[w]
@@ -349,7 +367,7 @@ class _Bwd:
             self.check(self.lib.usip_bn_bwd_reduce(p(G), G.stride(0), p(Y), Y.stride(0), p(st.scale), p(st.shift), p(st.mean),
                                                    p(st.invstd), 1 if relu else 0, p(part), P, C, s), "usip_bn_bwd_reduce")
             self.check(self.lib.usip_bn_bwd_finalize(p(part), nt, P, C, p(self.grads[norm.weight]), p(self.grads[norm.bias]),
-                                                     p(c1), p(c2), 0, s), "usip_bn_bwd_finalize")
+                                                     p(c1), p(c2), 1, s), "usip_bn_bwd_finalize")
             self.check(self.lib.usip_bn_bwd_apply(p(G), G.stride(0), p(Y), Y.stride(0), p(st.scale), p(st.shift), p(st.mean),
                                                   p(st.invstd), p(c1), p(c2), 1 if relu else 0, p(GY), GY.stride(0), P, C, s),
                        "usip_bn_bwd_apply")
@@ -427,7 +445,7 @@ def detector_backward(net, ctx, g_kp, g_sig):
     gz9, arg9, part9, nt9 = groupmax_select(G_feat, ctx["grp_a"], bna_last, Q, C2, True)
     c1 = torch.empty(C2, dtype=f32, device=dev); c2 = torch.empty(C2, dtype=f32, device=dev)
     check(lib.usip_bn_bwd_finalize(p(part9), nt9, G, C2, p(bw.grads[ka[-1].norm.weight]), p(bw.grads[ka[-1].norm.bias]),
-                                   p(c1), p(c2), 0, s()), "usip_bn_bwd_finalize")
+                                   p(c1), p(c2), 1, s()), "usip_bn_bwd_finalize")
     GYa = torch.empty((G, C2), dtype=f32, device=dev)
     with _Prof("groupmax_bwd_apply", nbytes=8.0 * G * C2):
         check(lib.usip_groupmax_bwd_apply(p(Ya_last), Ya_last.stride(0), p(gz9), p(arg9), p(bna_last.scale), p(bna_last.mean),
@@ -519,7 +537,7 @@ def detector_backward(net, ctx, g_kp, g_sig):
     bw.wgrad(GY0, ctx["X0"], bw.g2d(fp[0].conv.weight), P, H, W0.shape[1], name="wgrad_pn1.0")
     # conv biases in front of a train-mode BatchNorm receive exactly zero gradient (BN removes the mean); they
     # stay zero-initialised in bw.grads.
-    return [bw.grads[q] for q in net.parameters()]
+    return bw.result(net)
 
 
 def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):
@@ -629,4 +647,4 @@ def descriptor_backward(net, ctx, g_desc):
     W1 = _w2d(c1.conv.weight)
     bw.wgrad(GY1, ctx["rows"], bw.g2d(c1.conv.weight), G, W1.shape[0], W1.shape[1], name="wgrad_desc.conv1")
     # conv1..conv4 biases sit in front of a train-mode BatchNorm: exactly zero gradient (left zero-initialised)
-    return [bw.grads[q] for q in net.parameters()]
+    return bw.result(net)

@@ -8,6 +8,8 @@ from collections import OrderedDict
 
 import torch
 
+from usip_b200.optim import FlatAdam
+
 from . import losses, networks
 from ._common import random_point_dropout
 
@@ -20,8 +22,8 @@ class ModelDescriptor():
         self.descriptor = networks.DescriptorLiteOld(opt).to(opt.device)
         self.triplet_criteria = losses.DescPairScanLoss(opt)
         self.old_lr_descriptor = self.opt.lr
-        self.optimizer_descriptor = torch.optim.Adam(self.descriptor.parameters(), lr=self.old_lr_descriptor,
-                                                     betas=(0.9, 0.999), weight_decay=0)
+        self.optimizer_descriptor = FlatAdam(self.descriptor.parameters(), lr=self.old_lr_descriptor,
+                                             betas=(0.9, 0.999), weight_decay=0)        # keypoint_descriptor.py:32-35
         dev = opt.device
         B, N, M = opt.batch_size, opt.input_pc_num, opt.node_num
         self.anc_pc = torch.empty(B, 3, N, device=dev).uniform_(); self.anc_sn = torch.empty(B, 3, N, device=dev).uniform_()
@@ -68,7 +70,7 @@ class ModelDescriptor():
             (self.anc_descriptors, self.pos_descriptors), _ = self.forward_siamese(
                 (self.anc_pc, self.pos_pc), (self.anc_sn, self.pos_sn), (self.anc_keypoints, self.pos_keypoints),
                 is_train=True, epoch=epoch)
-            self.descriptor.zero_grad()
+            self.optimizer_descriptor.zero_grad()
             self._loss()
             self.loss.backward()
             self.optimizer_descriptor.step()

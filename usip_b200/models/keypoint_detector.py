@@ -13,6 +13,9 @@ from collections import OrderedDict
 
 import torch
 
+from usip_b200 import _lib, engine
+from usip_b200.optim import FlatAdam
+
 from . import losses, networks
 from ._common import random_point_dropout
 
@@ -32,10 +35,12 @@ class ModelDetector():
         self.detector = self.detector.to(self.opt.device)
 
         self.old_lr_detector = self.opt.lr
-        self.optimizer_detector = torch.optim.Adam(self.detector.parameters(), lr=self.old_lr_detector,
-                                                   betas=(0.9, 0.999), weight_decay=0)
+        # Adam(lr, betas=(0.9, 0.999), weight_decay=0) as in keypoint_detector.py:42-45, as ONE kernel over flat buffers
+        self.optimizer_detector = FlatAdam(self.detector.parameters(), lr=self.old_lr_detector, betas=(0.9, 0.999),
+                                           weight_decay=0)
         self._dp = None
-        self._flat_grad = None
+        self.use_cuda_graph = bool(getattr(opt, "use_cuda_graph", True))
+        self._train_graph_key = None
 
         dev = self.opt.device
         B, N, M = self.opt.batch_size, self.opt.input_pc_num, self.opt.node_num
@@ -60,8 +65,8 @@ class ModelDetector():
     def enable_data_parallel(self, process_group=None):
         """Switch on the gradient all-reduce.  Call after torch.distributed.init_process_group."""
         from usip_b200.dp import FlatGradAllReduce
-        self._dp = FlatGradAllReduce(self.detector.parameters(), process_group, buffers=list(self.detector.buffers()))
-        self._flat_grad = self._dp.flat
+        self._dp = FlatGradAllReduce(self.optimizer_detector, process_group, buffers=list(self.detector.buffers()))
+        self._train_graph_key = None
 
     def _allreduce_grads(self):
         if self._dp is not None:
@@ -146,19 +151,84 @@ class ModelDetector():
                                                                             is_train=is_train, epoch=epoch)
 
     def optimize(self, epoch=None):
-        with torch.cuda.device(self.src_pc.get_device()):
+        """keypoint_detector.py:158-207: (optional point dropout,) train-mode siamese forward, the three losses, backward,
+        (gradient all-reduce when data parallel,) Adam.  With `opt.use_cuda_graph` (default) and no point dropout the
+        whole step -- ~200 kernel launches, the NCCL all-reduce included -- is captured once per input shape and replayed
+        as ONE CUDA graph; results land in the same public attributes."""
+        with torch.cuda.device(self.src_pc.device):
             self.src_pc, self.src_sn, self.dst_pc, self.dst_sn = random_point_dropout(
                 self.opt, self.src_pc, self.src_sn, self.dst_pc, self.dst_sn)
             self.detector.train()
-            self._run_siamese(is_train=True, epoch=epoch)
-            if self._flat_grad is not None:
-                self._flat_grad.zero_()
+            if self.use_cuda_graph and self.opt.random_pc_dropout_lower_limit >= 0.99 and self._train_graph_key != "failed":
+                self._optimize_graph(epoch)
             else:
-                self.detector.zero_grad()
-            self._losses()
-            self.loss.backward()
-            self._allreduce_grads()
-            self.optimizer_detector.step()
+                self._optimize_eager(epoch)
+
+    def _optimize_eager(self, epoch):
+        self._run_siamese(is_train=True, epoch=epoch)
+        self.optimizer_detector.zero_grad()
+        self._losses()
+        self.loss.backward()
+        self._allreduce_grads()
+        self.optimizer_detector.step()
+
+    def _optimize_graph(self, epoch):
+        ins = [getattr(self, k) for k in self._GRAPH_INPUTS]
+        decays = any(getattr(m, "momentum_decay_step", None) for m in self.detector.modules())
+        key = (tuple(tuple(t.shape) for t in ins), (None if epoch is None else int(epoch)) if decays else None,
+               self._dp is not None, tuple(p.requires_grad for p in self.detector.parameters()))
+        if self._train_graph_key != key:
+            try:
+                self._capture_train_step(key, ins, epoch)
+            except Exception as e:                       # e.g. a collective that cannot be captured: keep training eagerly
+                import warnings
+                warnings.warn("usip_b200: CUDA-graph capture of the train step failed (%s: %s); running eagerly"
+                              % (type(e).__name__, e))
+                self._train_graph_key = "failed"
+                torch.cuda.synchronize()
+                for k, v in zip(self._GRAPH_INPUTS, ins):
+                    setattr(self, k, v)
+                return self._optimize_eager(epoch)
+        self.optimizer_detector.sync_hyperparams()        # lr lives in device memory; mirror it outside the graph
+        for dst, src in zip(self._tgraph_in, ins):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._tgraph.replay()
+        _lib.LAUNCHES[0] += self._tgraph_launches
+        _lib.WEIGHT_GEN[0] += 1                           # the replay moved the weights: packed tiles cached by eager paths are stale
+        for k, v in zip(self._GRAPH_INPUTS, self._tgraph_in):
+            setattr(self, k, v)
+        for k, v in self._tgraph_out.items():
+            setattr(self, k, v)
+
+    def _capture_train_step(self, key, ins, epoch):
+        opt_ = self.optimizer_detector
+        self._tgraph_in = [t.clone() for t in ins]
+        for k, v in zip(self._GRAPH_INPUTS, self._tgraph_in):
+            setattr(self, k, v)
+        # warm-up steps (allocator, kernel attributes) must not count as training: parameters, Adam state, the step
+        # counter and the BatchNorm buffers are restored afterwards
+        saved = [(t, t.detach().clone()) for t in [opt_.flat_p, opt_.exp_avg, opt_.exp_avg_sq, opt_.step_dev]
+                 + list(self.detector.buffers())]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._optimize_eager(epoch)
+            with torch.no_grad():
+                for t, v in saved:
+                    t.copy_(v)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        _lib.WEIGHT_GEN[0] += 1                           # the capture must contain the weight (re-)packing kernels
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES[0]
+        with torch.cuda.graph(g):
+            self._optimize_eager(epoch)
+        self._tgraph_launches = _lib.LAUNCHES[0] - n0
+        self._tgraph = g
+        self._tgraph_out = {k: getattr(self, k) for k in self._GRAPH_OUTPUTS}
+        self._train_graph_key = key
 
     def test_model(self):
         self.detector.eval()
@@ -190,14 +260,13 @@ class ModelDetector():
             return self.loss
         ins = [getattr(self, k) for k in self._GRAPH_INPUTS]
         key = (tuple(tuple(t.shape) for t in ins), bool(train_bn), epoch if epoch is None else int(epoch),
-               tuple(p._version for p in self.detector.parameters()))
+               tuple(p._version for p in self.detector.parameters()), _lib.WEIGHT_GEN[0])
         if getattr(self, "_graph_key", None) != key:
             self._capture_forward_loss(key, ins, epoch, train_bn)
         for dst, src in zip(self._graph_in, ins):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
-        from usip_b200 import _lib
         _lib.LAUNCHES[0] += self._graph_launches
         for k, v in zip(self._GRAPH_INPUTS, self._graph_in):
             setattr(self, k, v)
@@ -206,7 +275,6 @@ class ModelDetector():
         return self.loss
 
     def _capture_forward_loss(self, key, ins, epoch, train_bn):
-        from usip_b200 import _lib
         self._graph_in = [t.clone() for t in ins]
         for k, v in zip(self._GRAPH_INPUTS, self._graph_in):
             setattr(self, k, v)
@@ -232,7 +300,7 @@ class ModelDetector():
         self._graph = g
         self._graph_out = {k: getattr(self, k) for k in self._GRAPH_OUTPUTS}
         # the parameter versions may have been bumped by nothing here; recompute the key with the live versions
-        self._graph_key = (key[0], key[1], key[2], tuple(p._version for p in self.detector.parameters()))
+        self._graph_key = (key[0], key[1], key[2], tuple(p._version for p in self.detector.parameters()), _lib.WEIGHT_GEN[0])
 
     def freeze_model(self):
         for p in self.detector.parameters():
