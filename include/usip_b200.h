@@ -49,12 +49,17 @@ int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
  *   out_idx (B,M,K) i32      (bit-identical to ball_query on torch.norm(centers-xyz))
  *   out_group (B,3+S,M,K) f32 = x_aug gathered, xyz channels minus the centre  (`x_features`) (or NULL)
  *   out_rows  [B*M*K, ld_rows] f32: the same group as point-major rows for the MLP stack (or NULL)
- * scratch: usip_ball_group_scratch_bytes() bytes, 256-byte aligned (cell table, cell-sorted 32-byte records); without it
- * (or for S > 4) the brute-force single-kernel path runs. */
+ * scratch: usip_ball_group_scratch_bytes() bytes, 256-byte aligned (per cloud: bucket fill counts, 2-D bucket grid of
+ * 32-byte records, overflow list).  CONTRACT: its counter region must be all-zero when the call starts -- clear it ONCE with
+ * usip_ball_group_scratch_init() -- and every call leaves it all-zero again (the last CTA of each cloud restores it), so a
+ * scratch buffer that is kept between calls costs no memset launch.  One scratch per stream.  Without scratch (or for
+ * S > 4) the reference's in-order scan runs as a single kernel.  Two launches (build, query) chained by programmatic
+ * dependent launch; the query stages its candidate buckets with cp.async.bulk (TMA) into shared memory. */
 int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
                         int32_t* out_idx, float* out_group, float* out_rows, int ld_rows,
                         void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
+int usip_ball_group_scratch_init(void* scratch, int64_t scratch_bytes, int B, void* stream);
 
 /* Farthest point sampling of the SOM nodes          data/kitti_detector_loader.py:68-83 (FarthestSampler.sample), :144-145
  * pts (B, Ns, 3) f32 row-major (the numpy subset the reference samples from), start (B,) i32 = index of the first node
