@@ -61,6 +61,13 @@ int usip_ball_group_f32(const float* xyz, const float* feat, const float* center
 int64_t usip_ball_group_scratch_bytes(int B, int S, int N, int M, int K);
 int usip_ball_group_scratch_init(void* scratch, int64_t scratch_bytes, int B, void* stream);
 
+/* k-nearest-POINT grouping of the ablation detector RPN_Detector_KNN      models/networks.py:556-565
+ * (torch.norm + topk(k, largest=False, sorted=False) + gather + subtract the node), without the (B,M,N) matrix.
+ * out_idx (B,M,K) i32: the K points nearest to each centre, EXACT, in ascending point index (the reference's order is
+ * unspecified; ties at the K-th distance: lowest index first); out_group / out_rows as in usip_ball_group_f32.  K <= N. */
+int usip_knn_group_f32(const float* xyz, const float* feat, const float* centers, int32_t* out_idx, float* out_group,
+                       float* out_rows, int ld_rows, int B, int S, int N, int M, int K, void* stream);
+
 /* Farthest point sampling of the SOM nodes          data/kitti_detector_loader.py:68-83 (FarthestSampler.sample), :144-145
  * pts (B, Ns, 3) f32 row-major (the numpy subset the reference samples from), start (B,) i32 = index of the first node
  * (the reference draws it with np.random.randint) -> out_idx (B, k) i32 in selection order, out_nodes (B, 3, k) f32 (or

@@ -201,6 +201,31 @@ def softplus(x):
     return np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20))))
 
 
+def knn_fusion_head(P, coords, feat, K, sigma_lower_bound, kw, dtype=np.float32):
+    """GeneralKNNFusionModule on the nodes (models/layers.py:401-440) + head mlp1/2/3 + softplus (models/networks.py:143-154).
+    coords (B,3,M): the nodes the kNN runs on / the keypoint offsets are added to; feat (B,C1,M): per-node feature."""
+    B, _, M = coords.shape
+    knn_i, _ = knn(coords, coords, K)                                       # layers.py:417-421
+    ki = knn_i.astype(np.int64).reshape(B, 1, M * K)
+    nb_xyz = np.take_along_axis(coords, np.broadcast_to(ki, (B, 3, M * K)), axis=2).reshape(B, 3, M, K)
+    nb_feat = np.take_along_axis(feat, np.broadcast_to(ki, (B, feat.shape[1], M * K)), axis=2).reshape(B, -1, M, K)
+    g = np.concatenate([nb_xyz - coords[:, :, :, None], nb_feat], axis=1)   # :428-429
+    for i in range(3):
+        g = layer(g, P, "knnlayer_1.layers_before.%d" % i, **kw)
+    gmax = g.max(axis=3, keepdims=True)
+    y = np.concatenate([np.broadcast_to(gmax, g.shape), g], axis=1)         # :435 (max first)
+    for i in range(2):
+        y = layer(y, P, "knnlayer_1.layers_after.%d" % i, **kw)
+    knn_feat = y.max(axis=3)                                                # :438
+    agg = np.concatenate([feat, knn_feat], axis=1)                          # networks.py:143
+    y1 = layer(agg, P, "mlp1", **kw)
+    y2 = layer(y1, P, "mlp2", **kw)
+    out = layer(y2, P, "mlp3", bn=False, relu=False, **kw)
+    keypoints = out[:, 0:3, :] + coords                                     # :151
+    sigmas = softplus(out[:, 3, :]) + dtype(sigma_lower_bound)              # :154
+    return keypoints, sigmas, knn_i, knn_feat, out
+
+
 # ----------------------------------------------------------------------------- detector forward
 def detector_forward(P, x, sn, node, node_knn_k=16, sigma_lower_bound=1e-3, training=False,
                      momentum=0.1, dtype=np.float32, return_intermediates=False):
@@ -234,26 +259,7 @@ def detector_forward(P, x, sn, node, node_knn_k=16, sigma_lower_bound=1e-3, trai
     second = layer(h, P, "second_pointnet.layers.1", bn=False, relu=False, **kw)
     pool2, idx2 = segmented_max(second, min_idx, M)
     pool2 = pool2 * rm                                                      # :130-133
-    # GeneralKNNFusionModule (layers.py:401-440)
-    K = node_knn_k
-    knn_i, _ = knn(cluster_mean, cluster_mean, K)                           # layers.py:417-421
-    ki = knn_i.astype(np.int64).reshape(B, 1, M * K)
-    nb_xyz = np.take_along_axis(cluster_mean, np.broadcast_to(ki, (B, 3, M * K)), axis=2).reshape(B, 3, M, K)
-    nb_feat = np.take_along_axis(pool2, np.broadcast_to(ki, (B, pool2.shape[1], M * K)), axis=2).reshape(B, -1, M, K)
-    g = np.concatenate([nb_xyz - cluster_mean[:, :, :, None], nb_feat], axis=1)      # :428-429
-    for i in range(3):
-        g = layer(g, P, "knnlayer_1.layers_before.%d" % i, **kw)
-    gmax = g.max(axis=3, keepdims=True)
-    y = np.concatenate([np.broadcast_to(gmax, g.shape), g], axis=1)         # :435 (max first)
-    for i in range(2):
-        y = layer(y, P, "knnlayer_1.layers_after.%d" % i, **kw)
-    knn_feat = y.max(axis=3)                                                # :438
-    agg = np.concatenate([pool2, knn_feat], axis=1)                         # networks.py:143
-    y1 = layer(agg, P, "mlp1", **kw)
-    y2 = layer(y1, P, "mlp2", **kw)
-    out = layer(y2, P, "mlp3", bn=False, relu=False, **kw)
-    keypoints = out[:, 0:3, :] + cluster_mean                               # :151
-    sigmas = softplus(out[:, 3, :]) + dtype(sigma_lower_bound)              # :154
+    keypoints, sigmas, knn_i, knn_feat, out = knn_fusion_head(P, cluster_mean, pool2, node_knn_k, sigma_lower_bound, kw, dtype)
     res = dict(node_recomputed=cluster_mean, keypoints=keypoints.astype(np.float32),
                sigmas=sigmas.astype(np.float32), min_idx=min_idx, mask_row_max=row_max,
                new_stats=new_stats)
@@ -261,6 +267,50 @@ def detector_forward(P, x, sn, node, node_knn_k=16, sigma_lower_bound=1e-3, trai
         res.update(x_aug=x_aug, first_pn_out=first, idx1=idx1, pool1=pool1, second_pn_out=second, idx2=idx2,
                    pool2=pool2, knn_i=knn_i, knn_feat=knn_feat, head_out=out)
     return res
+
+
+# ----------------------------------------------------------------------------- ablation detectors
+def ablation_forward(P, x, sn, node, mode="knn", node_knn_k=16, sigma_lower_bound=1e-3, training=False, momentum=0.1,
+                     dtype=np.float32):
+    """RPN_Detector_KNN.forward (models/networks.py:545-608, mode="knn": the 64 points nearest to each node, :556-559) /
+    RPN_Detector_Ball.forward (:671-738, mode="ball": ball_query radius 2, k = 64, :681-690).  The nodes are used as given."""
+    x = x.astype(dtype); node = node.astype(dtype)
+    B, _, N = x.shape; M = node.shape[2]; k = 64
+    S = 0 if sn is None else sn.shape[1]
+    x_aug = np.concatenate([x, sn.astype(dtype)], axis=1) if S >= 1 else x
+    if mode == "knn":
+        idx, _ = knn(node, x, k)                                            # any order: only max / BN over k follow
+    else:
+        idx = ball_query_xyz(x, node, 2.0, k)
+    C = x_aug.shape[1]
+    gi = np.broadcast_to(idx.astype(np.int64).reshape(B, 1, M * k), (B, C, M * k))
+    grp = np.take_along_axis(x_aug, gi, axis=2).reshape(B, C, M, k).copy()
+    grp[:, 0:3] -= node[:, :, :, None]                                      # :565 / :692
+    new_stats = {} if training else None
+    kw = dict(training=training, momentum=momentum, new_stats=new_stats)
+    y = layer(grp, P, "conv1", **kw); y = layer(y, P, "conv2", **kw); first = layer(y, P, "conv3", **kw)
+    fmax = np.broadcast_to(first.max(axis=3, keepdims=True), first.shape)
+    y = layer(np.concatenate([first, fmax], axis=1), P, "conv4", **kw)      # :571 (per-sample first, max last)
+    second = layer(y, P, "conv5", **kw)
+    second_max = second.max(axis=3)                                         # :572
+    keypoints, sigmas, knn_i, knn_feat, out = knn_fusion_head(P, node, second_max, node_knn_k, sigma_lower_bound, kw, dtype)
+    return dict(keypoints=keypoints.astype(np.float32), sigmas=sigmas.astype(np.float32), group_idx=idx, new_stats=new_stats)
+
+
+def ablation_param_shapes(S=4, C1=128, C2=512):
+    """RPN_Detector_KNN / RPN_Detector_Ball state_dict layout (models/networks.py:483-543): name -> (shape, has_bn)."""
+    h = C1 // 2
+    return [("conv1", (h, 3 + S, 1, 1), True), ("conv2", (h, h, 1, 1), True), ("conv3", (h, h, 1, 1), True),
+            ("conv4", (C1, C1, 1, 1), True), ("conv5", (C1, C1, 1, 1), True),
+            ("knnlayer_1.layers_before.0", (C2 // 2, 3 + C1, 1, 1), True),
+            ("knnlayer_1.layers_before.1", (C2 // 2, C2 // 2, 1, 1), True),
+            ("knnlayer_1.layers_before.2", (C2 // 2, C2 // 2, 1, 1), True),
+            ("knnlayer_1.layers_after.0", (C2, C2, 1, 1), True), ("knnlayer_1.layers_after.1", (C2, C2, 1, 1), True),
+            ("mlp1", (512, C1 + C2, 1), True), ("mlp2", (256, 512, 1), True), ("mlp3", (4, 256, 1), False)]
+
+
+def init_ablation_params(S=4, seed=0, randomize_bn=True):
+    return _init_params(ablation_param_shapes(S), seed, randomize_bn)
 
 
 # ----------------------------------------------------------------------------- losses
@@ -438,9 +488,13 @@ def init_detector_params(S=4, seed=0, C1=128, C2=512, randomize_bn=False):
     """Random init following models/layers.py:196-205,278-287 and networks.py:70-71 (numpy RNG, so
     not bit-identical to torch's init -- used for synthetic benchmarks/tests where both sides get
     the same arrays)."""
+    return _init_params(detector_param_shapes(S, C1, C2), seed, randomize_bn)
+
+
+def _init_params(spec, seed, randomize_bn):
     rng = np.random.default_rng(seed)
     P = {}
-    for name, shp, bn in detector_param_shapes(S, C1, C2):
+    for name, shp, bn in spec:
         fan_in = int(np.prod(shp[1:]))
         std = 1e-4 if name == "mlp3" else np.sqrt(2.0 / fan_in)
         P[name + ".conv.weight"] = rng.normal(0, std, shp).astype(np.float32)
@@ -453,7 +507,7 @@ def init_detector_params(S=4, seed=0, C1=128, C2=512, randomize_bn=False):
             P[name + ".norm.running_var"] = (rng.uniform(0.5, 1.5, C) if randomize_bn else np.ones(C)).astype(np.float32)
             P[name + ".norm.num_batches_tracked"] = np.zeros((), np.int64)
     if randomize_bn:
-        for name, shp, bn in detector_param_shapes(S, C1, C2):
+        for name, shp, bn in spec:
             P[name + ".conv.bias"] = rng.normal(0, 0.05, shp[0]).astype(np.float32)
     return P
 
@@ -475,3 +529,13 @@ def desc_train_inputs(B, N, M, S, seed):
                 pos_pc=pos_pc, pos_sn=d["dst_sn"], pos_kp=pos_kp.astype(np.float32),
                 pos_sigma=rng.uniform(0, 4, (B, M)).astype(np.float32),
                 neg_idx=((np.arange(B) + 1) % B).astype(np.int64))
+
+
+def ablation_inputs(seed, B=2, N=2048, M=32, S=4):
+    """Inputs of the ablation-detector fixtures (regenerated from the seed by the consumers): a LiDAR-like cloud shrunk in
+    x/z so that balls of radius 2 hold a few .. more than 64 points, FPS nodes, fixed loss weights."""
+    d = synth_pair(B, N, M, S, kind="lidar", seed=seed)
+    sc = np.array([0.35, 1.0, 0.35], np.float32).reshape(1, 3, 1)
+    rng = np.random.default_rng(seed + 7)
+    return dict(pc=(d["src_pc"] * sc).astype(np.float32), sn=d["src_sn"], node=(d["src_node"] * sc).astype(np.float32),
+                w_kp=rng.normal(size=(B, 3, M)).astype(np.float32), w_sig=rng.normal(size=(B, M)).astype(np.float32))

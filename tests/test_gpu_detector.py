@@ -354,3 +354,77 @@ def test_full_size_baseline_configs(name, B, N, M, S, Kn, kind, lb, alpha):
         torch.cuda.empty_cache()
     assert rel_err(res[True][0], res[False][0]) < REL and rel_err(res[True][1], res[False][1]) < REL
     assert abs(res[True][2] - res[False][2]) <= REL * abs(res[False][2])
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("mode", ["knn", "ball"])
+def test_ablation_detectors_vs_reference_golden(mode, use_tc):
+    """RPN_Detector_KNN / RPN_Detector_Ball (networks.py:482-738) against outputs of the reference's own classes:
+    eval and train forward, every parameter gradient of L = sum(w_kp*kp) + sum(w_sig*sigma), running statistics."""
+    from usip_b200.models import networks
+    g = golden("detector_ablation.npz")
+    B, N, M, S, Kn, seed = [int(v) for v in g["cfg"]]
+    d = orc.ablation_inputs(seed, B, N, M, S)
+    P = orc.init_ablation_params(S=S, seed=seed, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    opt = make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn, use_tensor_cores=use_tc)
+    net = (networks.RPN_Detector_KNN if mode == "knn" else networks.RPN_Detector_Ball)(opt).to(dev())
+    load_params(net, P)
+    pc, sn, node = cu(d["pc"]), cu(d["sn"]), cu(d["node"])
+    net.eval()
+    with torch.no_grad():
+        node_o, kp, sig, desc = net(pc, sn, node, False, None)
+    assert desc is None and torch.equal(node_o, node)
+    assert rel_err(kp.cpu().numpy(), g[mode + "/eval_kp"]) < REL
+    assert rel_err(sig.cpu().numpy(), g[mode + "/eval_sig"]) < REL
+    net.train()
+    _, kp, sig, _ = net(pc, sn, node, True, 0)
+    loss = (kp * cu(d["w_kp"])).sum() + (sig * cu(d["w_sig"])).sum()
+    net.zero_grad()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(kp.detach().cpu().numpy(), g[mode + "/train_kp"]) < REL
+    assert rel_err(sig.detach().cpu().numpy(), g[mode + "/train_sig"]) < REL
+    assert abs(loss.item() - float(g[mode + "/loss"])) <= 2e-4 * abs(float(g[mode + "/loss"]))
+    for k, p in net.named_parameters():
+        ref = g[mode + "/grad/" + k]
+        gr = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
+        absmax, norm = float(ref[2]), float(ref[3])
+        if k.endswith("conv.bias") and (k.replace("conv.bias", "norm.weight") in dict(net.named_parameters())):
+            assert np.linalg.norm(gr) <= norm + 1e-12, k                # a bias in front of a train-mode BN: true gradient 0
+            continue
+        e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
+        e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
+        assert e_norm < 2e-3 and e_el < 5e-3, (k, e_norm, e_el)
+    sd = net.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            a = sd[k].cpu().numpy().reshape(-1)[:24]
+            assert np.allclose(a, g[mode + "/after/" + k], rtol=2e-4, atol=1e-6), k
+
+
+def test_knn_group_vs_oracle():
+    """usip_knn_group_f32: the K nearest points of every centre, exact, ascending index; gathered rows / group."""
+    from usip_b200 import ops
+    rng = np.random.default_rng(3)
+    B, N, M, K, S = 3, 5000, 40, 64, 4
+    pc = rng.uniform(-5, 5, (B, 3, N)).astype(np.float32)
+    pc[:, :, 100:140] = pc[:, :, 60:100]                              # duplicated points: exact distance ties
+    sn = rng.normal(size=(B, S, N)).astype(np.float32)
+    ctr = np.ascontiguousarray(pc[:, :, :M]) + rng.normal(0, 0.3, (B, 3, M)).astype(np.float32)
+    idx, grp, rows = ops.knn_group(cu(pc), cu(sn), cu(ctr), K, want_group=True, rows_ld=8)
+    idx = idx.cpu().numpy(); grp = grp.cpu().numpy(); rows = rows.cpu().numpy().reshape(B, M, K, 8)
+    ref_i, ref_d = orc.knn(ctr, pc, K)
+    d2 = ((pc[:, :, None, :] - ctr[:, :, :, None]) ** 2)
+    d2 = (d2[:, 0] + d2[:, 1]) + d2[:, 2]                             # fp32, the reference's summation order
+    for b in range(B):
+        for m in range(M):
+            sel = idx[b, m]
+            assert np.all(np.diff(sel) > 0)                           # ascending, distinct
+            kth = np.sort(d2[b, m])[K - 1]
+            assert np.all(d2[b, m, sel] <= kth) and np.sum(d2[b, m] < kth) == np.sum(d2[b, m, sel] < kth)
+    x_aug = np.concatenate([pc, sn], 1)
+    want = np.take_along_axis(x_aug, np.broadcast_to(idx.astype(np.int64).reshape(B, 1, M * K), (B, 3 + S, M * K)), 2).reshape(B, 3 + S, M, K)
+    want[:, :3] -= ctr[:, :, :, None]
+    assert np.array_equal(grp, want)
+    assert np.array_equal(rows[..., :7], want.transpose(0, 2, 3, 1)) and np.all(rows[..., 7] == 0)

@@ -252,6 +252,42 @@ def golden_fps(ref):
     np.savez_compressed(os.path.join(OUT, "fps.npz"), **out)
 
 
+def golden_ablation(ref):
+    """RPN_Detector_KNN / RPN_Detector_Ball (models/networks.py:482-738): eval and train forward, and the gradients of
+    L = sum(w_kp * keypoints) + sum(w_sig * sigmas) (ModelDetector cannot select these networks -- the lines are commented
+    out at keypoint_detector.py:23-24 -- so the fixture drives the networks directly)."""
+    B, N, M, S, Kn, seed = 2, 2048, 32, 4, 16, 1239
+    d = orc.ablation_inputs(seed, B, N, M, S)
+    opt = ref_shim.make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn)
+    P = orc.init_ablation_params(S=S, seed=seed, randomize_bn=True)
+    P["mlp3.conv.weight"] = (P["mlp3.conv.weight"] * 1000).astype(np.float32)
+    out = dict(cfg=np.array([B, N, M, S, Kn, seed], np.int64))
+    for mode, cls in (("knn", ref.networks.RPN_Detector_KNN), ("ball", ref.networks.RPN_Detector_Ball)):
+        torch.manual_seed(seed)
+        net = cls(opt)
+        load_params(net, P)
+        net.eval()
+        with torch.no_grad():
+            node_o, kp, sig, _ = net(t(d["pc"]), t(d["sn"]), t(d["node"]), False, None)
+        assert torch.equal(node_o, t(d["node"]))
+        out[mode + "/eval_kp"] = kp.numpy(); out[mode + "/eval_sig"] = sig.numpy()
+        net.train()
+        _, kp, sig, _ = net(t(d["pc"]), t(d["sn"]), t(d["node"]), True, 0)
+        loss = (kp * t(d["w_kp"])).sum() + (sig * t(d["w_sig"])).sum()
+        net.zero_grad()
+        loss.backward()
+        out[mode + "/train_kp"] = kp.detach().numpy(); out[mode + "/train_sig"] = sig.detach().numpy()
+        out[mode + "/loss"] = np.float32(loss.item())
+        for k, p_ in net.named_parameters():
+            g = p_.grad.detach().numpy().reshape(-1).astype(np.float64)
+            out[mode + "/grad/" + k] = np.concatenate([[g.mean(), g.std(), np.abs(g).max(), np.linalg.norm(g)], g[:24]]).astype(np.float32)
+        for k, v in net.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                out[mode + "/after/" + k] = v.detach().numpy().reshape(-1)[:24].copy()
+        print("ablation", mode, "loss", out[mode + "/loss"])
+    np.savez_compressed(os.path.join(OUT, "detector_ablation.npz"), **out)
+
+
 def _reference_function(relpath, name):
     """The reference's own, unmodified source of one top-level function, executed here (its module cannot be imported:
     evaluation/save_keypoints.py is a script with hard-coded dataset paths and GUI / visdom imports)."""
@@ -288,6 +324,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ref = ref_shim.modules()
+    if len(sys.argv) > 1:                                  # regenerate selected fixtures only, e.g. `make_golden.py ablation`
+        for name in sys.argv[1:]:
+            globals()["golden_" + name](ref)
+        return
     golden_index_max(ref)
     golden_query_topk(ref)
     golden_losses(ref)
@@ -299,6 +339,7 @@ def main():
     golden_descriptor_train(ref)
     golden_fps(ref)
     golden_nms(ref)
+    golden_ablation(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KB")
 

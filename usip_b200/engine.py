@@ -191,64 +191,20 @@ def _bn_mom(norm, epoch):
     return norm.momentum
 
 
-def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
-    """RPN_Detector.forward (models/networks.py:75-162) on the fused plan.
-
-    x (B,3,N), sn (B,S,N), node (B,3,M) CUDA f32 contiguous.  Returns
-    (cluster_mean (B,3,M), keypoints (B,3,M), sigmas (B,M), ctx) -- ctx holds everything backward needs when
-    keep=True."""
+def _knn_head_forward(R, net, AGG, C1, coords, Bp, M, Kn, epoch, keep):
+    """GeneralKNNFusionModule on the nodes (layers.py:401-440) + head mlp1/2/3 + softplus (networks.py:143-154).
+    AGG [Q, C1+C2]: columns [0,C1) hold the per-node feature (pool 2) on entry, columns [C1,C1+C2) receive the fused kNN
+    feature.  coords (B,3,M) are the nodes the kNN runs on and the keypoint offsets are added to.  Shared by RPN_Detector /
+    RPN_DetectorLite (coords = cluster means) and the ablation networks RPN_Detector_KNN / _Ball (coords = the given nodes)."""
     opt = net.opt
-    assert opt.k == 1, "only k=1 is supported (every shipped config; networks.py:91-92)"
-    if keep and not net.training:
-        raise NotImplementedError("gradients through eval-mode BatchNorm are not part of the hot path "
-                                  "(the reference only back-propagates in train mode, keypoint_detector.py:170)")
-    assert len(net.knnlayer_1.layers_before) >= 2 and len(net.knnlayer_1.layers_after) >= 2
-    dev = x.device
-    Bp, _, N = x.shape
-    M = node.shape[2]
-    S = opt.surface_normal_len if opt.surface_normal_len >= 1 else 0
-    Kn = opt.node_knn_k_1
-    P, Q = Bp * N, Bp * M
+    dev = AGG.device
+    Q = Bp * M
     G = Q * Kn
-    training = net.training
-    R = LayerRunner(net, training, use_tc, dev)
-    x = x.detach().contiguous(); node = node.detach().contiguous()
-    snc = sn.detach().contiguous() if S else None
-
-    # ---- grouping (som.query_topk + networks.py:87-108)
-    with _Prof("som_assign", nbytes=4.0 * Bp * (4 * N + 3 * M)):
-        min_idx, count = ops.som_assign(x, node)
-    with _Prof("cluster_sort"):
-        seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
-    with _Prof("cluster_mean_decenter", nbytes=4.0 * Bp * N * (3 + S + 8 + 1)):
-        cmean, X0 = ops.cluster_mean_decenter(x, snc, seg_off, perm, M, ldx=8)
-
-    # ---- first PointNet (3+S -> C1/2 -> C1/2 -> C1/2), networks.py:111-114
-    fp = net.first_pointnet.layers
-    H = fp[0].conv.weight.shape[0]
-    Y0, bn0, _ = R.run(X0, P, _w2d(fp[0].conv.weight), fp[0].conv.bias.detach(), fp[0].norm, _bn_mom(fp[0].norm, epoch), name="pn1.0")
-    Y1, bn1, _ = R.run(Y0, P, _w2d(fp[1].conv.weight), fp[1].conv.bias.detach(), fp[1].norm, _bn_mom(fp[1].norm, epoch), prev=bn0, name="pn1.1")
-    F1, _, _ = R.run(Y1, P, _w2d(fp[2].conv.weight), fp[2].conv.bias.detach(), prev=bn1, name="pn1.2")
-    # ---- pool 1 (index_max + gather * mask, networks.py:117-120)
-    with _Prof("segmax1", nbytes=4.0 * P * H):
-        pool1, arg1 = ops.segmax(F1, H, seg_off, perm, Bp, N, M, want_arg=keep)
-    # ---- second PointNet on cat(first, scattered max) (networks.py:123-127): W [f; s] = Wa f + Wb s
-    sp = net.second_pointnet.layers
-    C1 = sp[0].conv.weight.shape[0]
-    W3 = _w2d(sp[0].conv.weight)
-    V, _, _ = R.run(pool1, Q, _cols(W3, H), None, relu_in=False, name="pn2.0_node")
-    Y3, bn3, _ = R.run(F1, P, _cols(W3, 0, H), sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
-                       relu_in=False, addend=V, add_index=row_seg, name="pn2.0")
-    F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3, name="pn2.1")
-    # ---- pool 2 -> first C1 columns of the head input (networks.py:130-133,143)
     kb = net.knnlayer_1.layers_before
     ka = net.knnlayer_1.layers_after
     C2 = ka[-1].conv.weight.shape[0]
-    AGG = torch.empty((Q, C1 + C2), dtype=f32, device=dev)
     pool2 = AGG[:, :C1]
-    with _Prof("segmax2", nbytes=4.0 * P * C1):
-        _, arg2 = ops.segmax(F2, C1, seg_off, perm, Bp, N, M, out=pool2, want_arg=keep)
-
+    cmean = coords
     # ---- GeneralKNNFusionModule (layers.py:401-440)
     with _Prof("knn_nodes"):
         knn_i = ops.knn_nodes(cmean, Kn)
@@ -301,14 +257,79 @@ def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
     with _Prof("head_finalize"):
         keypoints, sigmas = ops.head_finalize(OUT, cmean, opt.loss_sigma_lower_bound, Bp, M)
 
+    kctx = dict(knn_i=knn_i)
+    if keep:
+        kctx.update(Kn=Kn, C1=C1, C2=C2, Cb=Cb, AGG=AGG, Z=Z, before=saved_before, grp_b=grp_b, amax=amax, U=U,
+                    after=saved_after, grp_a=grp_a, Y10=Y10, bn10=bn10, Y11=Y11, bn11=bn11, OUT=OUT, coords=coords)
+    return keypoints, sigmas, kctx
+
+
+def detector_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False):
+    """RPN_Detector.forward (models/networks.py:75-162) on the fused plan.
+
+    x (B,3,N), sn (B,S,N), node (B,3,M) CUDA f32 contiguous.  Returns
+    (cluster_mean (B,3,M), keypoints (B,3,M), sigmas (B,M), ctx) -- ctx holds everything backward needs when
+    keep=True."""
+    opt = net.opt
+    assert opt.k == 1, "only k=1 is supported (every shipped config; networks.py:91-92)"
+    if keep and not net.training:
+        raise NotImplementedError("gradients through eval-mode BatchNorm are not part of the hot path "
+                                  "(the reference only back-propagates in train mode, keypoint_detector.py:170)")
+    assert len(net.knnlayer_1.layers_before) >= 2 and len(net.knnlayer_1.layers_after) >= 2
+    dev = x.device
+    Bp, _, N = x.shape
+    M = node.shape[2]
+    S = opt.surface_normal_len if opt.surface_normal_len >= 1 else 0
+    Kn = opt.node_knn_k_1
+    P, Q = Bp * N, Bp * M
+    G = Q * Kn
+    training = net.training
+    R = LayerRunner(net, training, use_tc, dev)
+    x = x.detach().contiguous(); node = node.detach().contiguous()
+    snc = sn.detach().contiguous() if S else None
+
+    # ---- grouping (som.query_topk + networks.py:87-108)
+    with _Prof("som_assign", nbytes=4.0 * Bp * (4 * N + 3 * M)):
+        min_idx, count = ops.som_assign(x, node)
+    with _Prof("cluster_sort"):
+        seg_off, perm, row_seg = ops.cluster_sort(min_idx, M)
+    with _Prof("cluster_mean_decenter", nbytes=4.0 * Bp * N * (3 + S + 8 + 1)):
+        cmean, X0 = ops.cluster_mean_decenter(x, snc, seg_off, perm, M, ldx=8)
+
+    # ---- first PointNet (3+S -> C1/2 -> C1/2 -> C1/2), networks.py:111-114
+    fp = net.first_pointnet.layers
+    H = fp[0].conv.weight.shape[0]
+    Y0, bn0, _ = R.run(X0, P, _w2d(fp[0].conv.weight), fp[0].conv.bias.detach(), fp[0].norm, _bn_mom(fp[0].norm, epoch), name="pn1.0")
+    Y1, bn1, _ = R.run(Y0, P, _w2d(fp[1].conv.weight), fp[1].conv.bias.detach(), fp[1].norm, _bn_mom(fp[1].norm, epoch), prev=bn0, name="pn1.1")
+    F1, _, _ = R.run(Y1, P, _w2d(fp[2].conv.weight), fp[2].conv.bias.detach(), prev=bn1, name="pn1.2")
+    # ---- pool 1 (index_max + gather * mask, networks.py:117-120)
+    with _Prof("segmax1", nbytes=4.0 * P * H):
+        pool1, arg1 = ops.segmax(F1, H, seg_off, perm, Bp, N, M, want_arg=keep)
+    # ---- second PointNet on cat(first, scattered max) (networks.py:123-127): W [f; s] = Wa f + Wb s
+    sp = net.second_pointnet.layers
+    C1 = sp[0].conv.weight.shape[0]
+    W3 = _w2d(sp[0].conv.weight)
+    V, _, _ = R.run(pool1, Q, _cols(W3, H), None, relu_in=False, name="pn2.0_node")
+    Y3, bn3, _ = R.run(F1, P, _cols(W3, 0, H), sp[0].conv.bias.detach(), sp[0].norm, _bn_mom(sp[0].norm, epoch),
+                       relu_in=False, addend=V, add_index=row_seg, name="pn2.0")
+    F2, _, _ = R.run(Y3, P, _w2d(sp[1].conv.weight), sp[1].conv.bias.detach(), prev=bn3, name="pn2.1")
+    # ---- pool 2 -> first C1 columns of the head input (networks.py:130-133,143)
+    C2 = net.knnlayer_1.layers_after[-1].conv.weight.shape[0]
+    AGG = torch.empty((Q, C1 + C2), dtype=f32, device=dev)
+    pool2 = AGG[:, :C1]
+    with _Prof("segmax2", nbytes=4.0 * P * C1):
+        _, arg2 = ops.segmax(F2, C1, seg_off, perm, Bp, N, M, out=pool2, want_arg=keep)
+
+    keypoints, sigmas, kctx = _knn_head_forward(R, net, AGG, C1, cmean, Bp, M, Kn, epoch, keep)
+    knn_i = kctx["knn_i"]
+
     ctx = None
     if keep:
-        ctx = dict(Bp=Bp, N=N, M=M, S=S, Kn=Kn, H=H, C1=C1, C2=C2, Cb=Cb,
+        ctx = dict(kctx)
+        ctx.update(Bp=Bp, N=N, M=M, S=S, H=H,
                    seg_off=seg_off, perm=perm, row_seg=row_seg, min_idx=min_idx, count=count, cmean=cmean,
                    X0=X0, Y0=Y0, bn0=bn0, Y1=Y1, bn1=bn1, F1=F1, pool1=pool1, arg1=arg1, V=V,
-                   Y3=Y3, bn3=bn3, F2=F2, arg2=arg2, AGG=AGG, knn_i=knn_i, Z=Z,
-                   before=saved_before, grp_b=grp_b, amax=amax, U=U, after=saved_after, grp_a=grp_a,
-                   Y10=Y10, bn10=bn10, Y11=Y11, bn11=bn11, OUT=OUT, use_tc=use_tc)
+                   Y3=Y3, bn3=bn3, F2=F2, arg2=arg2, use_tc=use_tc)
     aux = dict(min_idx=min_idx, count=count, perm=perm, seg_off=seg_off, knn_i=knn_i)
     return cmean, keypoints, sigmas, ctx, aux
 
@@ -373,6 +394,33 @@ class _Bwd:
                        "usip_bn_bwd_apply")
         return GY
 
+    def groupmax_select(self, Gout, grp, st, Qn, C, with_stats):
+        """Gradient of out = max_k relu(bn(y_k)) at the selected row of each group: gz [Qn,C] (ReLU-masked), argsel [Qn,C]
+        and, with_stats, the BN-backward partial sums over the selected entries."""
+        p, s = ops._p, ops._stream
+        gz = torch.empty((Qn, C), dtype=f32, device=self.dev)
+        argsel = torch.empty((Qn, C), dtype=i32, device=self.dev)
+        nt = (Qn + 127) // 128
+        part = torch.empty((nt, 2, C), dtype=f32, device=self.dev) if with_stats else None
+        self.check(self.lib.usip_groupmax_bwd_select(p(Gout), Gout.stride(0), p(grp["gmax"]), p(grp["gmin"]), p(grp["amax"]),
+                                                     p(grp["amin"]), p(st.scale), p(st.shift), p(st.mean), p(st.invstd), p(gz),
+                                                     p(argsel), p(part), Qn, C, s()), "usip_groupmax_bwd_select")
+        return gz, argsel, part, nt
+
+    def groupmax_bn_bwd(self, Gout, Y, grp, st, norm, K, Q, C):
+        """g_y [Q*K, C] of a layer whose ONLY consumer is max_k relu(bn(y)) (layers.py:433,438; networks.py:572,700)."""
+        p, s = ops._p, ops._stream
+        G = Q * K
+        gz, arg, part, nt = self.groupmax_select(Gout, grp, st, Q, C, True)
+        c1 = torch.empty(C, dtype=f32, device=self.dev); c2 = torch.empty(C, dtype=f32, device=self.dev)
+        self.check(self.lib.usip_bn_bwd_finalize(p(part), nt, G, C, p(self.grads[norm.weight]), p(self.grads[norm.bias]),
+                                                 p(c1), p(c2), 1, s()), "usip_bn_bwd_finalize")
+        GY = torch.empty((G, C), dtype=f32, device=self.dev)
+        with _Prof("groupmax_bwd_apply", nbytes=8.0 * G * C):
+            self.check(self.lib.usip_groupmax_bwd_apply(p(Y), Y.stride(0), p(gz), p(arg), p(st.scale), p(st.mean), p(st.invstd),
+                                                        p(c1), p(c2), p(GY), GY.stride(0), K, G, C, s()), "usip_groupmax_bwd_apply")
+        return GY
+
     def wgrad(self, GY, X, gW, P, Cout, Cin, prev=None, relu=False, name="wgrad"):
         s = ops._stream(); p = ops._p
         tc = self.use_tc and Cout % 128 == 0 and Cin % 64 == 0 and P >= 4096
@@ -398,20 +446,18 @@ class _Bwd:
         self.check(self.lib.usip_colsum(ops._p(G), G.stride(0), ops._p(out), P, C, ops._stream()), "usip_colsum")
 
 
-def detector_backward(net, ctx, g_kp, g_sig):
-    """Backward of detector_forward.  Returns the gradients of net.parameters() in order."""
-    dev = ctx["cmean"].device
-    Bp, N, M, Kn = ctx["Bp"], ctx["N"], ctx["M"], ctx["Kn"]
-    H, C1, C2, Cb = ctx["H"], ctx["C1"], ctx["C2"], ctx["Cb"]
-    P, Q = Bp * N, Bp * M
+def _knn_head_backward(bw, net, ctx, g_kp, g_sig):
+    """Backward of _knn_head_forward: parameter gradients of mlp1/2/3 and knnlayer_1 are accumulated into bw.grads; returns
+    the gradient [Q, C1] of the per-node feature that entered AGG[:, :C1] (head path + kNN path)."""
+    dev = bw.dev
+    Bp, M = ctx["Bp"], ctx["M"]
+    Kn, C1, C2, Cb = ctx["Kn"], ctx["C1"], ctx["C2"], ctx["Cb"]
+    Q = Bp * M
     G = Q * Kn
-    bw = _Bwd(net, dev, ctx["use_tc"])
     lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
-    fp, sp = net.first_pointnet.layers, net.second_pointnet.layers
     kb, ka = net.knnlayer_1.layers_before, net.knnlayer_1.layers_after
     g_kp = None if g_kp is None else g_kp.contiguous()
     g_sig = None if g_sig is None else g_sig.contiguous()
-
     # ---- head (networks.py:143-154)
     G_OUT = torch.empty((Q, 4), dtype=f32, device=dev)
     check(lib.usip_head_bwd(p(g_kp), p(g_sig), p(ctx["OUT"]), ctx["OUT"].stride(0), p(G_OUT), Bp, M, s()), "usip_head_bwd")
@@ -431,26 +477,9 @@ def detector_backward(net, ctx, g_kp, g_sig):
     G_feat = G_AGG[:, C1:]
 
     # ---- kNN fusion, layers_after (layers.py:435-438)
-    def groupmax_select(Gout, grp, st, Qn, C, with_stats):
-        gz = torch.empty((Qn, C), dtype=f32, device=dev)
-        argsel = torch.empty((Qn, C), dtype=i32, device=dev)
-        nt = (Qn + 127) // 128
-        part = torch.empty((nt, 2, C), dtype=f32, device=dev) if with_stats else None
-        check(lib.usip_groupmax_bwd_select(p(Gout), Gout.stride(0), p(grp["gmax"]), p(grp["gmin"]), p(grp["amax"]),
-                                           p(grp["amin"]), p(st.scale), p(st.shift), p(st.mean), p(st.invstd), p(gz),
-                                           p(argsel), p(part), Qn, C, s()), "usip_groupmax_bwd_select")
-        return gz, argsel, part, nt
-
+    groupmax_select = bw.groupmax_select
     Ya_last, bna_last = ctx["after"][-1]
-    gz9, arg9, part9, nt9 = groupmax_select(G_feat, ctx["grp_a"], bna_last, Q, C2, True)
-    c1 = torch.empty(C2, dtype=f32, device=dev); c2 = torch.empty(C2, dtype=f32, device=dev)
-    check(lib.usip_bn_bwd_finalize(p(part9), nt9, G, C2, p(bw.grads[ka[-1].norm.weight]), p(bw.grads[ka[-1].norm.bias]),
-                                   p(c1), p(c2), 1, s()), "usip_bn_bwd_finalize")
-    GYa = torch.empty((G, C2), dtype=f32, device=dev)
-    with _Prof("groupmax_bwd_apply", nbytes=8.0 * G * C2):
-        check(lib.usip_groupmax_bwd_apply(p(Ya_last), Ya_last.stride(0), p(gz9), p(arg9), p(bna_last.scale), p(bna_last.mean),
-                                          p(bna_last.invstd), p(c1), p(c2), p(GYa), GYa.stride(0), Kn, G, C2, s()),
-              "usip_groupmax_bwd_apply")
+    GYa = bw.groupmax_bn_bwd(G_feat, Ya_last, ctx["grp_a"], bna_last, ka[-1].norm, Kn, Q, C2)
     # remaining after-layers, last -> first (li >= 1: plain BN+ReLU chains)
     for li in range(len(ka) - 1, 0, -1):
         Wl = _w2d(ka[li].conv.weight)
@@ -488,7 +517,7 @@ def detector_backward(net, ctx, g_kp, g_sig):
     gW5 = bw.g2d(kb[0].conv.weight)
     G_Z = torch.zeros((Q, Cb), dtype=f32, device=dev)
     with _Prof("knn_combine_bwd"):
-        check(lib.usip_knn_combine_bwd(p(GYb), GYb.stride(0), p(ctx["cmean"]), p(ctx["knn_i"]), p(G_Z), G_Z.stride(0), p(gW5),
+        check(lib.usip_knn_combine_bwd(p(GYb), GYb.stride(0), p(ctx["coords"]), p(ctx["knn_i"]), p(G_Z), G_Z.stride(0), p(gW5),
                                        gW5.stride(0), Bp, M, Kn, Cb, s()), "usip_knn_combine_bwd")
     del GYb
     pool2 = ctx["AGG"][:, :C1]
@@ -496,6 +525,21 @@ def detector_backward(net, ctx, g_kp, g_sig):
     G_pool2_knn = bw.dgrad(G_Z, _cols(W5, 3), Q, name="dgrad_knn_b0_node")    # [Q, C1]
     G_pool2_tot = G_pool2_knn
     G_pool2_tot += G_pool2                                                 # tiny [Q,C1] plumbing add
+
+    return G_pool2_tot
+
+
+def detector_backward(net, ctx, g_kp, g_sig):
+    """Backward of detector_forward.  Returns the gradients of net.parameters() in order."""
+    dev = ctx["cmean"].device
+    Bp, N, M = ctx["Bp"], ctx["N"], ctx["M"]
+    H, C1 = ctx["H"], ctx["C1"]
+    P, Q = Bp * N, Bp * M
+    bw = _Bwd(net, dev, ctx["use_tc"])
+    lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
+    fp, sp = net.first_pointnet.layers, net.second_pointnet.layers
+
+    G_pool2_tot = _knn_head_backward(bw, net, ctx, g_kp, g_sig)
 
     # ---- pool 2 un-pool (index_max gather backward), second PointNet
     G_F2 = torch.zeros((P, C1), dtype=f32, device=dev)
@@ -540,6 +584,97 @@ def detector_backward(net, ctx, g_kp, g_sig):
     return bw.result(net)
 
 
+def _group_net_forward(R, net, rows, Bp, M, K, keep, out=None):
+    """The grouped PointNet shared by DescriptorLiteOld (networks.py:375-381) and the ablation detectors
+    RPN_Detector_KNN / RPN_Detector_Ball (networks.py:567-572, 695-700):
+        conv1 -> conv2 -> conv3 -> max_k -> conv4 on cat(y, broadcast max) -> conv5 -> max_k
+    on point-major rows [Bp*M*K, ld] of the gathered, decentred groups.  conv1..conv4 carry BN+ReLU; conv5 is linear in the
+    descriptor (the raw group max is returned) and BN+ReLU in the detectors (max_k relu(bn(.)) is written to `out`).
+    The reference calls these convolutions WITHOUT epoch: their BN momentum never decays."""
+    dev = rows.device
+    G, Q = Bp * M * K, Bp * M
+    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
+    D = c3.conv.weight.shape[0]
+    Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, c1.norm.momentum, name="grp.conv1")
+    Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, c2.norm.momentum, prev=bn1, name="grp.conv2")
+    Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, c3.norm.momentum, prev=bn2,
+                          group=K, want_group=True, want_arg=keep, name="grp.conv3")
+    amax = torch.empty((Q, D), dtype=f32, device=dev)
+    ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
+    W4 = _w2d(c4.conv.weight)
+    C4 = W4.shape[0]
+    U, _, _ = R.run(amax, Q, _cols(W4, D), None, relu_in=False, name="grp.conv4_node")        # cat(y_first, max): max is LAST
+    Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, c4.norm.momentum, prev=bn3, addend=U,
+                       add_group=K, name="grp.conv4")
+    last_bn = getattr(c5, "norm", None) is not None
+    Y5, bn5, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), c5.norm if last_bn else None,
+                          c5.norm.momentum if last_bn else 0.1, prev=bn4, group=K, want_group=True, want_arg=keep,
+                          write_y=last_bn and keep, name="grp.conv5")
+    result = grp5["gmax"]
+    if last_bn:
+        C5 = c5.conv.weight.shape[0]
+        if out is None:
+            out = torch.empty((Q, C5), dtype=f32, device=dev)
+        ops.group_select(grp5["gmax"], grp5["gmin"], bn5.scale, bn5.shift, out, Q, C5)
+        result = out
+    gctx = dict(D=D)
+    if keep:
+        gctx.update(Bp=Bp, M=M, K=K, C4=C4, rows=rows, Y1=Y1, bn1=bn1, Y2=Y2, bn2=bn2, Y3=Y3, bn3=bn3, grp3=grp3, amax=amax,
+                    Y4=Y4, bn4=bn4, Y5=Y5, bn5=bn5, grp5=grp5)
+    return result, gctx
+
+
+ABLATION_K = 64             # networks.py:554, 680: `k = 64` is hard-coded in both ablation detectors
+ABLATION_RADIUS = 2.0       # networks.py:681
+
+
+def ablation_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False, mode="knn"):
+    """RPN_Detector_KNN.forward (models/networks.py:545-608, mode="knn") / RPN_Detector_Ball.forward (:671-738, mode="ball")
+    on the fused plan: group the points around the GIVEN nodes (64 nearest points / first 64 points within radius 2, both
+    without the (B,M,N) distance matrix), the grouped PointNet conv1..conv5 with two max-pools over the group, then the same
+    node-level kNN fusion module and head as RPN_Detector -- on the nodes themselves, which are also returned in place of the
+    recomputed cluster means.  Returns (node, keypoints, sigmas, ctx)."""
+    opt = net.opt
+    if keep and not net.training:
+        raise NotImplementedError("gradients through eval-mode BatchNorm are not part of the hot path")
+    dev = x.device
+    Bp, _, N = x.shape
+    M = node.shape[2]
+    S = opt.surface_normal_len if opt.surface_normal_len >= 1 else 0
+    Kn = opt.node_knn_k_1
+    K = ABLATION_K
+    Q = Bp * M
+    R = LayerRunner(net, net.training, use_tc, dev)
+    x = x.detach().contiguous(); node = node.detach().contiguous()
+    snc = sn.detach().contiguous() if S else None
+    with _Prof("group_%s" % mode):
+        if mode == "knn":
+            _, _, rows = ops.knn_group(x, snc, node, K, want_group=False, rows_ld=8)
+        else:
+            _, _, rows = ops.ball_group(x, snc, node, ABLATION_RADIUS, K, want_group=False, rows_ld=8)
+    C1 = net.conv5.conv.weight.shape[0]
+    C2 = net.knnlayer_1.layers_after[-1].conv.weight.shape[0]
+    AGG = torch.empty((Q, C1 + C2), dtype=f32, device=dev)
+    _, gctx = _group_net_forward(R, net, rows, Bp, M, K, keep, out=AGG[:, :C1])      # second_pn_out_max (networks.py:572)
+    keypoints, sigmas, kctx = _knn_head_forward(R, net, AGG, C1, node, Bp, M, Kn, epoch, keep)
+    ctx = None
+    if keep:
+        ctx = dict(gctx); ctx.update(kctx); ctx.update(Bp=Bp, M=M, use_tc=use_tc)
+    return node, keypoints, sigmas, ctx
+
+
+def ablation_backward(net, ctx, g_kp, g_sig):
+    """Backward of ablation_forward: gradients of net.parameters() in order (points and nodes carry none)."""
+    dev = ctx["AGG"].device
+    Bp, M, K = ctx["Bp"], ctx["M"], ctx["K"]
+    bw = _Bwd(net, dev, ctx["use_tc"])
+    G_pool = _knn_head_backward(bw, net, ctx, g_kp, g_sig)                  # gradient of max_k relu(bn5(conv5)) [Q, C1]
+    C5 = net.conv5.conv.weight.shape[0]
+    GY5 = bw.groupmax_bn_bwd(G_pool, ctx["Y5"], ctx["grp5"], ctx["bn5"], net.conv5.norm, K, Bp * M, C5)
+    _group_net_backward(bw, net, ctx, GY5)
+    return bw.result(net)
+
+
 def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, keep=False):
     """DescriptorLiteOld.forward (models/networks.py:333-385) on the fused plan.
     Returns (descriptor (B,C,M), x_features (B,3+S,M,K), ctx) -- ctx holds what descriptor_backward needs (keep=True)."""
@@ -561,29 +696,71 @@ def descriptor_forward(net, x, sn, keypoints, epoch, permute_idx, use_tc=True, k
     kp = keypoints.detach().contiguous()
     with _Prof("ball_group", nbytes=4.0 * Bp * (N * (3 + S) + 3 * M + M * K + (3 + S) * M * K)):
         idx, feats, rows = ops.ball_group(x, snp, kp, float(opt.ball_radius), K, want_group=True, rows_ld=8)
-    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
-    D = c3.conv.weight.shape[0]
-    # networks.py:375-379 calls conv1..conv4 WITHOUT epoch: the descriptor's BN momentum never decays
-    Y1, bn1, _ = R.run(rows, G, _w2d(c1.conv.weight), c1.conv.bias.detach(), c1.norm, c1.norm.momentum, name="desc.conv1")
-    Y2, bn2, _ = R.run(Y1, G, _w2d(c2.conv.weight), c2.conv.bias.detach(), c2.norm, c2.norm.momentum, prev=bn1, name="desc.conv2")
-    Y3, bn3, grp3 = R.run(Y2, G, _w2d(c3.conv.weight), c3.conv.bias.detach(), c3.norm, c3.norm.momentum, prev=bn2,
-                          group=K, want_group=True, want_arg=keep, name="desc.conv3")
-    amax = torch.empty((Q, D), dtype=f32, device=dev)
-    ops.group_select(grp3["gmax"], grp3["gmin"], bn3.scale, bn3.shift, amax, Q, D)          # y_first_max (networks.py:377)
-    W4 = _w2d(c4.conv.weight)
-    U, _, _ = R.run(amax, Q, _cols(W4, D), None, relu_in=False, name="desc.conv4_node")        # cat(y_first, max): max is LAST
-    Y4, bn4, _ = R.run(Y3, G, _cols(W4, 0, D), c4.conv.bias.detach(), c4.norm, c4.norm.momentum, prev=bn3, addend=U,
-                       add_group=K, name="desc.conv4")
-    _, _, grp5 = R.run(Y4, G, _w2d(c5.conv.weight), c5.conv.bias.detach(), prev=bn4, group=K, want_group=True,
-                       want_arg=keep, write_y=False, name="desc.conv5")
+    gmax5, gctx = _group_net_forward(R, net, rows, Bp, M, K, keep, out=None)
+    D = gctx["D"]
     desc = torch.empty((Bp, D, M), dtype=f32, device=dev)
-    _lib.check(_lib.load().usip_l2norm_to_bcm(ops._p(grp5["gmax"]), grp5["gmax"].stride(0), ops._p(desc), None, Bp, M, D,
+    _lib.check(_lib.load().usip_l2norm_to_bcm(ops._p(gmax5), gmax5.stride(0), ops._p(desc), None, Bp, M, D,
                                               ops._stream()), "usip_l2norm_to_bcm")
     ctx = None
     if keep:
-        ctx = dict(Bp=Bp, M=M, K=K, D=D, rows=rows, Y1=Y1, bn1=bn1, Y2=Y2, bn2=bn2, Y3=Y3, bn3=bn3, grp3=grp3, amax=amax,
-                   Y4=Y4, bn4=bn4, grp5=grp5, use_tc=use_tc)
+        ctx = dict(gctx)
+        ctx.update(use_tc=use_tc)
     return desc, feats, ctx
+
+
+def _group_net_backward(bw, net, ctx, GY5):
+    """Backward of _group_net_forward from GY5 [G, C5], the gradient of conv5's raw output rows (parameter gradients are
+    accumulated into bw.grads; points / centres carry no gradient)."""
+    dev = bw.dev
+    Bp, M, K, D = ctx["Bp"], ctx["M"], ctx["K"], ctx["D"]
+    Q, G = Bp * M, Bp * M * K
+    lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
+    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
+    grp3 = ctx["grp3"]
+    C5 = c5.conv.weight.shape[0]
+    W5 = _w2d(c5.conv.weight)
+    bw.wgrad(GY5, ctx["Y4"], bw.g2d(c5.conv.weight), G, C5, W5.shape[1], prev=ctx["bn4"], name="wgrad_grp.conv5")
+    if getattr(c5, "norm", None) is None:
+        bw.colsum(GY5, bw.grads[c5.conv.bias], G, C5)          # a bias in front of a train-mode BN has exactly zero gradient
+    G_a4 = bw.dgrad(GY5, W5, G, name="dgrad_grp.conv5")
+    del GY5
+    GY4 = bw.bn_bwd(G_a4, ctx["Y4"], ctx["bn4"], c4.norm, G, G_a4.shape[1], name="bn_bwd_grp.conv4")
+    del G_a4
+    # ---- conv4 on cat(y_first, broadcast max): Y4 = a3 WA^T + U[row/K] + b,  U = amax WB^T
+    W4 = _w2d(c4.conv.weight)
+    gW4 = bw.g2d(c4.conv.weight)
+    C4 = W4.shape[0]
+    bw.wgrad(GY4, ctx["Y3"], gW4[:, :D], G, C4, D, prev=ctx["bn3"], name="wgrad_grp.conv4")
+    G_a3 = bw.dgrad(GY4, _cols(W4, 0, D), G, name="dgrad_grp.conv4")                 # [G, D]
+    G_U = torch.empty((Q, C4), dtype=f32, device=dev)
+    check(lib.usip_group_sum(p(GY4), GY4.stride(0), p(G_U), G_U.stride(0), K, Q, C4, s()), "usip_group_sum")
+    del GY4
+    bw.wgrad(G_U, ctx["amax"], gW4[:, D:], Q, C4, D, name="wgrad_grp.conv4_node")
+    G_amax = bw.dgrad(G_U, _cols(W4, D), Q, name="dgrad_grp.conv4_node")             # [Q, D]
+    # the max path joins the dense gradient of a3 at the arg rows (the ReLU mask is applied by bn_bwd below)
+    gz = torch.empty((Q, D), dtype=f32, device=dev); arg3 = torch.empty((Q, D), dtype=i32, device=dev)
+    bn3 = ctx["bn3"]
+    check(lib.usip_groupmax_bwd_select(p(G_amax), G_amax.stride(0), p(grp3["gmax"]), p(grp3["gmin"]), p(grp3["amax"]),
+                                       p(grp3["amin"]), p(bn3.scale), p(bn3.shift), p(bn3.mean), p(bn3.invstd), p(gz), p(arg3),
+                                       None, Q, D, s()), "usip_groupmax_bwd_select")
+    check(lib.usip_groupmax_scatter_add(p(G_a3), G_a3.stride(0), p(G_amax), p(arg3), K, Q, D, s()), "usip_groupmax_scatter_add")
+    # ---- conv3, conv2, conv1
+    GY3 = bw.bn_bwd(G_a3, ctx["Y3"], bn3, c3.norm, G, D, name="bn_bwd_grp.conv3")
+    del G_a3
+    W3 = _w2d(c3.conv.weight)
+    bw.wgrad(GY3, ctx["Y2"], bw.g2d(c3.conv.weight), G, W3.shape[0], W3.shape[1], prev=ctx["bn2"], name="wgrad_grp.conv3")
+    G_a2 = bw.dgrad(GY3, W3, G, name="dgrad_grp.conv3")
+    del GY3
+    GY2 = bw.bn_bwd(G_a2, ctx["Y2"], ctx["bn2"], c2.norm, G, G_a2.shape[1], name="bn_bwd_grp.conv2")
+    del G_a2
+    W2 = _w2d(c2.conv.weight)
+    bw.wgrad(GY2, ctx["Y1"], bw.g2d(c2.conv.weight), G, W2.shape[0], W2.shape[1], prev=ctx["bn1"], name="wgrad_grp.conv2")
+    G_a1 = bw.dgrad(GY2, W2, G, name="dgrad_grp.conv2")
+    del GY2
+    GY1 = bw.bn_bwd(G_a1, ctx["Y1"], ctx["bn1"], c1.norm, G, G_a1.shape[1], name="bn_bwd_grp.conv1")
+    del G_a1
+    W1 = _w2d(c1.conv.weight)
+    bw.wgrad(GY1, ctx["rows"], bw.g2d(c1.conv.weight), G, W1.shape[0], W1.shape[1], name="wgrad_grp.conv1")
 
 
 def descriptor_backward(net, ctx, g_desc):
@@ -596,55 +773,13 @@ def descriptor_backward(net, ctx, g_desc):
     Q, G = Bp * M, Bp * M * K
     bw = _Bwd(net, dev, ctx["use_tc"])
     lib, check, p, s = bw.lib, bw.check, ops._p, ops._stream
-    c1, c2, c3, c4, c5 = net.conv1, net.conv2, net.conv3, net.conv4, net.conv5
-    grp5, grp3 = ctx["grp5"], ctx["grp3"]
+    grp5 = ctx["grp5"]
     # ---- l2 normalisation and the max over the ball (conv5 is linear: the max of the raw output routes to its arg row)
     G_y = torch.empty((Q, D), dtype=f32, device=dev)
     check(lib.usip_l2norm_bwd(p(g_desc.contiguous()), p(grp5["gmax"]), grp5["gmax"].stride(0), p(G_y), G_y.stride(0), Bp, M, D, s()),
           "usip_l2norm_bwd")
     GY5 = torch.zeros((G, D), dtype=f32, device=dev)
     check(lib.usip_groupmax_scatter_add(p(GY5), GY5.stride(0), p(G_y), p(grp5["amax"]), K, Q, D, s()), "usip_groupmax_scatter_add")
-    W5 = _w2d(c5.conv.weight)
-    bw.wgrad(GY5, ctx["Y4"], bw.g2d(c5.conv.weight), G, D, W5.shape[1], prev=ctx["bn4"], name="wgrad_desc.conv5")
-    bw.colsum(GY5, bw.grads[c5.conv.bias], G, D)
-    G_a4 = bw.dgrad(GY5, W5, G, name="dgrad_desc.conv5")
-    del GY5
-    GY4 = bw.bn_bwd(G_a4, ctx["Y4"], ctx["bn4"], c4.norm, G, G_a4.shape[1], name="bn_bwd_desc.conv4")
-    del G_a4
-    # ---- conv4 on cat(y_first, broadcast max): Y4 = a3 WA^T + U[row/K] + b,  U = amax WB^T
-    W4 = _w2d(c4.conv.weight)
-    gW4 = bw.g2d(c4.conv.weight)
-    C4 = W4.shape[0]
-    bw.wgrad(GY4, ctx["Y3"], gW4[:, :D], G, C4, D, prev=ctx["bn3"], name="wgrad_desc.conv4")
-    G_a3 = bw.dgrad(GY4, _cols(W4, 0, D), G, name="dgrad_desc.conv4")                 # [G, D]
-    G_U = torch.empty((Q, C4), dtype=f32, device=dev)
-    check(lib.usip_group_sum(p(GY4), GY4.stride(0), p(G_U), G_U.stride(0), K, Q, C4, s()), "usip_group_sum")
-    del GY4
-    bw.wgrad(G_U, ctx["amax"], gW4[:, D:], Q, C4, D, name="wgrad_desc.conv4_node")
-    G_amax = bw.dgrad(G_U, _cols(W4, D), Q, name="dgrad_desc.conv4_node")             # [Q, D]
-    # the max path joins the dense gradient of a3 at the arg rows (the ReLU mask is applied by bn_bwd below)
-    gz = torch.empty((Q, D), dtype=f32, device=dev); arg3 = torch.empty((Q, D), dtype=i32, device=dev)
-    bn3 = ctx["bn3"]
-    check(lib.usip_groupmax_bwd_select(p(G_amax), G_amax.stride(0), p(grp3["gmax"]), p(grp3["gmin"]), p(grp3["amax"]),
-                                       p(grp3["amin"]), p(bn3.scale), p(bn3.shift), p(bn3.mean), p(bn3.invstd), p(gz), p(arg3),
-                                       None, Q, D, s()), "usip_groupmax_bwd_select")
-    check(lib.usip_groupmax_scatter_add(p(G_a3), G_a3.stride(0), p(G_amax), p(arg3), K, Q, D, s()), "usip_groupmax_scatter_add")
-    # ---- conv3, conv2, conv1
-    GY3 = bw.bn_bwd(G_a3, ctx["Y3"], bn3, c3.norm, G, D, name="bn_bwd_desc.conv3")
-    del G_a3
-    W3 = _w2d(c3.conv.weight)
-    bw.wgrad(GY3, ctx["Y2"], bw.g2d(c3.conv.weight), G, W3.shape[0], W3.shape[1], prev=ctx["bn2"], name="wgrad_desc.conv3")
-    G_a2 = bw.dgrad(GY3, W3, G, name="dgrad_desc.conv3")
-    del GY3
-    GY2 = bw.bn_bwd(G_a2, ctx["Y2"], ctx["bn2"], c2.norm, G, G_a2.shape[1], name="bn_bwd_desc.conv2")
-    del G_a2
-    W2 = _w2d(c2.conv.weight)
-    bw.wgrad(GY2, ctx["Y1"], bw.g2d(c2.conv.weight), G, W2.shape[0], W2.shape[1], prev=ctx["bn1"], name="wgrad_desc.conv2")
-    G_a1 = bw.dgrad(GY2, W2, G, name="dgrad_desc.conv2")
-    del GY2
-    GY1 = bw.bn_bwd(G_a1, ctx["Y1"], ctx["bn1"], c1.norm, G, G_a1.shape[1], name="bn_bwd_desc.conv1")
-    del G_a1
-    W1 = _w2d(c1.conv.weight)
-    bw.wgrad(GY1, ctx["rows"], bw.g2d(c1.conv.weight), G, W1.shape[0], W1.shape[1], name="wgrad_desc.conv1")
+    _group_net_backward(bw, net, ctx, GY5)
     # conv1..conv4 biases sit in front of a train-mode BatchNorm: exactly zero gradient (left zero-initialised)
     return bw.result(net)

@@ -39,7 +39,7 @@ class ModelDetector():
         self.optimizer_detector = FlatAdam(self.detector.parameters(), lr=self.old_lr_detector, betas=(0.9, 0.999),
                                            weight_decay=0)
         self._dp = None
-        self.use_cuda_graph = bool(getattr(opt, "use_cuda_graph", True))
+        self.use_cuda_graph = bool(getattr(opt, "use_cuda_graph", True)) and not os.environ.get("USIP_NO_TRAIN_GRAPH")
         self._train_graph_key = None
 
         dev = self.opt.device

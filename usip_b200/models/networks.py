@@ -5,6 +5,8 @@ in usip_b200/engine.py.
   RPN_Detector      models/networks.py:20-162   (C1=128, C2=512)
   RPN_DetectorLite  models/networks.py:165-307  (C1=64,  C2=256; same graph)
   DescriptorLiteOld models/networks.py:310-385
+  RPN_Detector_KNN  models/networks.py:482-608  (ablation: 64 nearest points per node instead of the SOM assignment)
+  RPN_Detector_Ball models/networks.py:611-738  (ablation: first 64 points within radius 2 of each node)
 """
 import numpy as np
 import torch
@@ -112,6 +114,79 @@ class RPN_Detector(_RPNBase):
 class RPN_DetectorLite(_RPNBase):
     C1 = 64
     C2 = 256
+
+
+class _AblationFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x, sn, node, epoch, *params):
+        node_out, kp, sig, saved = engine.ablation_forward(net, x, sn, node, epoch, use_tc=net.use_tc, keep=net._keep,
+                                                           mode=net.GROUPING)
+        ctx.net = net
+        ctx.saved_plan = saved
+        return kp, sig
+
+    @staticmethod
+    def backward(ctx, g_kp, g_sig):
+        if ctx.saved_plan is None:
+            raise RuntimeError("detector forward ran without saving activations (no_grad / frozen)")
+        grads = engine.ablation_backward(ctx.net, ctx.saved_plan, g_kp, g_sig)
+        ctx.saved_plan = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class _RPNAblationBase(_PackedWeightHooks, nn.Module):
+    """Shared body of the two ablation detectors (identical constructors in the reference, networks.py:483-543, 612-669):
+    conv1..conv5 grouped PointNet, the node kNN fusion module, the head.  The nodes are used as given -- no SOM
+    re-assignment, no recomputed cluster means -- and are returned as the first output (networks.py:608, 738)."""
+    GROUPING = None
+
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.C1, self.C2 = 128, 512
+        C1, C2 = self.C1, self.C2
+        bn = dict(momentum=opt.bn_momentum, bn_momentum_decay_step=opt.bn_momentum_decay_step,
+                  bn_momentum_decay=opt.bn_momentum_decay)
+        kw = dict(kernel_size=(1, 1), stride=1, padding=0, bias=True, activation=opt.activation,
+                  normalization=opt.normalization, **bn)
+        self.conv1 = MyConv2d(3 + opt.surface_normal_len, C1 // 2, **kw)
+        self.conv2 = MyConv2d(C1 // 2, C1 // 2, **kw)
+        self.conv3 = MyConv2d(C1 // 2, C1 // 2, **kw)
+        self.conv4 = MyConv2d(C1, C1, **kw)
+        self.conv5 = MyConv2d(C1, C1, **kw)
+        assert opt.node_knn_k_1 >= 2
+        _check_group(opt.node_knn_k_1, "node_knn_k_1")
+        self.knnlayer_1 = GeneralKNNFusionModule(3 + C1, (C2 // 2, C2 // 2, C2 // 2), (C2, C2),
+                                                 activation=opt.activation, normalization=opt.normalization, **bn)
+        self.mlp1 = EquivariantLayer(C1 + C2, 512, activation=opt.activation, normalization=opt.normalization, **bn)
+        self.mlp2 = EquivariantLayer(512, 256, activation=opt.activation, normalization=opt.normalization, **bn)
+        self.mlp3 = EquivariantLayer(256, 4, activation=None, normalization=None)
+        self.mlp3.conv.weight.data.normal_(0, 1e-4)
+        self.mlp3.conv.bias.data.zero_()
+        self.softplus = torch.nn.Softplus()
+        self.use_tc = bool(getattr(opt, "use_tensor_cores", True))
+        self._keep = False
+        self._install_weight_hooks()
+        if opt.activation != "relu" or opt.normalization != "batch":
+            raise NotImplementedError("the B200 plan implements activation='relu', normalization='batch'")
+
+    def forward(self, x, sn, node, is_train=False, epoch=None):
+        """-> (node (B,3,M), keypoints (B,3,M), sigmas (B,M), None)"""
+        if not x.is_cuda:
+            raise RuntimeError("usip_b200 runs on CUDA tensors only (no CPU fallback)")
+        params = tuple(self.parameters())
+        self._keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        with torch.cuda.device(x.device):
+            kp, sig = _AblationFn.apply(self, x, sn, node, epoch, *params)
+        return node, kp, sig, None
+
+
+class RPN_Detector_KNN(_RPNAblationBase):
+    GROUPING = "knn"
+
+
+class RPN_Detector_Ball(_RPNAblationBase):
+    GROUPING = "ball"
 
 
 class _DescriptorFn(torch.autograd.Function):

@@ -106,6 +106,26 @@ def ball_group(xyz, feat, centers, radius, K, want_group=True, rows_ld=0):
     return idx, grp
 
 
+def knn_group(xyz, feat, centers, K, want_group=True, rows_ld=0):
+    """K nearest points of every centre + gather + decentre (RPN_Detector_KNN front end, networks.py:556-565).
+    Returns (idx (B,M,K) i32 ascending, group (B,3+S,M,K) f32 or None[, rows [B*M*K, rows_ld]])."""
+    _req(xyz, f32, "xyz"); _req(centers, f32, "centers")
+    B, _, N = xyz.shape
+    M = centers.shape[2]
+    S = 0 if feat is None else feat.shape[1]
+    if S:
+        _req(feat, f32, "feat")
+    idx = torch.empty((B, M, int(K)), dtype=i32, device=xyz.device)
+    grp = torch.empty((B, 3 + S, M, int(K)), dtype=f32, device=xyz.device) if want_group else None
+    rows = torch.empty((B * M * int(K), rows_ld), dtype=f32, device=xyz.device) if rows_ld else None
+    with torch.cuda.device(xyz.device):
+        check(_lib.load().usip_knn_group_f32(_p(xyz), _p(feat) if S else None, _p(centers), _p(idx), _p(grp), _p(rows), rows_ld,
+                                             B, S, N, M, int(K), _stream()), "usip_knn_group_f32")
+    if rows_ld:
+        return idx, grp, rows
+    return idx, grp
+
+
 def fps(pts, start, k, want_nodes=True):
     """Farthest point sampling.  pts (B,Ns,3) f32, start (B,) i32 -> (idx (B,k) i32, nodes (B,3,k) f32 or None)."""
     _req(pts, f32, "pts"); _req(start, i32, "start")
