@@ -18,20 +18,16 @@ COLS = [
     ("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio", "sec/ld", 1),
     ("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio", "sec/st", 1),
     ("lts__t_sector_hit_rate.pct", "L2hit%", 1),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2%", 1),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1%", 1),
     ("launch__registers_per_thread", "regs", 1),
     ("launch__grid_size", "grid", 1),
     ("launch__block_size", "block", 1),
 ]
-STALLS = [("long_scoreboard", "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct"),
-          ("barrier", "smsp__average_warp_latency_issue_stalled_barrier.pct"),
-          ("short_scoreboard", "smsp__average_warp_latency_issue_stalled_short_scoreboard.pct"),
-          ("lg_throttle", "smsp__average_warp_latency_issue_stalled_lg_throttle.pct"),
-          ("math_pipe", "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.pct"),
-          ("wait", "smsp__average_warp_latency_issue_stalled_wait.pct"),
-          ("membar", "smsp__average_warp_latency_issue_stalled_membar.pct"),
-          ("not_selected", "smsp__average_warp_latency_issue_stalled_not_selected.pct"),
-          ("mio_throttle", "smsp__average_warp_latency_issue_stalled_mio_throttle.pct"),
-          ("sleeping", "smsp__average_warp_latency_issue_stalled_sleeping.pct")]
+# warps stalled on <reason> per issue slot that issued (a ratio: 3.0 = on average three warps were waiting on it)
+STALLS = [(n, "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % n) for n in
+          ("long_scoreboard", "barrier", "short_scoreboard", "lg_throttle", "math_pipe_throttle", "wait", "membar",
+           "not_selected", "mio_throttle", "sleeping", "branch_resolving", "no_instruction", "dispatch_stall", "tex_throttle")]
 
 
 def num(v):
@@ -81,7 +77,7 @@ def main():
                 rec[short] = num(v)
         st = [(n, num(r[idx[k]])) for n, k in STALLS if k in idx]
         st = sorted([(n, v) for n, v in st if v is not None], key=lambda t: -t[1])[:3]
-        rec["top_stalls"] = " ".join("%s:%.0f%%" % t for t in st)
+        rec["top_stalls"] = " ".join("%s:%.1f" % t for t in st)
         recs.append(rec)
     shorts = [s for _, s, _ in COLS]
     with open(out + ".csv", "w") as f:

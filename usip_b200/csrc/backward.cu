@@ -12,14 +12,73 @@ namespace usip {
 constexpr int BW_ROWS = 128;      // rows per reduction tile (same as the forward stat tile)
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm(+ReLU) backward, phase 1: per-tile partial sums of g_z and g_z * xhat,
-// g_z = g * 1[scale*y+shift > 0].  CTA = 128 rows x CW channels (CW = min(C,128)).
+// BatchNorm(+ReLU) backward, phase 1: partial sums of g_z and g_z * xhat,  g_z = g * 1[scale*y+shift > 0].
+// part holds cdiv(P,128) rows of [2][C]; CTA i accumulates the 128-row tiles i, i+grid, ... into row i and the rows past
+// the grid are written as zeros, so the finalize kernel sums the same number of rows whatever the grid is.
+// Fast kernel (C/4 divides 256): a thread owns one 4-column group, streams rows with independent loads in flight.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                     float* __restrict__ part, int P, int C) {
+                     float* __restrict__ part, int P, int C, int ntiles) {
+  __shared__ float red[2][256][4];
+  const int c4n = C >> 2, rpp = 256 / c4n;
+  const int cgp = threadIdx.x % c4n, c = cgp * 4, rl = threadIdx.x / c4n;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+  const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int rend = min(P, (tile + 1) * BW_ROWS);
+    for (int r0 = tile * BW_ROWS + rl; r0 < rend; r0 += 4 * rpp) {
+      float4 g4[4], y4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * rpp;
+        if (r < rend) {
+          g4[u] = __ldg(reinterpret_cast<const float4*>(G + (size_t)r * ldg + c));
+          y4[u] = __ldg(reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + u * rpp < rend) {
+          const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}, yv[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float z = fmaf(yv[j], scv[j], shv[j]);
+            const float gz = (!relu || z > 0.f) ? gv[j] : 0.f;
+            s1[j] += gz; s2[j] = fmaf(gz, (yv[j] - muv[j]) * isv[j], s2[j]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { red[0][threadIdx.x][j] = s1[j]; red[1][threadIdx.x][j] = s2[j]; }
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    float a[4] = {0, 0, 0, 0}, bsum[4] = {0, 0, 0, 0};
+    for (int k = 0; k < rpp; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] += red[0][k * c4n + threadIdx.x][j]; bsum[j] += red[1][k * c4n + threadIdx.x][j]; }
+    float* o = part + (size_t)blockIdx.x * 2 * C + threadIdx.x * 4;
+    *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(o + C) = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+  }
+  // partial rows no CTA owns
+  for (int t = gridDim.x + blockIdx.x; t < ntiles; t += gridDim.x)
+    for (int i = threadIdx.x; i < 2 * C; i += 256) part[(size_t)t * 2 * C + i] = 0.f;
+}
+
+// generic variant: CTA = one 128-row tile x min(C,128) channels
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_tile_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                          float* __restrict__ part, int P, int C) {
   __shared__ float red[2][32][132];
   const int CW = min(C, 128), c4n = CW / 4, rsn = 256 / c4n;
   const int tile = blockIdx.x, cb = blockIdx.y * 128;
@@ -92,11 +151,54 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int ntiles, double count,
 }
 
 // phase 3: g_y = scale * (g_z - c1 - xhat*c2)            (scale = gamma*invstd)
+// HBM-bound (2 reads + 1 write of [P,C]): a thread owns one 4-column group -- its six per-channel vectors live in
+// registers -- and streams rows with four independent row loads in flight.  (C/4 divides 256.)
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
                     int relu, float* __restrict__ GY, int ldo, int P, int C) {
+  const int c4n = C >> 2, rpp = 256 / c4n;
+  const int c = (threadIdx.x % c4n) * 4, rl = threadIdx.x / c4n;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 k1 = *reinterpret_cast<const float4*>(c1 + c), k2 = *reinterpret_cast<const float4*>(c2 + c);
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w}, muv[4] = {mu.x, mu.y, mu.z, mu.w};
+  const float isv[4] = {is.x, is.y, is.z, is.w}, k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k2v[4] = {k2.x, k2.y, k2.z, k2.w};
+  const long long step = (long long)gridDim.x * rpp;
+  for (long long r0 = (long long)blockIdx.x * rpp + rl; r0 < P; r0 += 4 * step) {
+    float4 g4[4], y4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * step;
+      if (r < P) {
+        g4[u] = __ldcs(reinterpret_cast<const float4*>(G + (size_t)r * ldg + c));
+        y4[u] = __ldcs(reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * step;
+      if (r < P) {
+        const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w}, yv[4] = {y4[u].x, y4[u].y, y4[u].z, y4[u].w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float z = fmaf(yv[j], scv[j], shv[j]);
+          const float gz = (!relu || z > 0.f) ? gv[j] : 0.f;
+          o[j] = scv[j] * (gz - k1v[j] - (yv[j] - muv[j]) * isv[j] * k2v[j]);
+        }
+        *reinterpret_cast<float4*>(GY + (size_t)r * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+// any C % 4 == 0: grid-stride over (row, 4-column group)
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_generic_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ Y, int ldy,
+                            const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ c1, const float* __restrict__ c2,
+                            int relu, float* __restrict__ GY, int ldo, int P, int C) {
   const int c4n = C / 4;
   const size_t total = (size_t)P * c4n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -269,15 +371,84 @@ knn_combine_bwd_kernel(const float* __restrict__ GY, int ldg, const float* __res
   for (int i = threadIdx.x; i < C * 3; i += 256) atomicAdd(&gW[(size_t)(i / 3) * ldw + (i % 3)], sw[i]);
 }
 
-// column sums: out[c] (+)= sum_r G[r,c]
+// column sums: out[c] += sum_r G[r,c].  HBM-bound ([262144 x 128] fp32 = 134 MB): every thread streams float4s of one
+// 4-column group over a strided set of rows (a warp covers 128 consecutive floats of a row when C >= 128, whole rows
+// otherwise), partial sums meet in shared memory, one atomicAdd per column and CTA.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out, int P, int C) {
+  __shared__ float red[256][4];
+  const int c4n = C >> 2;                                   // float4 groups per row (host guarantees C % 4 == 0, C <= 1024)
+  const int cg = threadIdx.x % c4n, rl = threadIdx.x / c4n, rpp = 256 / c4n;   // rows per pass of this CTA
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rpp) {
+    for (long long r = (long long)blockIdx.x * rpp + rl; r < P; r += (long long)gridDim.x * rpp) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(G + (size_t)r * ldg + cg * 4));
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < c4n) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < rpp; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] += red[k * c4n + threadIdx.x][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(out + threadIdx.x * 4 + j, t[j]);
+  }
+}
+// generic fallback (any C, any alignment): one thread per column over a 1024-row slab
+__global__ void __launch_bounds__(256)
+colsum_slow_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out, int P, int C) {
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= C) return;
   const int r0 = blockIdx.x * 1024, r1 = min(P, r0 + 1024);
   float s = 0.f;
   for (int r = r0; r < r1; ++r) s += G[(size_t)r * ldg + c];
   atomicAdd(out + c, s);
+}
+
+// wgrad for a NARROW input (Cin <= 8, e.g. the first layer of a point stack: xyz + normals):
+//   gW[m, j] += sum_r GY[r, m] * act(X)[r, j].   HBM-bound on GY ([P, Cout] read once); thread = one output channel m of
+// one row subset, 8 accumulators; GY loads are coalesced across m, the X row is a 32-byte broadcast.
+__global__ void __launch_bounds__(256)
+wgrad_narrow_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__ X, int ldx,
+                    const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu,
+                    float* __restrict__ gW, int ldw, int P, int Cout, int Cin) {
+  __shared__ float red[256][9];
+  const int m = threadIdx.x % Cout, rl = threadIdx.x / Cout, rpp = 256 / Cout;      // host: Cout in {32, 64, 128, 256}
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = (in_scale && j < Cin) ? in_scale[j] : 1.f; sh[j] = (in_shift && j < Cin) ? in_shift[j] : 0.f; }
+  const bool x8 = (ldx == 8) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  for (long long r = (long long)blockIdx.x * rpp + rl; r < P; r += (long long)gridDim.x * rpp) {
+    const float g = __ldcs(GY + (size_t)r * ldg + m);
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (x8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8)), b = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8 + 4));
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+      for (int j = 0; j < Cin; ++j) x[j] = __ldg(X + (size_t)r * ldx + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = fmaf(x[j], sc[j], sh[j]);
+      if (in_relu) v = fmaxf(v, 0.f);
+      acc[j] = fmaf(g, j < Cin ? v : 0.f, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < Cout) {
+    for (int j = 0; j < Cin; ++j) {
+      float t = 0.f;
+      for (int k = 0; k < rpp; ++k) t += red[k * Cout + threadIdx.x][j];
+      atomicAdd(gW + (size_t)threadIdx.x * ldw + j, t);
+    }
+  }
 }
 
 // networks.py:151-154 backward: G_out4[q,0:3] = g_kp, G_out4[q,3] = g_sig * sigmoid(x)
@@ -456,8 +627,17 @@ extern "C" int usip_bn_bwd_reduce(const float* G, int ldg, const float* Y, int l
   USIP_REQUIRE(G && Y && scale && shift && mean && invstd && part && C % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 &&
                (C <= 128 ? (128 % C == 0 || C % 4 == 0) : C % 128 == 0), "bn_bwd_reduce: bad args");
   USIP_REQUIRE(C >= 32, "bn_bwd_reduce: C must be >= 32");
+  const int c4n = C / 4, ntiles = cdiv(P, BW_ROWS);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(part) |
+                         reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(mean) |
+                         reinterpret_cast<uintptr_t>(invstd)) % 16) == 0;
+  if (aligned && c4n <= 256 && 256 % c4n == 0) {
+    const int blocks = min(ntiles, 148 * 4);
+    bn_bwd_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, relu, part, P, C, ntiles);
+    return check_launch("bn_bwd_reduce_kernel");
+  }
   dim3 grid(cdiv(P, BW_ROWS), cdiv(C, 128));
-  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, relu, part, P, C);
+  bn_bwd_reduce_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, relu, part, P, C);
   return check_launch("bn_bwd_reduce_kernel");
 }
 
@@ -474,10 +654,20 @@ extern "C" int usip_bn_bwd_apply(const float* G, int ldg, const float* Y, int ld
                                  float* GY, int ldo, int P, int C, void* stream) {
   USIP_REQUIRE(G && Y && GY && C % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0, "bn_bwd_apply: bad args");
   size_t total = (size_t)P * (C / 4);
+  const int c4n = C / 4;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(GY) |
+                         reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(mean) |
+                         reinterpret_cast<uintptr_t>(invstd) | reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) % 16) == 0;
+  if (aligned && c4n <= 256 && 256 % c4n == 0) {
+    const int rpp = 256 / c4n;
+    const int blocks = (int)min((long long)148 * 8, (long long)cdiv(P, rpp * 4));
+    bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, c1, c2, relu, GY, ldo, P, C);
+    return check_launch("bn_bwd_apply_kernel");
+  }
   int blocks = (int)min((size_t)148 * 16, cdiv64(total, 256));
-  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, c1, c2, relu,
-                                                                GY, ldo, P, C);
-  return check_launch("bn_bwd_apply_kernel");
+  bn_bwd_apply_generic_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, Y, ldy, scale, shift, mean, invstd, c1, c2, relu,
+                                                                        GY, ldo, P, C);
+  return check_launch("bn_bwd_apply_generic_kernel");
 }
 
 extern "C" int usip_groupmax_bwd_select(const float* Gout, int ldg, const float* gmax, const float* gmin,
@@ -543,9 +733,15 @@ extern "C" int usip_knn_combine_bwd(const float* GY, int ldg, const float* pts, 
 
 extern "C" int usip_colsum(const float* G, int ldg, float* out, int P, int C, void* stream) {
   USIP_REQUIRE(G && out, "colsum: bad args");
+  if (C % 4 == 0 && C <= 1024 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(G) % 16) == 0) {
+    const int rpp = 256 / (C / 4);
+    const int blocks = (int)min((long long)cdiv(P, rpp * 4), 148LL * 8);
+    colsum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(G, ldg, out, P, C);
+    return check_launch("colsum_kernel");
+  }
   dim3 grid(cdiv(P, 1024), cdiv(C, 256));
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, out, P, C);
-  return check_launch("colsum_kernel");
+  colsum_slow_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, ldg, out, P, C);
+  return check_launch("colsum_slow_kernel");
 }
 
 extern "C" int usip_head_bwd(const float* g_kp, const float* g_sig, const float* out4, int ld, float* G, int B, int M,
@@ -567,6 +763,12 @@ extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, con
   if (precision == 1) {
     int rc = wgrad_tc(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin, (cudaStream_t)stream);
     if (rc != -2) return rc;
+  }
+  if (Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) && P >= 4096) {
+    const int rpp = 256 / Cout;
+    const int blocks = (int)min((long long)cdiv(P, rpp * 8), 148LL * 8);
+    wgrad_narrow_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin);
+    return check_launch("wgrad_narrow_kernel");
   }
   const int tiles = cdiv(Cout, 128) * cdiv(Cin, 128);
   int splits = max(1, min(cdiv(P, 128), (148 * 4) / tiles));

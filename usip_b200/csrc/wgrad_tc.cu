@@ -120,7 +120,8 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = r0 + ra + 4 * j;
-          x[j] = r < r_end ? __ldg(reinterpret_cast<const float4*>(GY + (size_t)r * ldg + m0 + ca * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // output channels past Cout (a 64-wide layer in the 128-row UMMA tile) are zero rows of the operand
+          x[j] = (r < r_end && m0 + ca * 4 < Cout) ? __ldg(reinterpret_cast<const float4*>(GY + (size_t)r * ldg + m0 + ca * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -238,11 +239,11 @@ static int launch_wgrad_tc(const float* GY, int ldg, const float* X, int ldx, co
     if (e != cudaSuccess) { set_last_error("wgrad_tc smem attr"); return (int)e; }
     attr = true;
   }
-  const int tiles = (Cout / 128) * (Cin / BN);
+  const int tiles = cdiv(Cout, 128) * (Cin / BN);
   int splits = max(1, min(cdiv(P, 4 * WT_BK), 148 / tiles));
   int rows = cdiv(cdiv(P, splits), WT_BK) * WT_BK;
   splits = cdiv(P, rows);
-  dim3 grid(splits, Cout / 128, Cin / BN);
+  dim3 grid(splits, cdiv(Cout, 128), Cin / BN);
   wgrad_tc_kernel<BN, STAGES><<<grid, WT_THREADS, SM::BYTES, st>>>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, rows);
   return check_launch("wgrad_tc_kernel");
 }
@@ -250,7 +251,7 @@ static int launch_wgrad_tc(const float* GY, int ldg, const float* X, int ldx, co
 // returns -2 when the shape is not eligible (caller falls back to the SIMT kernel)
 int wgrad_tc(const float* GY, int ldg, const float* X, int ldx, const float* sc, const float* sh, int relu, float* gW,
              int ldw, int P, int Cout, int Cin, cudaStream_t st) {
-  const bool ok = (Cout % 128 == 0) && (Cin % 64 == 0) && P >= 4096 && (ldg % 4 == 0) && (ldx % 4 == 0) &&
+  const bool ok = (Cout % 4 == 0) && (Cout >= 64) && (Cin % 64 == 0) && P >= 4096 && (ldg % 4 == 0) && (ldx % 4 == 0) &&
                   (reinterpret_cast<uintptr_t>(GY) % 16 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
                   (!sc || (reinterpret_cast<uintptr_t>(sc) % 16 == 0 && reinterpret_cast<uintptr_t>(sh) % 16 == 0));
   if (!ok) return -2;

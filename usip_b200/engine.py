@@ -423,7 +423,7 @@ class _Bwd:
 
     def wgrad(self, GY, X, gW, P, Cout, Cin, prev=None, relu=False, name="wgrad"):
         s = ops._stream(); p = ops._p
-        tc = self.use_tc and Cout % 128 == 0 and Cin % 64 == 0 and P >= 4096
+        tc = self.use_tc and Cout % 4 == 0 and Cout >= 64 and Cin % 64 == 0 and P >= 4096
         with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if tc else "fp32 SIMT"):
             self.check(self.lib.usip_wgrad(p(GY), GY.stride(0), p(X), X.stride(0), None if prev is None else p(prev.scale),
