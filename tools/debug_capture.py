@@ -20,12 +20,11 @@ def mk():
     return md
 
 def stage_fwd(md): md._run_siamese(is_train=True, epoch=0)
-def stage_fwd_loss(md): stage_fwd(md); md.optimizer_detector.zero_grad(); md._losses()
-def stage_bwd(md): stage_fwd_loss(md); md.loss.backward()
-def stage_all(md): stage_bwd(md); md.optimizer_detector.step()
+def stage_direct(md): md._train_step_direct(0)
+def stage_all(md): md._optimize_eager(0)
 
-for mode in ("global", "thread_local"):
-    for name, fn in (("fwd(keep)", stage_fwd), ("fwd+loss", stage_fwd_loss), ("+backward", stage_bwd), ("+adam", stage_all)):
+for mode in ("global",):
+    for name, fn in (("fwd(keep)", stage_fwd), ("direct fwd+loss+bwd", stage_direct), ("+adam", stage_all)):
         md = mk()
         side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -659,19 +659,21 @@ def ablation_forward(net, x, sn, node, epoch=None, use_tc=True, keep=False, mode
     keypoints, sigmas, kctx = _knn_head_forward(R, net, AGG, C1, node, Bp, M, Kn, epoch, keep)
     ctx = None
     if keep:
-        ctx = dict(gctx); ctx.update(kctx); ctx.update(Bp=Bp, M=M, use_tc=use_tc)
+        ctx = dict(kctx)                                        # (both plans keep an "amax": the grouped PointNet's state is nested)
+        ctx.update(Bp=Bp, M=M, use_tc=use_tc, group_net=gctx)
     return node, keypoints, sigmas, ctx
 
 
 def ablation_backward(net, ctx, g_kp, g_sig):
     """Backward of ablation_forward: gradients of net.parameters() in order (points and nodes carry none)."""
     dev = ctx["AGG"].device
-    Bp, M, K = ctx["Bp"], ctx["M"], ctx["K"]
+    gctx = ctx["group_net"]
+    Bp, M, K = ctx["Bp"], ctx["M"], gctx["K"]
     bw = _Bwd(net, dev, ctx["use_tc"])
     G_pool = _knn_head_backward(bw, net, ctx, g_kp, g_sig)                  # gradient of max_k relu(bn5(conv5)) [Q, C1]
     C5 = net.conv5.conv.weight.shape[0]
-    GY5 = bw.groupmax_bn_bwd(G_pool, ctx["Y5"], ctx["grp5"], ctx["bn5"], net.conv5.norm, K, Bp * M, C5)
-    _group_net_backward(bw, net, ctx, GY5)
+    GY5 = bw.groupmax_bn_bwd(G_pool, gctx["Y5"], gctx["grp5"], gctx["bn5"], net.conv5.norm, K, Bp * M, C5)
+    _group_net_backward(bw, net, gctx, GY5)
     return bw.result(net)
 
 

@@ -13,7 +13,7 @@ from collections import OrderedDict
 
 import torch
 
-from usip_b200 import _lib, engine
+from usip_b200 import _lib, engine, ops
 from usip_b200.optim import FlatAdam
 
 from . import losses, networks
@@ -165,12 +165,76 @@ class ModelDetector():
                 self._optimize_eager(epoch)
 
     def _optimize_eager(self, epoch):
-        self._run_siamese(is_train=True, epoch=epoch)
-        self.optimizer_detector.zero_grad()
-        self._losses()
-        self.loss.backward()
+        """One train step.  The default is the autograd-free plan (`_train_step_direct`): this class owns the whole chain
+        loss -> keypoints/sigmas -> network, so forward, the three losses, their gradients and engine.detector_backward are
+        launched back to back on the current stream -- no autograd graph, no engine thread hand-off, capturable as one
+        CUDA graph.  `opt.use_autograd_step = True` runs the reference's literal sequence (forward_siamese, criteria,
+        loss.backward()) through the autograd Functions instead; both give the same gradients (tests)."""
+        if getattr(self.opt, "use_autograd_step", False) or not isinstance(self.detector, networks._RPNBase):
+            self._run_siamese(is_train=True, epoch=epoch)
+            self.optimizer_detector.zero_grad()
+            self._losses()
+            self.loss.backward()
+        else:
+            self._train_step_direct(epoch)
         self._allreduce_grads()
         self.optimizer_detector.step()
+
+    @torch.no_grad()
+    def _train_step_direct(self, epoch):
+        """keypoint_detector.py:170-205 without autograd: same kernels as the autograd Functions in losses.py / networks.py."""
+        net, opt = self.detector, self.opt
+        B = self.src_pc.shape[0]
+        x = torch.cat((self.src_pc, self.dst_pc), dim=0)
+        sn = torch.cat((self.src_sn, self.dst_sn), dim=0)
+        node = torch.cat((self.src_node, self.dst_node), dim=0)
+        cmean, kp, sig, ctx, aux = engine.detector_forward(net, x, sn, node, epoch, use_tc=net.use_tc, keep=True)
+        net._last_aux = aux
+        self.src_node_recomputed, self.dst_node_recomputed = cmean[:B], cmean[B:]
+        self.src_keypoints, self.dst_keypoints = kp[:B], kp[B:]
+        self.src_sigmas, self.dst_sigmas = sig[:B], sig[B:]
+        self.src_descriptors = self.dst_descriptors = None
+        self.optimizer_detector.zero_grad()                                   # keypoint_detector.py:186
+        # ---- losses, forward (keypoint_detector.py:182-204)
+        R = self.src_R_dst.contiguous()
+        scale = self.src_scale_dst.reshape(-1).contiguous()
+        shift = self.src_shift_dst.reshape(B, 3).contiguous()
+        kp_t = ops.transform_points(self.src_keypoints, R, scale, shift)
+        self.src_keypoints_transformed = kp_t
+        out3, saved = losses.chamfer_prob_fwd(kp_t, self.dst_keypoints, self.src_sigmas, self.dst_sigmas)
+        self.loss_chamfer, self.chamfer_pure, self.chamfer_weighted = out3[0], out3[1], out3[2]
+        alpha = float(opt.keypoint_on_pc_alpha)
+        plane = opt.keypoint_on_pc_type == 'point_to_plane'
+        if not plane and opt.keypoint_on_pc_type != 'point_to_point':
+            raise NotImplementedError("keypoint_on_pc_type=%r" % opt.keypoint_on_pc_type)
+        sides = []
+        for kps, pc, snn in ((self.src_keypoints, self.src_pc, self.src_sn), (self.dst_keypoints, self.dst_pc, self.dst_sn)):
+            pc = pc.contiguous()
+            if plane:
+                snn = snn.contiguous()
+                d, arg = losses.point_on_surface_fwd(kps, pc, snn)
+            else:
+                d, arg = ops.pairwise_min(kps, pc)
+            sides.append((kps, pc, snn, d, arg, ops.mean_scale(d, alpha)[0]))
+        self.loss_keypoint_on_pc_src, self.loss_keypoint_on_pc_dst = sides[0][5], sides[1][5]
+        self.loss = self.loss_chamfer + self.loss_keypoint_on_pc_src + self.loss_keypoint_on_pc_dst
+        # ---- losses, backward: d loss / d keypoints, sigmas
+        if getattr(self, "_one", None) is None or self._one.device != kp.device:
+            self._one = torch.ones(1, dtype=torch.float32, device=kp.device)
+        g_kpt, g_dst, g_ss, g_sd = losses.chamfer_prob_bwd(saved, self._one)
+        g_kp = torch.empty_like(kp)
+        g_kp[:B] = losses.transform_bwd(g_kpt, R, scale)
+        g_kp[B:] = g_dst
+        for half, (kps, pc, snn, d, arg, _) in zip((g_kp[:B], g_kp[B:]), sides):
+            n = d.numel()
+            g = self._one.expand(d.shape[0], d.shape[1]).contiguous() if not plane else None
+            if plane:
+                gk = losses.point_on_surface_bwd(kps, pc, snn, arg, torch.full_like(d, alpha / n))
+            else:
+                gk, _ = losses.pairmin_bwd(kps, pc, d, arg, g, want_b=False, scale=alpha / n)
+            half += gk
+        g_sig = torch.cat((g_ss, g_sd), dim=0)
+        engine.detector_backward(net, ctx, g_kp, g_sig)
 
     def _optimize_graph(self, epoch):
         ins = [getattr(self, k) for k in self._GRAPH_INPUTS]

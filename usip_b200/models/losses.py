@@ -16,6 +16,66 @@ from usip_b200 import _lib, ops
 from usip_b200.ops import _p, _stream
 
 
+# ---- functional cores: used by the autograd Functions below and by the autograd-free train step of ModelDetector ----
+def pairmin_bwd(a, b, d, arg, g, want_b=False, scale=1.0):
+    """Gradient of d_i = min_j ||a_i - b_j|| w.r.t. a (and b): g (B,Ma) upstream, times `scale`."""
+    B, _, Ma = a.shape
+    ga = torch.empty_like(a)
+    gb = torch.zeros_like(b) if want_b else None
+    _lib.check(_lib.load().usip_pairwise_min_bwd(_p(a), _p(b), _p(d), _p(arg), _p(g.contiguous()), float(scale), _p(ga),
+                                                 _p(gb), B, Ma, b.shape[2], _stream()), "usip_pairwise_min_bwd")
+    return ga, gb
+
+
+def chamfer_prob_fwd(src, dst, sig_src, sig_dst):
+    """ChamferLoss_Brute sigma branch (losses.py:79-97): -> (out3 = [loss, pure, weighted], saved)."""
+    d_sd, i_sd = ops.pairwise_min(src, dst)
+    d_ds, i_ds = ops.pairwise_min(dst, src)
+    out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst)
+    return out3, (src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds)
+
+
+def chamfer_prob_bwd(saved, g_loss):
+    """-> (g_src, g_dst, g_sig_src, g_sig_dst) for the upstream gradient g_loss (1-element tensor) of the chamfer loss."""
+    src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds = saved
+    B, _, M = src.shape
+    N = dst.shape[2]
+    g_src = torch.zeros_like(src); g_dst = torch.zeros_like(dst)
+    g_ss = torch.zeros_like(sig_src); g_sd = torch.zeros_like(sig_dst)
+    gout = g_loss.reshape(1).to(torch.float32).contiguous()
+    _lib.check(_lib.load().usip_chamfer_prob_bwd(_p(src), _p(dst), _p(sig_src), _p(sig_dst), _p(d_sd), _p(i_sd),
+                                                 _p(d_ds), _p(i_ds), _p(gout), _p(g_src), _p(g_dst), _p(g_ss),
+                                                 _p(g_sd), B, M, N, _stream()), "usip_chamfer_prob_bwd")
+    return g_src, g_dst, g_ss, g_sd
+
+
+def transform_bwd(g, R, scale):
+    g = g.contiguous()
+    B, _, M = g.shape
+    gk = torch.empty_like(g)
+    _lib.check(_lib.load().usip_transform_points_bwd(_p(g), _p(R), _p(scale), _p(gk), B, M, _stream()),
+               "usip_transform_points_bwd")
+    return gk
+
+
+def point_on_surface_fwd(kp, pc, sn):
+    B, _, M = kp.shape
+    _, arg = ops.pairwise_min(kp, pc)                       # nearest cloud point of every keypoint (not differentiated)
+    loss = torch.empty((B, M), dtype=torch.float32, device=kp.device)
+    _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), None, _p(loss), None, B, M, pc.shape[2],
+                                                 sn.shape[1], _stream()), "usip_point_on_surface")
+    return loss, arg
+
+
+def point_on_surface_bwd(kp, pc, sn, arg, g):
+    B, _, M = kp.shape
+    g_kp = torch.empty_like(kp)
+    _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), _p(g.reshape(B, M).contiguous().float()),
+                                                 None, _p(g_kp), B, M, pc.shape[2], sn.shape[1], _stream()),
+               "usip_point_on_surface")
+    return g_kp
+
+
 class _PairMinFn(torch.autograd.Function):
     """min_j ||a_i - b_j|| (B,Ma); differentiable w.r.t. both point sets (sub-gradient 0 at d == 0)."""
 
@@ -31,13 +91,8 @@ class _PairMinFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         a, b, d, arg = ctx.saved_tensors
-        B, _, Ma = a.shape
-        Nb = b.shape[2]
-        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
-        gb = torch.zeros_like(b) if ctx.needs_input_grad[1] else None
-        _lib.check(_lib.load().usip_pairwise_min_bwd(_p(a), _p(b), _p(d), _p(arg), _p(g.contiguous()), 1.0, _p(ga),
-                                                     _p(gb), B, Ma, Nb, _stream()), "usip_pairwise_min_bwd")
-        return ga, gb
+        ga, gb = pairmin_bwd(a, b, d, arg, g, want_b=ctx.needs_input_grad[1])
+        return (ga if ctx.needs_input_grad[0] else None), gb
 
 
 class _ChamferProbFn(torch.autograd.Function):
@@ -47,26 +102,15 @@ class _ChamferProbFn(torch.autograd.Function):
         sig_src = sig_src.contiguous(); sig_dst = sig_dst.contiguous()
         from usip_b200 import engine
         with engine._Prof("chamfer_prob"):
-            d_sd, i_sd = ops.pairwise_min(src, dst)
-            d_ds, i_ds = ops.pairwise_min(dst, src)
-            out3 = ops.chamfer_prob_reduce(d_sd, i_sd, d_ds, i_ds, sig_src, sig_dst)
-        ctx.save_for_backward(src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds)
+            out3, saved = chamfer_prob_fwd(src, dst, sig_src, sig_dst)
+        ctx.save_for_backward(*saved)
         loss, pure, weighted = out3[0], out3[1], out3[2]
         ctx.mark_non_differentiable(pure, weighted)
         return loss, pure, weighted
 
     @staticmethod
     def backward(ctx, g_loss, g_pure, g_weighted):
-        src, dst, sig_src, sig_dst, d_sd, i_sd, d_ds, i_ds = ctx.saved_tensors
-        B, _, M = src.shape
-        N = dst.shape[2]
-        g_src = torch.zeros_like(src); g_dst = torch.zeros_like(dst)
-        g_ss = torch.zeros_like(sig_src); g_sd = torch.zeros_like(sig_dst)
-        gout = g_loss.reshape(1).to(torch.float32).contiguous()
-        _lib.check(_lib.load().usip_chamfer_prob_bwd(_p(src), _p(dst), _p(sig_src), _p(sig_dst), _p(d_sd), _p(i_sd),
-                                                     _p(d_ds), _p(i_ds), _p(gout), _p(g_src), _p(g_dst), _p(g_ss),
-                                                     _p(g_sd), B, M, N, _stream()), "usip_chamfer_prob_bwd")
-        return g_src, g_dst, g_ss, g_sd
+        return chamfer_prob_bwd(ctx.saved_tensors, g_loss)
 
 
 class _TransformFn(torch.autograd.Function):
@@ -82,12 +126,7 @@ class _TransformFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         R, scale = ctx.saved_tensors
-        g = g.contiguous()
-        B, _, M = g.shape
-        gk = torch.empty_like(g)
-        _lib.check(_lib.load().usip_transform_points_bwd(_p(g), _p(R), _p(scale), _p(gk), B, M, _stream()),
-                   "usip_transform_points_bwd")
-        return gk, None, None, None
+        return transform_bwd(g, R, scale), None, None, None
 
 
 class _MeanScaleFn(torch.autograd.Function):
@@ -144,22 +183,14 @@ class _PointOnSurfaceFn(torch.autograd.Function):
     def forward(ctx, keypoint, pc, sn):
         kp = keypoint.contiguous(); pc = pc.contiguous(); sn = sn.contiguous()
         B, _, M = kp.shape
-        _, arg = ops.pairwise_min(kp, pc)                       # nearest cloud point of every keypoint (not differentiated)
-        loss = torch.empty((B, M), dtype=torch.float32, device=kp.device)
-        _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), None, _p(loss), None, B, M, pc.shape[2],
-                                                     sn.shape[1], _stream()), "usip_point_on_surface")
+        loss, arg = point_on_surface_fwd(kp, pc, sn)
         ctx.save_for_backward(kp, pc, sn, arg)
         return loss.view(B, M, 1, 1)                            # the reference returns the (B,M,1,1) matmul result
 
     @staticmethod
     def backward(ctx, g):
         kp, pc, sn, arg = ctx.saved_tensors
-        B, _, M = kp.shape
-        g_kp = torch.empty_like(kp)
-        _lib.check(_lib.load().usip_point_on_surface(_p(kp), _p(pc), _p(sn), _p(arg), _p(g.reshape(B, M).contiguous().float()),
-                                                     None, _p(g_kp), B, M, pc.shape[2], sn.shape[1], _stream()),
-                   "usip_point_on_surface")
-        return g_kp, None, None
+        return point_on_surface_bwd(kp, pc, sn, arg, g), None, None
 
 
 class PointOnSurfaceLoss(nn.Module):
