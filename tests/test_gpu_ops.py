@@ -35,6 +35,23 @@ def test_index_max_vs_oracle(B, C, N, K):
     assert np.array_equal(out, orc.index_max(data, index, K))
 
 
+def test_index_max_bucket_kernel_edge_cases():
+    """The HBM-speed bucket kernel (csrc/indexmax.cu; taken when B*C >= 64, C >= 8, N % 4 == 0, N <= 16384): exact ties
+    (first maximum wins whatever the bucket order), values at / below the -1000 floor, NaN, empty clusters, -0.0."""
+    from usip_b200 import index_max
+    rng = np.random.default_rng(77)
+    B, C, N, K = 5, 16, 2000, 48
+    data = (np.round(rng.normal(size=(B, C, N)) * 2) / 2).astype(np.float32)          # many exact ties
+    data[:, 1, :] = -2000.0                                                            # never above the floor
+    data[:, 2, ::3] = -1000.0                                                          # exactly the floor: not '>'
+    data[:, 3, ::7] = np.nan
+    data[:, 4, ::2] = -0.0
+    data[:, 5, :] = 3.5                                                                # one value everywhere: n = first of the cluster
+    index = rng.integers(0, K // 2, size=(B, N)).astype(np.int32)                      # upper half of the clusters empty
+    out = index_max.forward_cuda_shared_mem(cu(data), cu(index), K).cpu().numpy()
+    assert np.array_equal(out, orc.index_max(data, index, K))
+
+
 def test_index_max_vs_reference_cuda_full_size():
     """KITTI shape (B'=16, C=128, N=16384, K=512) against the reference's own kernel (global-mem variant, no cap)."""
     from usip_b200 import index_max

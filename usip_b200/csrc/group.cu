@@ -417,6 +417,9 @@ static int launch_index_max_smem(const float* data, const int32_t* index, int32_
   return check_launch("index_max_smem_kernel");
 }
 
+bool index_max_bucket_ok(const float* data, int N, int K);                                    // indexmax.cu
+int launch_index_max_bucket(const float* data, const int32_t* index, int32_t* out, int B, int C, int N, int K, cudaStream_t st);
+
 }  // namespace usip
 
 using namespace usip;
@@ -425,6 +428,8 @@ extern "C" int usip_index_max_f32(const float* data, const int32_t* index, int32
                                   unsigned long long* scratch, int B, int C, int N, int K, void* stream) {
   USIP_REQUIRE(data && index && out_idx && B > 0 && C > 0 && N > 0 && K > 0, "index_max: bad args");
   cudaStream_t st = (cudaStream_t)stream;
+  // enough rows per cloud to amortise the per-cloud bucket sort: the HBM-speed kernel; else the atomic-max kernels below
+  if (C >= 8 && (long long)B * C >= 64 && index_max_bucket_ok(data, N, K)) return launch_index_max_bucket(data, index, out_idx, B, C, N, K, st);
   const size_t budget = 96 * 1024;   // keep >= 2 CTAs / SM
   if ((size_t)8 * K * 12 <= budget && C >= 8) return launch_index_max_smem<8>(data, index, out_idx, B, C, N, K, st);
   if ((size_t)4 * K * 12 <= budget && C >= 4) return launch_index_max_smem<4>(data, index, out_idx, B, C, N, K, st);
