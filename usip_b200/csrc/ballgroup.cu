@@ -17,6 +17,7 @@
 // within r of a centre lies in the 3 x 3 block around the centre's cell; clouds whose overflow list is full, balls with
 // more than 64 hits, K > 64 and non-finite radii take the reference's own in-order scan (bit-identical by construction).
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace usip {
 
@@ -88,13 +89,15 @@ __device__ BxGrid bx_make_grid(const float* __restrict__ cp, int M, float radius
   int n0 = 1, n1 = 1;
   if (g.ok) {
     for (int it = 0; it < 96; ++it) {
-      n0 = (int)fminf(floorf(e[g.a0] / h), 1e6f) + 3; n1 = (int)fminf(floorf(e[g.a1] / h), 1e6f) + 3;
+      // two margin cells on either side: a centre's cell index stays in [1, n-2] whatever the last-bit rounding of
+      // (c - o) * inv_h does, so its 3 x 3 block never leaves the grid
+      n0 = (int)fminf(floorf(e[g.a0] / h), 1e6f) + 5; n1 = (int)fminf(floorf(e[g.a1] / h), 1e6f) + 5;
       if ((long long)n0 * n1 <= BX_MAX_CELLS) break;
       h *= 1.26f;
     }
     if ((long long)n0 * n1 > BX_MAX_CELLS) g.ok = 0;
   }
-  g.o0 = lo[g.a0] - h; g.o1 = lo[g.a1] - h; g.inv_h = 1.0f / h; g.n0 = n0; g.n1 = n1;
+  g.o0 = lo[g.a0] - 2.f * h; g.o1 = lo[g.a1] - 2.f * h; g.inv_h = 1.0f / h; g.n0 = n0; g.n1 = n1;
   return g;
 }
 
@@ -185,8 +188,10 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
     if (novf > BX_OVF) brute = true;
     const bool cfin = fabsf(cx) <= 1e30f && fabsf(cy) <= 1e30f && fabsf(cz) <= 1e30f;
     if (!brute && cfin) {
-      // finite centres lie in cells [1, n-2]: the 3 x 3 block never leaves the grid
-      const int k0 = (int)floorf((bx_axis(cx, cy, cz, g.a0) - g.o0) * g.inv_h), k1 = (int)floorf((bx_axis(cx, cy, cz, g.a1) - g.o1) * g.inv_h);
+      // finite centres lie in cells [1, n-2] (bx_make_grid): the 3 x 3 block never leaves the grid; the clamp only
+      // guards the address arithmetic
+      const int k0 = min(max((int)floorf((bx_axis(cx, cy, cz, g.a0) - g.o0) * g.inv_h), 1), g.n0 - 2);
+      const int k1 = min(max((int)floorf((bx_axis(cx, cy, cz, g.a1) - g.o1) * g.inv_h), 1), g.n1 - 2);
       const int base = (k1 - 1) * g.n0 + (k0 - 1);
       const float4* bk = buckets + (size_t)b * BX_MAX_CELLS * BX_CAP * 2;
       float4* st = stage[wib];
@@ -356,7 +361,8 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
   cfg.gridDim = dim3((unsigned)(cpc * B)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("USIP_BALL_NO_PDL") != nullptr;            // debug aid: plain stream order instead
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
   const BxGrid* grids = sc.grids; const float4* bk = sc.buckets; const float4* ov = sc.ovf;
   cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_query_kernel, xyz, feat, centers, grids, sc.counts, sc.ovf_cnt, sc.done, bk, ov, t_max,
                                       out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, cpc);
