@@ -207,7 +207,7 @@ def _layer_ref(X, W, b, scale, shift, relu, addend, add_idx):
     return Y
 
 
-@pytest.mark.parametrize("precision", [0, 1, 2])
+@pytest.mark.parametrize("precision", [0, 1, 2, 3])      # 0 SIMT fp32; tcgen05 3xTF32: 1 smem operands, 2 CTA pair, 3 A through TMEM
 @pytest.mark.parametrize("P,Cin,Cout,group", [(1000, 7, 64, 0), (4096, 64, 64, 16), (2048, 128, 128, 32),
                                               (1536, 256, 256, 16), (1024, 512, 512, 64), (700, 640, 512, 0),
                                               (512, 256, 4, 0), (640, 131, 256, 0),

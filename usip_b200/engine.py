@@ -78,12 +78,12 @@ class BNState:
 # Packed (hi/lo TF32, pre-swizzled) weight tiles are cached per weight view and re-used while the parameter's
 # autograd version counter is unchanged (inference / fwd-only loops); an optimizer step bumps the version and the
 # next launch re-packs into the same workspace.
-def _tc_workspace(W, P, Cin, Cout, group, transposed):
+def _tc_workspace(W, P, Cin, Cout, group, transposed, prec=1):
     owner = getattr(W, "_owner", None)
     if owner is None:                                  # unknown provenance: never reuse packed tiles
         return torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device), False
     cache = owner.__dict__.setdefault("_usip_tc", {})  # lives and dies with the Parameter object
-    key = (W.data_ptr() - owner.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32)
+    key = (W.data_ptr() - owner.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32, prec)
     ver = (owner._version, _lib.WEIGHT_GEN[0])
     ent = cache.get(key)
     if ent is not None and ent[0] == ver and ent[2] == owner.data_ptr():
@@ -103,7 +103,9 @@ def invalidate_packed_weights(module):
 
 
 import os as _os
-_TC_PREC = 2 if _os.environ.get("USIP_TC_PAIR") else 1     # A/B switch: opt into the CTA-pair kernel for wide layers
+# tensor-core kernel variant: 1 = operands through shared memory, 3 = A operand through tensor memory (tcgen05.st, TS-form
+# MMA; csrc/mlp_tc.cu TcSmem), 2 = CTA-pair kernel (measured slower, experiment only)
+_TC_PREC = 2 if _os.environ.get("USIP_TC_PAIR") else (1 if _os.environ.get("USIP_TC_SMEM_A") else 3)
 
 
 def _precision_for(P, Cin, Cout, use_tc, group=0):
@@ -163,7 +165,7 @@ class LayerRunner:
             if want_arg:
                 grp["amax"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
                 grp["amin"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
-        ws, packed = _tc_workspace(W, P, Cin, Cout, group if want_group else 0, False) if prec else (None, False)
+        ws, packed = _tc_workspace(W, P, Cin, Cout, group if want_group else 0, False, prec) if prec else (None, False)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(X, W, bias, P, Cin, Cout,
@@ -436,7 +438,7 @@ class _Bwd:
         if out is None:
             out = torch.empty((P, Cin), dtype=f32, device=self.dev)
         prec = _precision_for(P, Cout, Cin, self.use_tc)
-        ws, packed = _tc_workspace(W2d, P, Cout, Cin, 0, True) if prec else (None, False)
+        ws, packed = _tc_workspace(W2d, P, Cout, Cin, 0, True, prec) if prec else (None, False)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed)
