@@ -50,6 +50,9 @@ def run():
         dnet.train()
         with torch.no_grad():
             dnet(pc, sn, kp, True, None)
+    if "ballonly" in what:
+        ops.ball_group(pc, sn, kp, 1.0, K, want_group=True)
+        index_max.forward_cuda_shared_mem(data, index, 512)
     if "ops" in what:
         index_max.forward_cuda_shared_mem(data, index, 512)
         ball_query.forward_cuda_shared_mem(dist, 1.0, K)
@@ -60,6 +63,9 @@ for _ in range(2):
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
 run()
+if "ballonly" in what:
+    for _ in range(3):
+        run()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("ncu_step done:", sorted(what))
