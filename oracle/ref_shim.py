@@ -62,8 +62,10 @@ def _ball_query_restatement(node_to_point_dist, radius, K):
     return torch.from_numpy(orc.ball_query_dist(d, float(radius), int(K)))
 
 
-def install(use_ref_ext: bool = True, mode: str = "cpu"):
-    """Make `import models.networks` etc. resolve to the reference (CPU shims, or its own CUDA extensions)."""
+def install(use_ref_ext: bool = True, mode: str = "cpu", operators: str = "reference"):
+    """Make `import models.networks` etc. resolve to the reference (CPU shims, or its own CUDA extensions).
+    operators="dropin" (cuda mode): leave `index_max` / `ball_query` to sys.path, with <repo>/usip_b200/dropin in front --
+    the literal operator-level recipe of INTEGRATION.md: the unmodified reference on THIS repo's operators."""
     global _installed
     if _installed is not None:
         if _installed != mode:
@@ -83,6 +85,12 @@ def install(use_ref_ext: bool = True, mode: str = "cpu"):
     _stub("h5py")
 
     if mode == "cuda":
+        if operators == "dropin":
+            _finish(root, mode)
+            sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "usip_b200", "dropin"))
+            for name in ("index_max", "ball_query"):
+                sys.modules.pop(name, None)
+            return
         # 2'. the reference's own CUDA extensions, compiled from its sources by oracle/build_ref.py
         from . import build_ref
         sys.modules["index_max"] = build_ref._load_so("index_max")
@@ -145,8 +153,8 @@ def make_opt(**over):
     return o
 
 
-def modules(mode="cpu"):
-    install(mode=mode)
+def modules(mode="cpu", operators="reference"):
+    install(mode=mode, operators=operators)
     networks = importlib.import_module("models.networks")
     losses = importlib.import_module("models.losses")
     layers = importlib.import_module("models.layers")

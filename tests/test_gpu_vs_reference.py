@@ -314,3 +314,44 @@ def test_reference_networks_on_our_operators(ref):
     assert calls["im"] == 2 and calls["bq"] == 1          # networks.py:118,131 and :359 really went through our modules
     for a, b in zip(res["ours"], res["ref"]):
         assert np.array_equal(a, b)
+
+
+def test_dropin_directory_serves_the_reference_networks(ref, tmp_path):
+    """INTEGRATION.md section 2, literally: a fresh interpreter puts <repo>/usip_b200/dropin in front of the (staged)
+    reference tree, imports the reference's own `models.networks` -- whose `import index_max` / `import ball_query`
+    (networks.py:17-18) now resolve to this repo -- and must reproduce, bit for bit, what the reference computes on its own
+    extensions in this process."""
+    import os, subprocess, sys
+    cfg = dict(B=2, N=4096, M=128, S=4, Kn=16, kind="lidar", lb=1e-3, alpha=0.01, seed=31)
+    d = orc.synth_pair(cfg["B"], cfg["N"], cfg["M"], cfg["S"], kind=cfg["kind"], seed=cfg["seed"])
+    rmd = _mk(ref.keypoint_detector.ModelDetector, cfg)
+    rmd.set_input(*[torch.from_numpy(d[k]) for k in KEYS])
+    with torch.no_grad():
+        rmd.test_model()
+    want = os.path.join(tmp_path, "want.npz")
+    np.savez(want, kp=torch.cat([rmd.src_keypoints, rmd.dst_keypoints]).cpu().numpy(),
+             sig=torch.cat([rmd.src_sigmas, rmd.dst_sigmas]).cpu().numpy(), loss=np.float32(rmd.loss.item()))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, os; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False\n"
+        "from oracle import ref_shim, usip_oracle as orc\n"
+        "ref = ref_shim.modules(mode='cuda', operators='dropin')\n"
+        "import index_max, ball_query\n"
+        "drop = os.path.join(%r, 'usip_b200', 'dropin')\n"
+        "assert index_max.__file__.startswith(drop) and ball_query.__file__.startswith(drop), index_max.__file__\n"
+        "assert ref.networks.index_max is index_max and 'oracle' in ref.networks.__file__\n"
+        "from tests import test_gpu_vs_reference as T\n"
+        "cfg = %r\n"
+        "d = orc.synth_pair(cfg['B'], cfg['N'], cfg['M'], cfg['S'], kind=cfg['kind'], seed=cfg['seed'])\n"
+        "rmd = T._mk(ref.keypoint_detector.ModelDetector, cfg)\n"
+        "rmd.set_input(*[torch.from_numpy(d[k]) for k in T.KEYS])\n"
+        "with torch.no_grad(): rmd.test_model()\n"
+        "w = np.load(%r)\n"
+        "assert np.array_equal(torch.cat([rmd.src_keypoints, rmd.dst_keypoints]).cpu().numpy(), w['kp'])\n"
+        "assert np.array_equal(torch.cat([rmd.src_sigmas, rmd.dst_sigmas]).cpu().numpy(), w['sig'])\n"
+        "assert np.float32(rmd.loss.item()) == w['loss']\n"
+        "print('dropin ok')\n" % (root, root, cfg, want))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dropin ok" in r.stdout, (r.stdout[-1000:], r.stderr[-3000:])

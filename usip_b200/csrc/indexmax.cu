@@ -13,7 +13,7 @@
 
 namespace usip {
 
-constexpr int IMS_THREADS = 512;
+constexpr int IMS_THREADS = 1024;          // two threads per cluster at K = 512: half a segment each, merged by one shuffle
 constexpr int IMS_MAXN = 16384;            // one row buffer = 64 KB; bucket order as uint16
 constexpr int IMS_MAXK = 4096;
 
@@ -96,17 +96,25 @@ index_max_bucket_kernel(const float* __restrict__ data, const int32_t* __restric
     }
     mbar_wait(bar0 + 8 * s, (it >> 1) & 1);
     const float* row = rowbuf + (size_t)s * L.npad;
-    for (int k = tid; k < K; k += IMS_THREADS) {
+    // lanes 2i and 2i+1 share cluster k: each walks every other element (two independent dependent-load chains per
+    // cluster instead of one), then the pair is merged.  Order: (value, n) lexicographic = the reference's first maximum.
+    const int sub = tid & 1;
+    for (int k0 = 0; k0 < K; k0 += IMS_THREADS / 2) {
+      const int k = k0 + (tid >> 1);
       float best = -1000.0f;                                      // index_max_cuda.cu:38 / :71
-      int bn = 0;
-      bool has = false;
-      const int j1 = seg[k + 1];
-      for (int j = seg[k]; j < j1; ++j) {
-        const int n = perm[j];
-        const float v = row[n];
-        if (v > best || (has && v == best && n < bn)) { best = v; bn = n; has = true; }
+      int bn = 0x7fffffff;                                        // "nothing above the floor yet"
+      if (k < K) {
+        const int j1 = seg[k + 1];
+        for (int j = seg[k] + sub; j < j1; j += 2) {
+          const int n = perm[j];
+          const float v = row[n];
+          if (v > best || (v == best && n < bn && bn != 0x7fffffff)) { best = v; bn = n; }
+        }
       }
-      out[(size_t)r * K + k] = bn;
+      const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+      const int on = __shfl_xor_sync(0xffffffffu, bn, 1);
+      if (on != 0x7fffffff && (bn == 0x7fffffff || ob > best || (ob == best && on < bn))) { best = ob; bn = on; }
+      if (k < K && sub == 0) out[(size_t)r * K + k] = bn == 0x7fffffff ? 0 : bn;
     }
     __syncthreads();                                              // rowbuf[s] may be refilled from the next iteration on
   }
