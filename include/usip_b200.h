@@ -288,7 +288,7 @@ int usip_colsum(const float* G, int ldg, float* out, int P, int C, void* stream)
 int usip_head_bwd(const float* g_kp, const float* g_sig, const float* out4, int ld, float* G, int B, int M,
                   void* stream);
 /* gW[Cout,Cin] += GY[P,Cout]^T * act(X)[P,Cin], act = optional folded BN affine + ReLU (same prologue as forward);
- * precision 1: tcgen05 3xTF32 (MN-major operands) when Cout>=64, Cout%4==0, Cin%64==0, P>=4096 (a 64-wide layer fills half of the
+ * precision 1: tcgen05 3xTF32 (MN-major operands; precision 4: the same kernel as plain single-pass TF32) when Cout>=64, Cout%4==0, Cin%64==0, P>=4096 (a 64-wide layer fills half of the
  * 128-row UMMA tile with zero rows); Cin<=8 has an HBM-bound row-streaming kernel; otherwise the register-tiled fp32 SIMT kernel */
 int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale, const float* in_shift,
                int in_relu, float* gW, int ldw, int P, int Cout, int Cin, int precision, void* stream);

@@ -753,15 +753,15 @@ extern "C" int usip_head_bwd(const float* g_kp, const float* g_sig, const float*
 
 namespace usip {
 int wgrad_tc(const float* GY, int ldg, const float* X, int ldx, const float* sc, const float* sh, int relu, float* gW,
-             int ldw, int P, int Cout, int Cin, cudaStream_t st);   // wgrad_tc.cu (-2: shape not eligible)
+             int ldw, int P, int Cout, int Cin, int single, cudaStream_t st);   // wgrad_tc.cu (-2: shape not eligible)
 }
 
 extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, const float* in_scale,
                           const float* in_shift, int in_relu, float* gW, int ldw, int P, int Cout, int Cin,
                           int precision, void* stream) {
   USIP_REQUIRE(GY && X && gW && P > 0 && Cout > 0 && Cin > 0 && (!in_scale == !in_shift), "wgrad: bad args");
-  if (precision == 1) {
-    int rc = wgrad_tc(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin, (cudaStream_t)stream);
+  if (precision == 1 || precision == 4) {            // 1: 3xTF32 (fp32-equivalent), 4: plain TF32 (one MMA per MAC)
+    int rc = wgrad_tc(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin, precision == 4, (cudaStream_t)stream);
     if (rc != -2) return rc;
   }
   if (Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) && P >= 4096) {

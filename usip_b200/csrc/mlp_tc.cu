@@ -238,7 +238,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           }
         }
         tmem_st8(a_t + 8 * jj, hi);
-        tmem_st8(a_t + 32 + 8 * jj, lo);
+        if (!(d.debug_flags & 8)) tmem_st8(a_t + 32 + 8 * jj, lo);
       }
       fetch(it + 2);                                 // next own chunk: in flight while the stores drain and the MMAs run
       tmem_st_wait();
@@ -399,12 +399,17 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           if (ATMEM) {
             const uint32_t at_hi = tmem_base + 2 * BN + s * 64, at_lo = at_hi + 32;       // A stage in tensor memory
             const uint32_t bt_hi = stage_base + s * SM::STAGE, bt_lo = bt_hi + BN * 128;
+            const bool single = (d.debug_flags & 8) != 0;     // plain TF32 (hi x hi only): the backward-precision option
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t dbh = make_kmajor_sw128_desc(bt_hi + ks * 32), dbl = make_kmajor_sw128_desc(bt_lo + ks * 32);
-              umma_tf32_ts(tmem_d, at_lo + ks * 8, dbh, idesc, (kc | ks) != 0);
-              umma_tf32_ts(tmem_d, at_hi + ks * 8, dbl, idesc, 1u);
-              umma_tf32_ts(tmem_d, at_hi + ks * 8, dbh, idesc, 1u);
+              if (single) {
+                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbh, idesc, (kc | ks) != 0);
+              } else {
+                umma_tf32_ts(tmem_d, at_lo + ks * 8, dbh, idesc, (kc | ks) != 0);
+                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbl, idesc, 1u);
+                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbh, idesc, 1u);
+              }
             }
           } else if (MIXED) {
             // a*w ~= tf32(a_hi*w_hi) + bf16(a_lo)*bf16(w_hi) + bf16(a_hi)*bf16(w_lo): the cross terms are 2^-11 of the

@@ -63,7 +63,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__ X, int ldx,
                 const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu,
-                float* __restrict__ gW, int ldw, int P, int Cout, int Cin, int rows_per_cta) {
+                float* __restrict__ gW, int ldw, int P, int Cout, int Cin, int rows_per_cta, int single) {
   using SM = WtSmem<BN, STAGES>;
   constexpr int MBA = 4, MBB = BN / 32;
   extern __shared__ uint8_t wt_smem_raw[];
@@ -178,9 +178,13 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
           // k-step kg covers stage rows 8kg..8kg+7 = two 4-row groups, each (blocks * 512) B
           const uint64_t dah = wt_desc_mn(a_hi + kg * MBA * 1024, 512, MBA * 512), dal = wt_desc_mn(a_lo + kg * MBA * 1024, 512, MBA * 512);
           const uint64_t dbh = wt_desc_mn(b_hi + kg * MBB * 1024, 512, MBB * 512), dbl = wt_desc_mn(b_lo + kg * MBB * 1024, 512, MBB * 512);
-          wt_umma(tmem_d, dal, dbh, idesc, (it | kg) != 0);
-          wt_umma(tmem_d, dah, dbl, idesc, 1u);
-          wt_umma(tmem_d, dah, dbh, idesc, 1u);
+          if (single) {                                  // plain TF32: hi x hi only (backward-precision option)
+            wt_umma(tmem_d, dah, dbh, idesc, (it | kg) != 0);
+          } else {
+            wt_umma(tmem_d, dal, dbh, idesc, (it | kg) != 0);
+            wt_umma(tmem_d, dah, dbl, idesc, 1u);
+            wt_umma(tmem_d, dah, dbh, idesc, 1u);
+          }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty_bar(s)) : "memory");
         if (it == nst - 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done_bar) : "memory");
@@ -230,7 +234,7 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
 
 template <int BN, int STAGES>
 static int launch_wgrad_tc(const float* GY, int ldg, const float* X, int ldx, const float* sc, const float* sh, int relu,
-                           float* gW, int ldw, int P, int Cout, int Cin, cudaStream_t st) {
+                           float* gW, int ldw, int P, int Cout, int Cin, int single, cudaStream_t st) {
   using SM = WtSmem<BN, STAGES>;
   static_assert(SM::BYTES <= 232448, "shared memory budget");
   static bool attr = false;
@@ -244,20 +248,20 @@ static int launch_wgrad_tc(const float* GY, int ldg, const float* X, int ldx, co
   int rows = cdiv(cdiv(P, splits), WT_BK) * WT_BK;
   splits = cdiv(P, rows);
   dim3 grid(splits, cdiv(Cout, 128), Cin / BN);
-  wgrad_tc_kernel<BN, STAGES><<<grid, WT_THREADS, SM::BYTES, st>>>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, rows);
+  wgrad_tc_kernel<BN, STAGES><<<grid, WT_THREADS, SM::BYTES, st>>>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, rows, single);
   return check_launch("wgrad_tc_kernel");
 }
 
 // returns -2 when the shape is not eligible (caller falls back to the SIMT kernel)
 int wgrad_tc(const float* GY, int ldg, const float* X, int ldx, const float* sc, const float* sh, int relu, float* gW,
-             int ldw, int P, int Cout, int Cin, cudaStream_t st) {
+             int ldw, int P, int Cout, int Cin, int single, cudaStream_t st) {
   const bool ok = (Cout % 4 == 0) && (Cout >= 64) && (Cin % 64 == 0) && P >= 4096 && (ldg % 4 == 0) && (ldx % 4 == 0) &&
                   (reinterpret_cast<uintptr_t>(GY) % 16 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) &&
                   (!sc || (reinterpret_cast<uintptr_t>(sc) % 16 == 0 && reinterpret_cast<uintptr_t>(sh) % 16 == 0));
   if (!ok) return -2;
-  if (Cin % 256 == 0) return launch_wgrad_tc<256, 2>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, st);
-  if (Cin % 128 == 0) return launch_wgrad_tc<128, 3>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, st);
-  return launch_wgrad_tc<64, 4>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, st);
+  if (Cin % 256 == 0) return launch_wgrad_tc<256, 2>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, single, st);
+  if (Cin % 128 == 0) return launch_wgrad_tc<128, 3>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, single, st);
+  return launch_wgrad_tc<64, 4>(GY, ldg, X, ldx, sc, sh, relu, gW, ldw, P, Cout, Cin, single, st);
 }
 
 }  // namespace usip

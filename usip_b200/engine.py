@@ -355,6 +355,9 @@ class _Bwd:
         self.check = _lib.check
         self.dev = dev
         self.use_tc = use_tc
+        # opt.backward_precision: "3xtf32" (default, fp32-equivalent like the forward) or "tf32" -- the dgrad / wgrad GEMMs as
+        # ONE TF32 MMA per MAC, the arithmetic PyTorch's default cuDNN path gives the reference's backward
+        self.tf32_bwd = str(getattr(getattr(net, "opt", None), "backward_precision", "3xtf32")).lower() == "tf32"
         params = list(net.parameters())
         # usip_b200.optim.FlatAdam publishes a view of its flat gradient buffer on every parameter: accumulate straight
         # into it (autograd's own semantics for an existing .grad) and hand autograd nothing to add.  Without it (a
@@ -430,7 +433,7 @@ class _Bwd:
                    precision="3xTF32 tcgen05" if tc else "fp32 SIMT"):
             self.check(self.lib.usip_wgrad(p(GY), GY.stride(0), p(X), X.stride(0), None if prev is None else p(prev.scale),
                                            None if prev is None else p(prev.shift), 1 if (relu or prev is not None) else 0,
-                                           p(gW), gW.stride(0), P, Cout, Cin, 1 if self.use_tc else 0, s), "usip_wgrad")
+                                           p(gW), gW.stride(0), P, Cout, Cin, (4 if self.tf32_bwd else 1) if self.use_tc else 0, s), "usip_wgrad")
 
     def dgrad(self, GY, W2d, P, name="dgrad", out=None):
         """G_in[P,Cin] = GY[P,Cout] @ W2d[Cout,Cin] (the forward weight, used transposed by the layer kernel)."""
@@ -441,7 +444,8 @@ class _Bwd:
         ws, packed = _tc_workspace(W2d, P, Cout, Cin, 0, True, prec) if prec else (None, False)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
-            ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed)
+            ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed,
+                          debug_flags=8 if (self.tf32_bwd and prec == 3) else 0)
         return out
 
     def colsum(self, G, out, P, C):
