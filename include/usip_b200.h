@@ -133,17 +133,17 @@ typedef struct usip_layer_desc {
   float* gmax; float* gmin;            /* [P/group,Cout] per-group max / min of Y, or NULL            */
   int32_t* garg_max; int32_t* garg_min;/* [P/group,Cout] row-in-group of the max / min, or NULL       */
   int32_t group;
-  int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0),
-                                          2 = same, CTA-pair (cta_group::2) kernel where eligible, 3 = alias of 1 */
+  int32_t precision;                   /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05 (Cin%32==0, Cout%64==0) */
   void* tc_workspace;                  /* precision 1: >= usip_layer_tc_workspace_bytes(Cin,Cout) bytes */
   int64_t tc_workspace_bytes;
   int32_t tc_weights_packed;           /* 1: tc_workspace already holds the packed weights of this W  */
   int32_t debug_flags;                 /* profiling aids of the tcgen05 kernel, 0 in production (tools/tc_microbench.py).
                                           Results become WRONG with: 1 = skip the epilogue body, 2 = producers skip the X
-                                          loads, 4 = no weight TMA, 8 = issue 1 of the 3 MMAs, 32 = no Y stores, 64 = no
-                                          statistics / group pass.  Results stay correct with: 16 = TF32 main product + two
-                                          BF16 cross terms instead of 3xTF32 (~1e-6 relative error), 128 = also prefetch X
-                                          tiles into L2 */
+                                          loads, 4 = no weight TMA, 32 = no Y stores, 64 = no statistics / group pass.
+                                          Results stay correct (at a different precision) with: 8 = plain single-pass TF32
+                                          (hi x hi product only, ~5e-4 relative: the backward-precision option of the train
+                                          step), 16 = TF32 main product + two BF16 cross terms instead of 3xTF32 (~1e-6
+                                          relative error); 128 = also prefetch X tiles into L2 */
   unsigned long long* debug_clocks;    /* [grid][17 warps][8] clock64() accumulators (lane 0 of each warp): where each warp
                                           role spends its time.  Only written by a library built with -DUSIP_TC_PROF
                                           (USIP_NVCC_EXTRA); NULL = off */

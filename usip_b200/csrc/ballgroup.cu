@@ -85,19 +85,21 @@ __device__ BxGrid bx_make_grid(const float* __restrict__ cp, int M, float radius
   if (e[1] < e[drop]) drop = 1;
   if (e[2] < e[drop]) drop = 2;
   g.a0 = drop == 0 ? 1 : 0; g.a1 = drop == 2 ? 1 : 2;
+  const float e0 = bx_axis(e[0], e[1], e[2], g.a0), e1 = bx_axis(e[0], e[1], e[2], g.a1);       // (selects, no local arrays)
+  const float lo0 = bx_axis(lo[0], lo[1], lo[2], g.a0), lo1 = bx_axis(lo[0], lo[1], lo[2], g.a1);
   float h = fmaxf(radius * 1.001f, 1e-6f);
   int n0 = 1, n1 = 1;
   if (g.ok) {
     for (int it = 0; it < 96; ++it) {
       // two margin cells on either side: a centre's cell index stays in [1, n-2] whatever the last-bit rounding of
       // (c - o) * inv_h does, so its 3 x 3 block never leaves the grid
-      n0 = (int)fminf(floorf(e[g.a0] / h), 1e6f) + 5; n1 = (int)fminf(floorf(e[g.a1] / h), 1e6f) + 5;
+      n0 = (int)fminf(floorf(e0 / h), 1e6f) + 5; n1 = (int)fminf(floorf(e1 / h), 1e6f) + 5;
       if ((long long)n0 * n1 <= BX_MAX_CELLS) break;
       h *= 1.26f;
     }
     if ((long long)n0 * n1 > BX_MAX_CELLS) g.ok = 0;
   }
-  g.o0 = lo[g.a0] - 2.f * h; g.o1 = lo[g.a1] - 2.f * h; g.inv_h = 1.0f / h; g.n0 = n0; g.n1 = n1;
+  g.o0 = lo0 - 2.f * h; g.o1 = lo1 - 2.f * h; g.inv_h = 1.0f / h; g.n0 = n0; g.n1 = n1;
   return g;
 }
 
@@ -108,18 +110,16 @@ bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
   __shared__ float red[6][8];
   const int b = blockIdx.y, tid = threadIdx.x;
   const float* p = xyz + (size_t)b * 3 * N;
-  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow
+  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow.  Everything
+  // is indexed by compile-time constants (fully unrolled): no local-memory arrays.
   float px[4], py[4], pz[4], pf[4][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
-    px[j] = py[j] = pz[j] = NAN;
+    const bool in = n < N;
+    px[j] = in ? __ldg(p + n) : NAN; py[j] = in ? __ldg(p + N + n) : NAN; pz[j] = in ? __ldg(p + 2 * N + n) : NAN;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) pf[j][c] = 0.f;
-    if (n < N) {
-      px[j] = __ldg(p + n); py[j] = __ldg(p + N + n); pz[j] = __ldg(p + 2 * N + n);
-      for (int c = 0; c < S && c < 4; ++c) pf[j][c] = __ldg(feat + ((size_t)b * S + c) * N + n);
-    }
+    for (int c = 0; c < 4; ++c) pf[j][c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
   }
   const BxGrid g = bx_make_grid(centers + (size_t)b * 3 * M, M, radius, red);
   if (blockIdx.x == 0 && tid == 0) grids[b] = g;
@@ -128,24 +128,32 @@ bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
   if (!g.ok) return;
   int32_t* cnt = counts + (size_t)b * BX_MAX_CELLS;
   float4* bk = buckets + (size_t)b * BX_MAX_CELLS * BX_CAP * 2;
+  // all four fill-count atomics are issued before any of their results is used (four L2 round trips in flight)
+  int cell[4], slot[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
     const float x = px[j], y = py[j], z = pz[j];
-    if (!(fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f)) continue;    // never within a finite radius (also n >= N)
-    const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
-    if (!(f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1)) continue;  // farther than a cell from every centre
-    const int cell = (int)f1 * g.n0 + (int)f0;
-    const int slot = atomicAdd(cnt + cell, 1);
+    cell[j] = -1;
+    if (fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f) {            // non-finite (and n >= N): never within a finite radius
+      const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
+      if (f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1) cell[j] = (int)f1 * g.n0 + (int)f0;   // else: farther than a cell from every centre
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) slot[j] = cell[j] >= 0 ? atomicAdd(cnt + cell[j], 1) : 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (cell[j] < 0) continue;
+    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
     float4* dst;
-    if (slot < BX_CAP) {
-      dst = bk + ((size_t)cell * BX_CAP + slot) * 2;
+    if (slot[j] < BX_CAP) {
+      dst = bk + ((size_t)cell[j] * BX_CAP + slot[j]) * 2;
     } else {
       const int o = atomicAdd(ovf_cnt + b, 1);
       if (o >= BX_OVF) continue;                             // the query sees ovf_cnt > BX_OVF and scans the cloud in order
       dst = ovf + ((size_t)b * BX_OVF + o) * 2;
     }
-    dst[0] = make_float4(x, y, z, __int_as_float(n));
+    dst[0] = make_float4(px[j], py[j], pz[j], __int_as_float(n));
     dst[1] = make_float4(pf[j][0], pf[j][1], pf[j][2], pf[j][3]);
   }
 }
@@ -204,7 +212,7 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
       int fill = 0;                                               // lanes 0..8: fill count of bucket (lane / 3, lane % 3)
       if (lane < 9) fill = __ldcg(cnt + base + (lane / 3) * g.n0 + (lane % 3));
       const unsigned over = __ballot_sync(0xffffffffu, fill > BX_CAP);
-      mbar_wait(bar, 0);
+      mbar_wait_sleep(bar, 0);
       // 72 slots, 32 per pass: slot s belongs to bucket s / 8
       for (int s0 = 0; s0 < 9 * BX_CAP && !brute; s0 += 32) {
         const int s = s0 + lane;
@@ -282,13 +290,15 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
         n = u > 0 ? o[e] : 0;
         if (out_group || out_rows) {
           v[0] = __ldg(p + n) - cx; v[1] = __ldg(p + N + n) - cy; v[2] = __ldg(p + 2 * N + n) - cz;
-          for (int c = 0; c < S && c < 4; ++c) v[3 + c] = __ldg(pfeat + (size_t)c * N + n);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (c < S) v[3 + c] = __ldg(pfeat + (size_t)c * N + n);
         }
       }
       if (!brute || k >= u) o[k] = n;
       if (out_group) {
         float* gp = out_group + ((size_t)b * C * M + m) * K + k;
-        for (int c = 0; c < C; ++c) __stcs(gp + (size_t)c * M * K, v[c]);                 // streaming: written once, read by the next op
+#pragma unroll
+        for (int c = 0; c < 7; ++c) if (c < C) __stcs(gp + (size_t)c * M * K, v[c]);      // streaming: written once, read by the next op
       }
       if (out_rows) {
         float* rowp = out_rows + ((size_t)w * K + k) * ld_rows;
@@ -296,7 +306,9 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
           __stcs(reinterpret_cast<float4*>(rowp), make_float4(v[0], v[1], v[2], v[3]));
           __stcs(reinterpret_cast<float4*>(rowp) + 1, make_float4(v[4], v[5], v[6], v[7]));
         } else {
-          for (int c = 0; c < ld_rows; ++c) rowp[c] = c < C ? v[c] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) if (c < ld_rows) rowp[c] = c < C ? v[c] : 0.f;
+          for (int c = 8; c < ld_rows; ++c) rowp[c] = 0.f;
         }
       }
     }

@@ -559,7 +559,7 @@ extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
   }
   if (d.addend) USIP_REQUIRE(d.add_index || d.add_group > 0, "layer_fwd: addend needs add_index or add_group");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d.precision >= 1 && d.precision <= 3) return layer_fwd_tc(d, st);
+  if (d.precision == 1) return layer_fwd_tc(d, st);
   if (d.Cout <= 8 && !d.stat_partial && !d.gmax && !d.gmin && !d.addend && (size_t)(8 + 2) * d.Cin * 4 <= 48 * 1024) {
     const size_t smem = (size_t)(8 + 2) * d.Cin * sizeof(float);
     layer_fwd_rowwarp_kernel<8><<<cdiv(d.P, 8), 256, smem, st>>>(d);

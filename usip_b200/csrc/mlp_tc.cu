@@ -67,7 +67,7 @@ __device__ __forceinline__ uint32_t bf16_tile_off(int r, int c) {
 // ------------------------------------------------------------------------------------------------
 // weight pre-pack: W[Cout,Cin] (row stride ldw) -> per (n_tile, k_chunk) one contiguous, pre-swizzled block, so a
 // stage's B operand is a single bulk copy.
-//   mixed == 0 (CTA-pair kernel, 3xTF32): [w_hi | w_lo], TF32, BN x 128 B each, SWIZZLE_128B
+//   mixed == 0 (3xTF32, the default):     [w_hi | w_lo], TF32, BN x 128 B each, SWIZZLE_128B
 //   mixed == 1 (this kernel):             [w_hi TF32, BN x 128 B, SWIZZLE_128B | bf16(w_hi), BN x 64 B, SWIZZLE_64B |
 //                                          bf16(w - w_hi), BN x 64 B, SWIZZLE_64B]          (same 256 B per row)
 // ------------------------------------------------------------------------------------------------
@@ -104,31 +104,21 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_AFF_MAX = 1024;            // A-through-TMEM variant: input channels whose folded BN affine is staged in smem
-
-// ATMEM: the A operand (activations) is written by the producers straight into TENSOR MEMORY (tcgen05.st) and consumed by
-// tcgen05.mma from there; only the weights cross shared memory.  In the all-smem variant one K=8 step moves 60 KB through
-// the SM's 128 B/clk shared-memory pipe (3 MMAs x (4 KB A + 8 KB B) reads, 8 KB A + 16 KB B writes) in the 375 clk its
-// MMAs take at N=256 -- the pipe, not the tensor core, is the bound (ncu: tensor pipe 82 % active, smem data pipe
-// saturated).  With A in TMEM the same step moves 40 KB.
-template <int BN, int STAGES, bool COMBINE, bool MIXED, bool ATMEM = false>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 struct TcSmem {
-  static constexpr int A_STAGE = ATMEM ? 0 : 2 * TC_BM * 128;     // 3xTF32: hi + lo;  mixed: hi (128 B rows) + 2 BF16 tiles (64 B rows)
+  static constexpr int A_STAGE = 2 * TC_BM * 128;                 // 3xTF32: hi + lo;  mixed: hi (128 B rows) + 2 BF16 tiles (64 B rows)
   static constexpr int B_STAGE = 2 * BN * 128;
   static constexpr int STAGE = A_STAGE + B_STAGE;
   static constexpr int TRANS = TC_EPI_WARPS * 32 * 32 * 4;       // per-warp 32x32 staging tile, XOR-swizzled 16B chunks
   static constexpr int COMB = COMBINE ? 4 * 4 * BN * 4 : 0;      // max, min, argmax, argmin per lane quarter (group > 32 only)
-  static constexpr int AFF = ATMEM ? 2 * TC_AFF_MAX * 4 : 0;     // folded BN scale / shift of the input channels
   static constexpr int BARS = 256;
-  static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + AFF + BARS + 1024;   // +1024 alignment slack
+  static constexpr int BYTES = STAGES * STAGE + TRANS + COMB + BARS + 1024;   // +1024 alignment slack
 };
 
-template <int BN, int STAGES, bool COMBINE, bool MIXED, bool ATMEM = false>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack) {
-  using SM = TcSmem<BN, STAGES, COMBINE, MIXED, ATMEM>;
-  static_assert(!(ATMEM && MIXED), "the A-through-TMEM variant is pure 3xTF32");
-  static_assert(!ATMEM || 2 * BN + STAGES * 64 <= 512, "accumulators + A stages must fit the 512 TMEM columns");
+  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
   constexpr int BK = TC_BK;                          // 32 floats per K chunk
   constexpr int CPR = BK / 4;                        // 16-byte chunks per fp32 operand row
   constexpr int DEPTH = 1;                           // register-prefetched X chunks per producer thread
@@ -139,9 +129,8 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   const uint32_t stage_base = smem_base;
   float* trans = reinterpret_cast<float*>(smem + STAGES * SM::STAGE);
   float* comb = reinterpret_cast<float*>(smem + STAGES * SM::STAGE + SM::TRANS);
-  float* s_aff = reinterpret_cast<float*>(smem + STAGES * SM::STAGE + SM::TRANS + SM::COMB);      // ATMEM only
-  const uint32_t bar_base = smem_base + STAGES * SM::STAGE + SM::TRANS + SM::COMB + SM::AFF;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * SM::STAGE + SM::TRANS + SM::COMB + SM::AFF + 192);
+  const uint32_t bar_base = smem_base + STAGES * SM::STAGE + SM::TRANS + SM::COMB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + STAGES * SM::STAGE + SM::TRANS + SM::COMB + 192);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
@@ -152,8 +141,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
   const int KC = Cin / BK;
   const int m_tiles = (P + TC_BM - 1) / TC_BM, n_tiles = Cout / BN;
   const int num_tiles = m_tiles * n_tiles;
-  constexpr int TMEM_NEED = 2 * BN + (ATMEM ? STAGES * 64 : 0);   // two accumulators (+ hi/lo A stages of 32 columns each)
-  constexpr uint32_t TMEM_COLS = (TMEM_NEED <= 32) ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
 
   if (warp == TC_MMA_WARP) {
     if (lane == 0) {
@@ -181,71 +169,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
 #define TICK(k) do { } while (0)
 #endif
 
-  if (ATMEM && warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_PROD_WARPS) {
-    // =============================== A producers, tensor-memory variant ===========================
-    // thread = one row of the 128-row tile = one TMEM lane (warp w owns lanes 32*(w%4)..+31); the two groups of four
-    // warps alternate over the K chunks as in the shared-memory variant
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
-    const int pw = warp - TC_PROD_WARP0, grp = pw >> 2, q = pw & 3;
-    const int prow = q * 32 + lane;
-    const bool lead = (q == 0 && lane == 0);
-    const bool has_aff = d.in_scale != nullptr;
-    const float relu_floor = d.in_relu ? 0.f : -INFINITY;
-    for (int i = pw * 32 + lane; i < Cin; i += TC_PROD_WARPS * 32) {
-      s_aff[i] = has_aff ? __ldg(d.in_scale + i) : 1.f;
-      s_aff[TC_AFF_MAX + i] = has_aff ? __ldg(d.in_shift + i) : 0.f;
-    }
-    named_bar_sync(2, TC_PROD_WARPS * 32);
-    const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t total_it = (uint32_t)max(my_tiles, 0) * (uint32_t)KC;
-    float4 xr[8];                                    // this thread's row slice of its next K chunk (register prefetch)
-    auto fetch = [&](uint32_t it2) {
-      if (it2 >= total_it) return;
-      const int tile2 = (int)blockIdx.x + (int)(it2 / KC) * (int)gridDim.x;
-      const int row = (tile2 / n_tiles) * TC_BM + prow;
-      const float4* src = reinterpret_cast<const float4*>(d.X + (size_t)row * d.ldx + (int)(it2 % KC) * BK);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xr[j] = row < P ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fetch((uint32_t)grp);
-    for (uint32_t it = (uint32_t)grp; it < total_it; it += 2) {
-      const int tile = (int)blockIdx.x + (int)(it / KC) * (int)gridDim.x;
-      const int kc = (int)(it % KC), nt = tile % n_tiles;
-      const int s = it % STAGES;
-      mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
-      tc_fence_after();                              // the MMAs that read this A stage have retired (commit -> mbarrier)
-      if (lead) {
-        mbar_arrive_expect_tx(full_bar(s), SM::B_STAGE);
-        bulk_g2s(stage_base + s * SM::STAGE, wpack + ((size_t)nt * KC + kc) * 2 * (size_t)BN * BK, SM::B_STAGE, full_bar(s));
-      }
-      const uint32_t a_t = tmem_base + 2 * BN + s * 64 + ((uint32_t)(q * 32) << 16);
-      const float4* sc4 = reinterpret_cast<const float4*>(s_aff + kc * BK);
-      const float4* sh4 = reinterpret_cast<const float4*>(s_aff + TC_AFF_MAX + kc * BK);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 x = xr[2 * jj + h], sc = sc4[2 * jj + h], sh = sh4[2 * jj + h];   // broadcast shared loads
-          const float v[4] = {fmaxf(fmaf(x.x, sc.x, sh.x), relu_floor), fmaxf(fmaf(x.y, sc.y, sh.y), relu_floor),
-                              fmaxf(fmaf(x.z, sc.z, sh.z), relu_floor), fmaxf(fmaf(x.w, sc.w, sh.w), relu_floor)};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[4 * h + e] = (__float_as_uint(v[e]) + 0x1000u) & 0xffffe000u;                // rna_tf32 for finite inputs
-            lo[4 * h + e] = (__float_as_uint(v[e] - __uint_as_float(hi[4 * h + e])) + 0x1000u) & 0xffffe000u;
-          }
-        }
-        tmem_st8(a_t + 8 * jj, hi);
-        if (!(d.debug_flags & 8)) tmem_st8(a_t + 32 + 8 * jj, lo);
-      }
-      fetch(it + 2);                                 // next own chunk: in flight while the stores drain and the MMAs run
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(full_bar(s));
-    }
-  } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_PROD_WARPS) {
+  if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_PROD_WARPS) {
     // =============================== A producers (+ weight bulk copies) ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
     const int pw = warp - TC_PROD_WARP0;            // 0..7
@@ -345,7 +269,8 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
 #pragma unroll
           for (int q = 0; q < 4; ++q) split4(v[q], hi[q], lo[q]);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          if (!(d.debug_flags & 8))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
       }
       TICK(1);
@@ -396,22 +321,7 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
           const uint32_t a_lo = a_hi + TC_BM * 128;
           const uint32_t b_hi = a_hi + SM::A_STAGE;
           const uint32_t b_lo = b_hi + BN * 128;
-          if (ATMEM) {
-            const uint32_t at_hi = tmem_base + 2 * BN + s * 64, at_lo = at_hi + 32;       // A stage in tensor memory
-            const uint32_t bt_hi = stage_base + s * SM::STAGE, bt_lo = bt_hi + BN * 128;
-            const bool single = (d.debug_flags & 8) != 0;     // plain TF32 (hi x hi only): the backward-precision option
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t dbh = make_kmajor_sw128_desc(bt_hi + ks * 32), dbl = make_kmajor_sw128_desc(bt_lo + ks * 32);
-              if (single) {
-                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbh, idesc, (kc | ks) != 0);
-              } else {
-                umma_tf32_ts(tmem_d, at_lo + ks * 8, dbh, idesc, (kc | ks) != 0);
-                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbl, idesc, 1u);
-                umma_tf32_ts(tmem_d, at_hi + ks * 8, dbh, idesc, 1u);
-              }
-            }
-          } else if (MIXED) {
+          if (MIXED) {
             // a*w ~= tf32(a_hi*w_hi) + bf16(a_lo)*bf16(w_hi) + bf16(a_hi)*bf16(w_lo): the cross terms are 2^-11 of the
             // product, so 8 mantissa bits leave ~2^-19 relative error -- fp32-sgemm level (tools/tc_precision.py) --
             // at 2/3 of the tensor time and shared-memory operand traffic of 3xTF32.
@@ -432,8 +342,10 @@ layer_fwd_tc_kernel(const usip_layer_desc d, const uint32_t* __restrict__ wpack)
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t dah = make_kmajor_sw128_desc(a_hi + ks * 32), dal = make_kmajor_sw128_desc(a_lo + ks * 32);
               const uint64_t dbh = make_kmajor_sw128_desc(b_hi + ks * 32), dbl = make_kmajor_sw128_desc(b_lo + ks * 32);
-              umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
-              if (!(d.debug_flags & 8)) {
+              if (d.debug_flags & 8) {                       // plain TF32: hi x hi only (backward-precision option)
+                umma_tf32(tmem_d, dah, dbh, idesc, (kc | ks) != 0);
+              } else {
+                umma_tf32(tmem_d, dal, dbh, idesc, (kc | ks) != 0);
                 umma_tf32(tmem_d, dah, dbl, idesc, 1u);
                 umma_tf32(tmem_d, dah, dbh, idesc, 1u);
               }
@@ -678,31 +590,27 @@ static int tc_sm_count() {
   return sm_count;
 }
 
-template <int BN, int STAGES, bool COMBINE, bool MIXED, bool ATMEM = false>
+template <int BN, int STAGES, bool COMBINE, bool MIXED>
 static int launch_tc(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st) {
-  using SM = TcSmem<BN, STAGES, COMBINE, MIXED, ATMEM>;
+  using SM = TcSmem<BN, STAGES, COMBINE, MIXED>;
   static_assert(SM::BYTES <= 232448, "shared memory budget");
   static bool attr_set = false;
   const int sm_count = tc_sm_count();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED, ATMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES);
     if (e != cudaSuccess) { set_last_error("layer_fwd_tc smem attr"); return (int)e; }
     attr_set = true;
   }
   const int grid = tc_grid(d.P, d.Cout, BN, sm_count);
-  layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED, ATMEM><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
+  layer_fwd_tc_kernel<BN, STAGES, COMBINE, MIXED><<<grid, TC_THREADS, SM::BYTES, st>>>(d, wpack);
   return check_launch("layer_fwd_tc_kernel");
 }
-
-bool tc2_eligible(const usip_layer_desc& d);                                   // mlp_tc2.cu
-int launch_tc2(const usip_layer_desc& d, const uint32_t* wpack, cudaStream_t st);
 
 int tc_tile_n(int Cout) { return Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64); }
 
 // column-tile width the single-CTA kernel will use for this layer
 static int tc_pick_bn(const usip_layer_desc& d) {
   int BN = tc_tile_n(d.Cout);
-  if (d.precision == 3 && BN > 128) BN = 128;                         // A-through-TMEM: 2 accumulators + 4 A stages in 512 columns
   if ((d.gmax || d.gmin) && d.group > 32 && BN > 128) BN = 128;       // cross-warp group combine needs the small tile
   // few row tiles (node-level GEMMs): narrower column tiles fill more SMs
   while (BN > 64 && (long long)cdiv(d.P, TC_BM) * (d.Cout / BN) < 120 && d.Cout % (BN / 2) == 0) BN /= 2;
@@ -711,7 +619,6 @@ static int tc_pick_bn(const usip_layer_desc& d) {
 
 // number of [2, Cout] BN-statistic partial rows usip_layer_fwd writes for this descriptor (tensor-core precisions)
 int tc_stat_slots(const usip_layer_desc& d) {
-  if (d.precision == 2 && d.Cout % 256 == 0 && tc2_eligible(d)) return cdiv(d.P, TC_STAT_ROWS);   // pair kernel: per 32 rows
   const int BN = tc_pick_bn(d);
   return tc_grid(d.P, d.Cout, BN, tc_sm_count()) / (d.Cout / BN) * 4;
 }
@@ -727,27 +634,18 @@ int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {
   USIP_REQUIRE(d.tc_workspace && d.tc_workspace_bytes >= (int64_t)2 * d.Cout * d.Cin * 4, "layer_fwd_tc: workspace too small");
   if (d.gmax || d.gmin) USIP_REQUIRE(d.group == 16 || d.group == 32 || d.group == 64 || d.group == 128, "layer_fwd_tc: group must be 16/32/64/128");
   int BN = tc_pick_bn(d);
-  // precision 2 opts into the CTA-pair (cta_group::2) kernel for wide layers with enough tiles.  Measured on B200 it
-  // is ~10-25% SLOWER than the single-CTA kernel with register prefetch, so it is not the default.
   // default: pure 3xTF32.  debug_flags & 16 selects TF32 + 2 BF16 cross terms: measured on B200 it buys 2% (the kernel is
-  // not tensor-bound) and costs ~8x in error (still fp32-sgemm level, tools/tc_precision.py), so it stays an experiment.
+  // bound by its shared-memory pipe, not by the tensor pipe) and costs ~8x in error, so it stays an experiment.
+  // debug_flags & 8 issues the hi x hi product only: plain single-pass TF32, the backward-precision option of the train step.
   const bool x3 = (d.debug_flags & 16) == 0;
-  const bool atmem = d.precision == 3 && d.Cin <= TC_AFF_MAX;         // A operand through tensor memory (see TcSmem)
-  const bool pair = d.precision == 2 && d.Cout % 256 == 0 && tc2_eligible(d);
-  if (pair) BN = 256;
   uint32_t* wpack = reinterpret_cast<uint32_t*>(d.tc_workspace);
   if (!d.tc_weights_packed) {
     const int total = d.Cout * (d.Cin / 4);
-    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.w_transposed, d.Cout, d.Cin, BN, (pair || x3) ? 0 : 1, wpack);
+    tc_pack_weights_kernel<<<cdiv(total, 256), 256, 0, st>>>(d.W, d.ldw, d.w_transposed, d.Cout, d.Cin, BN, x3 ? 0 : 1, wpack);
     int e = check_launch("tc_pack_weights_kernel");
     if (e) return e;
   }
-  if (pair) return launch_tc2(d, wpack, st);
   const bool combine = (d.gmax || d.gmin) && d.group > 32;
-  if (atmem) {
-    if (combine) return BN == 128 ? launch_tc<128, 4, true, false, true>(d, wpack, st) : launch_tc<64, 4, true, false, true>(d, wpack, st);
-    return BN == 128 ? launch_tc<128, 4, false, false, true>(d, wpack, st) : launch_tc<64, 4, false, false, true>(d, wpack, st);
-  }
   if (x3) {
     if (combine) return BN == 128 ? launch_tc<128, 2, true, false>(d, wpack, st) : launch_tc<64, 3, true, false>(d, wpack, st);
     if (BN == 256) return launch_tc<256, 2, false, false>(d, wpack, st);

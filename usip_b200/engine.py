@@ -103,9 +103,7 @@ def invalidate_packed_weights(module):
 
 
 import os as _os
-# tensor-core kernel variant: 1 = operands through shared memory, 3 = A operand through tensor memory (tcgen05.st, TS-form
-# MMA; csrc/mlp_tc.cu TcSmem), 2 = CTA-pair kernel (measured slower, experiment only)
-_TC_PREC = 2 if _os.environ.get("USIP_TC_PAIR") else (1 if _os.environ.get("USIP_TC_SMEM_A") else 3)
+_TC_PREC = 1          # usip_layer_desc.precision of the tcgen05 3xTF32 kernel
 
 
 def _precision_for(P, Cin, Cout, use_tc, group=0):
@@ -445,7 +443,7 @@ class _Bwd:
         with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed,
-                          debug_flags=8 if (self.tf32_bwd and prec == 3) else 0)
+                          debug_flags=8 if (self.tf32_bwd and prec) else 0)
         return out
 
     def colsum(self, G, out, P, C):

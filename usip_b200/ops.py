@@ -240,13 +240,13 @@ def layer_fwd(X, W, bias, P, Cin, Cout, ldx=None, ldw=None, in_scale=None, in_sh
     d.precision = precision
     d.debug_flags = debug_flags
     d.debug_clocks = debug_clocks.data_ptr() if debug_clocks is not None else None
-    if precision in (1, 2, 3):
+    if precision == 1:
         if tc_ws is None:
             tc_ws = torch.empty((2 * Cin * Cout,), dtype=f32, device=X.device)
         d.tc_workspace = tc_ws.data_ptr(); d.tc_workspace_bytes = tc_ws.numel() * 4
         d.tc_weights_packed = 1 if tc_packed else 0
     check(_lib.load().usip_layer_fwd(ctypes.byref(d), _stream()),
-          "usip_layer_fwd_tc" if (precision in (1, 2, 3) and not tc_packed) else "usip_layer_fwd")
+          "usip_layer_fwd_tc" if (precision == 1 and not tc_packed) else "usip_layer_fwd")
 
 
 def bn_finalize(stat_partial, ntiles, count, C, gamma, beta, eps, momentum, running_mean, running_var,
