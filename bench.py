@@ -263,6 +263,7 @@ def main():
     ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT layers only")
     ap.add_argument("--train", action="store_true", help="(kept for compatibility: the train step is always timed)")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step record")
+    ap.add_argument("--no-tf32-backward", action="store_true", help="skip the extra train-step record with TF32 backward GEMMs")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip timing the reference's own GPU path (N=1 only)")
     ap.add_argument("--no-descriptor", action="store_true", help="skip the descriptor-path sub-record (N=1 only)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
@@ -441,6 +442,32 @@ def main():
                  "loss_after": float(md.loss)}
         assert np.isfinite(train["loss_after"])
 
+    # ---- the same train step with the backward GEMMs in plain single-pass TF32 (opt.backward_precision = "tf32": the
+    # arithmetic PyTorch's default cuDNN path gives the reference's backward).  A labelled extra, never the headline.
+    train_tf32 = None
+    if not args.no_train and world == 1 and not args.no_tf32_backward:
+        opt2 = make_opt(batch_size=cfg["B"], input_pc_num=cfg["N"], node_num=cfg["M"], surface_normal_len=cfg["S"],
+                        node_knn_k_1=cfg["Kn"], loss_sigma_lower_bound=cfg["lb"], keypoint_on_pc_alpha=cfg["alpha"],
+                        use_tensor_cores=not args.no_tc, device=dev, gpu_ids=[local], backward_precision="tf32")
+        md2 = ModelDetector(opt2)
+        load_params(md2.detector, P0)
+        md_main = md
+
+        def step_train2(i):
+            b = resident[i % nb]
+            md2.src_pc, md2.src_sn, md2.src_node = b["src_pc"], b["src_sn"], b["src_node"]
+            md2.dst_pc, md2.dst_sn, md2.dst_node = b["dst_pc"], b["dst_sn"], b["dst_node"]
+            md2.src_R_dst, md2.src_scale_dst, md2.src_shift_dst = b["R"], b["scale"], b["shift"]
+            md2.optimize(epoch=0)
+        for i in range(W):
+            step_train2(i)
+        ms_t2, l_t2 = timed(step_train2, K)
+        train_tf32 = {"value": clouds * K / (ms_t2 * 1e-3), "unit": "clouds/s", "ms_per_step": ms_t2 / K, "gpu_launches": l_t2,
+                      "includes": "as train_step, but dgrad / wgrad GEMMs as one TF32 MMA per MAC (forward stays 3xTF32)",
+                      "loss_after": float(md2.loss)}
+        del md2
+        torch.cuda.empty_cache()
+
     # ---- N=1 extras: the reference's own GPU path on the same tensors, the descriptor path, the CPU baseline
     ref_gpu = desc = cb = None
     if rank == 0 and world == 1:
@@ -476,6 +503,8 @@ def main():
             line["cpu_baseline"] = cb
         if train:
             line["train_step"] = train
+        if train_tf32:
+            line["train_step_tf32_backward"] = train_tf32
         if ref_gpu:
             line["reference_gpu"] = ref_gpu
         if desc:

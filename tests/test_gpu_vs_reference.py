@@ -218,6 +218,8 @@ def test_detector_full_size_vs_reference_gpu(ref, name):
             # tolerance, at most 2*lr apart where it is noise (dead channels, |g| ~ 1e-8)
             gr = np.abs(r_grad[k])
             big = gr > 0.2 * gr.max()
+            if k.endswith("conv.bias") and np.linalg.norm(r64_grad[k]) < 1e-6 * np.linalg.norm(r64_grad[k.replace("bias", "weight")]):
+                big[:] = False                                  # analytically zero gradient: the reference steps on rounding noise
             assert np.abs(a - b_).max() <= 2.0 * lr * 1.0001 + 1e-7, k
             if big.any():
                 assert np.abs(a - b_)[big].max() <= 0.02 * lr + 1e-7, (k, np.abs(a - b_)[big].max())
