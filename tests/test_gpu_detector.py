@@ -395,10 +395,11 @@ def test_ablation_detectors_vs_reference_golden(mode, use_tc):
             continue
         e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
         e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
-        # element tolerance: two max-pools over K = 64 (half of the rows cyclic duplicates in ball mode) route whole
-        # gradients through single arg-max rows; one decision flipped by a 1e-7 forward difference moves an element by
-        # ~1e-2 of max|g| (tests/test_gpu_vs_reference.py measures the reference's own fp32-vs-fp64 spread at this level)
-        assert e_norm < 5e-3 and e_el < 3e-2, (k, e_norm, e_el)
+        # element tolerance: two max-pools over K = 64 route whole gradients through single arg-max rows, and this fixture
+        # has only B*M = 64 groups per channel: ONE arg-max decision flipped by a 1e-7 forward difference moves a sum by
+        # 1/64 .. 1/8 of a typical term, i.e. percent level (tests/test_gpu_vs_reference.py measures the reference's own
+        # fp32-vs-fp64 spread: 1.4e-2 with 8192 groups per channel).  The norm is the tight check.
+        assert e_norm < 5e-3 and e_el < 5e-2, (k, e_norm, e_el)
     sd = net.state_dict()
     for k in sd:
         if k.endswith("running_mean") or k.endswith("running_var"):

@@ -423,20 +423,34 @@ wgrad_narrow_kernel(const float* __restrict__ GY, int ldg, const float* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = (in_scale && j < Cin) ? in_scale[j] : 1.f; sh[j] = (in_shift && j < Cin) ? in_shift[j] : 0.f; }
   const bool x8 = (ldx == 8) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  for (long long r = (long long)blockIdx.x * rpp + rl; r < P; r += (long long)gridDim.x * rpp) {
-    const float g = __ldcs(GY + (size_t)r * ldg + m);
-    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (x8) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8)), b = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8 + 4));
-      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-    } else {
-      for (int j = 0; j < Cin; ++j) x[j] = __ldg(X + (size_t)r * ldx + j);
+  const long long step = (long long)gridDim.x * rpp;
+  for (long long r0 = (long long)blockIdx.x * rpp + rl; r0 < P; r0 += 4 * step) {
+    float g[4];
+    float4 xa[4], xb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                              // four independent rows in flight per thread
+      const long long r = r0 + u * step;
+      g[u] = 0.f; xa[u] = xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < P) {
+        g[u] = __ldcs(GY + (size_t)r * ldg + m);
+        if (x8) {
+          xa[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8)); xb[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8 + 4));
+        } else {
+          float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < Cin; ++j) t[j] = __ldg(X + (size_t)r * ldx + j);
+          xa[u] = make_float4(t[0], t[1], t[2], t[3]); xb[u] = make_float4(t[4], t[5], t[6], t[7]);
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = fmaf(x[j], sc[j], sh[j]);
-      if (in_relu) v = fmaxf(v, 0.f);
-      acc[j] = fmaf(g, j < Cin ? v : 0.f, acc[j]);
+    for (int u = 0; u < 4; ++u) {
+      const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(x[j], sc[j], sh[j]);
+        if (in_relu) v = fmaxf(v, 0.f);
+        acc[j] = fmaf(g[u], j < Cin ? v : 0.f, acc[j]);      // rows past P carry g = 0
+      }
     }
   }
 #pragma unroll
@@ -766,7 +780,7 @@ extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, con
   }
   if (Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) && P >= 4096) {
     const int rpp = 256 / Cout;
-    const int blocks = (int)min((long long)cdiv(P, rpp * 8), 148LL * 8);
+    const int blocks = (int)min((long long)cdiv(P, rpp * 8), 148LL * 2);      // few CTAs: each ends in Cout*Cin atomics on the same words
     wgrad_narrow_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin);
     return check_launch("wgrad_narrow_kernel");
   }
