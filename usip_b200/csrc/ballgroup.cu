@@ -6,9 +6,10 @@
 //                    into fixed-capacity buckets: slot = atomicAdd(count[cell]); record (x,y,z,index | f0..f3) -> bucket
 //                    [cell][slot], or -> the cloud's overflow list when the bucket is full.  No histogram, no scan, no
 //                    second pass: points farther than a cell from every centre are dropped on the spot.
-//   bx_query_kernel  one warp per keypoint: the 3 x 3 neighbouring buckets are three contiguous 768-byte rows; one elected
-//                    lane fetches them with three cp.async.bulk copies (TMA, mbarrier complete_tx) while nine lanes read
-//                    the nine fill counts; warp-ballot radius test on the staged records; hits are ranked by point index
+//   bx_query_kernel  one warp per keypoint: the 3 x 3 neighbouring buckets are a 768-byte x 3-row box of the cloud's bucket
+//                    plane (fixed pitch of 128 cells); one elected lane fetches the box with ONE tensor-map TMA
+//                    (cp.async.bulk.tensor.3d, mbarrier complete_tx; out-of-range parts are zero-filled by the hardware)
+//                    while nine lanes read the nine fill counts; warp-ballot radius test on the staged records; hits are ranked by point index
 //                    (the reference keeps the FIRST K hits in index order) and index, gathered record and decentred
 //                    group are written in one pass of full 128-byte lines.  The last CTA of a cloud to finish clears the
 //                    counts again, so the scratch is left as it was found: all-zero counters.
@@ -18,14 +19,17 @@
 // more than 64 hits, K > 64 and non-finite radii take the reference's own in-order scan (bit-identical by construction).
 #include "tc_common.cuh"
 #include <cstdlib>
+#include <cuda.h>           // CUtensorMap types only; the encoder is resolved at run time
 
 namespace usip {
 
 constexpr int BX_CAP = 8;                 // records per bucket: 8 x 32 B = 256 B, a 3-bucket row is one 768-byte bulk copy
-constexpr int BX_MAX_CELLS = 16384;       // per cloud -> 4 MB of buckets
+constexpr int BX_PITCH = 128;             // cells per row of the bucket plane (fixed, so ONE tensor map describes every cloud)
+constexpr int BX_ROWS = 128;              // rows of the bucket plane
+constexpr int BX_MAX_CELLS = BX_PITCH * BX_ROWS;   // per cloud -> 4 MB of buckets
 constexpr int BX_OVF = 4096;              // overflow records per cloud before the cloud falls back to the in-order scan
 constexpr int BX_HITS = 64;               // hits kept per keypoint before the in-order fallback (= max K of the fast path)
-constexpr int BX_CHUNK = 1024;            // points per CTA in the build kernel
+constexpr int BX_CHUNK = 256;             // points per CTA in the build kernel: one per thread, ~7 CTAs per SM hide the L2 round trips
 
 struct BxGrid { float o0, o1, inv_h; int n0, n1, a0, a1, ok; };            // 32 bytes
 
@@ -94,10 +98,10 @@ __device__ BxGrid bx_make_grid(const float* __restrict__ cp, int M, float radius
       // two margin cells on either side: a centre's cell index stays in [1, n-2] whatever the last-bit rounding of
       // (c - o) * inv_h does, so its 3 x 3 block never leaves the grid
       n0 = (int)fminf(floorf(e0 / h), 1e6f) + 5; n1 = (int)fminf(floorf(e1 / h), 1e6f) + 5;
-      if ((long long)n0 * n1 <= BX_MAX_CELLS) break;
+      if (n0 <= BX_PITCH && n1 <= BX_ROWS) break;
       h *= 1.26f;
     }
-    if ((long long)n0 * n1 > BX_MAX_CELLS) g.ok = 0;
+    if (n0 > BX_PITCH || n1 > BX_ROWS) g.ok = 0;
   }
   g.o0 = lo0 - 2.f * h; g.o1 = lo1 - 2.f * h; g.inv_h = 1.0f / h; g.n0 = n0; g.n1 = n1;
   return g;
@@ -110,56 +114,38 @@ bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
   __shared__ float red[6][8];
   const int b = blockIdx.y, tid = threadIdx.x;
   const float* p = xyz + (size_t)b * 3 * N;
-  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow.  Everything
-  // is indexed by compile-time constants (fully unrolled): no local-memory arrays.
-  float px[4], py[4], pz[4], pf[4][4];
+  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow
+  const int n = blockIdx.x * BX_CHUNK + tid;
+  const bool in = n < N;
+  const float x = in ? __ldg(p + n) : NAN, y = in ? __ldg(p + N + n) : NAN, z = in ? __ldg(p + 2 * N + n) : NAN;
+  float f[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
-    const bool in = n < N;
-    px[j] = in ? __ldg(p + n) : NAN; py[j] = in ? __ldg(p + N + n) : NAN; pz[j] = in ? __ldg(p + 2 * N + n) : NAN;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) pf[j][c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
-  }
+  for (int c = 0; c < 4; ++c) f[c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
   const BxGrid g = bx_make_grid(centers + (size_t)b * 3 * M, M, radius, red);
   if (blockIdx.x == 0 && tid == 0) grids[b] = g;
   // let the query kernel's CTAs start (they wait for this grid's completion before touching the buckets)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!g.ok) return;
-  int32_t* cnt = counts + (size_t)b * BX_MAX_CELLS;
-  float4* bk = buckets + (size_t)b * BX_MAX_CELLS * BX_CAP * 2;
-  // all four fill-count atomics are issued before any of their results is used (four L2 round trips in flight)
-  int cell[4], slot[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float x = px[j], y = py[j], z = pz[j];
-    cell[j] = -1;
-    if (fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f) {            // non-finite (and n >= N): never within a finite radius
-      const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
-      if (f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1) cell[j] = (int)f1 * g.n0 + (int)f0;   // else: farther than a cell from every centre
-    }
+  if (!(fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f)) return;      // non-finite (and n >= N): never within a finite radius
+  const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
+  if (!(f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1)) return;    // farther than a cell from every centre
+  const int cell = (int)f1 * BX_PITCH + (int)f0;
+  const int slot = atomicAdd(counts + (size_t)b * BX_MAX_CELLS + cell, 1);
+  float4* dst;
+  if (slot < BX_CAP) {
+    dst = buckets + ((size_t)b * BX_MAX_CELLS + cell) * BX_CAP * 2 + (size_t)slot * 2;
+  } else {
+    const int o = atomicAdd(ovf_cnt + b, 1);
+    if (o >= BX_OVF) return;                                 // the query sees ovf_cnt > BX_OVF and scans the cloud in order
+    dst = ovf + ((size_t)b * BX_OVF + o) * 2;
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) slot[j] = cell[j] >= 0 ? atomicAdd(cnt + cell[j], 1) : 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (cell[j] < 0) continue;
-    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
-    float4* dst;
-    if (slot[j] < BX_CAP) {
-      dst = bk + ((size_t)cell[j] * BX_CAP + slot[j]) * 2;
-    } else {
-      const int o = atomicAdd(ovf_cnt + b, 1);
-      if (o >= BX_OVF) continue;                             // the query sees ovf_cnt > BX_OVF and scans the cloud in order
-      dst = ovf + ((size_t)b * BX_OVF + o) * 2;
-    }
-    dst[0] = make_float4(px[j], py[j], pz[j], __int_as_float(n));
-    dst[1] = make_float4(pf[j][0], pf[j][1], pf[j][2], pf[j][3]);
-  }
+  dst[0] = make_float4(x, y, z, __int_as_float(n));
+  dst[1] = make_float4(f[0], f[1], f[2], f[3]);
 }
 
 __global__ void __launch_bounds__(256)
-bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const float* __restrict__ centers,
+bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ xyz, const float* __restrict__ feat,
+                const float* __restrict__ centers,
                 const BxGrid* __restrict__ grids, int32_t* __restrict__ counts, int32_t* __restrict__ ovf_cnt,
                 int32_t* __restrict__ done, const float4* __restrict__ buckets, const float4* __restrict__ ovf,
                 float t_max, int32_t* __restrict__ out_idx, float* __restrict__ out_group, float* __restrict__ out_rows,
@@ -200,17 +186,16 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
       // guards the address arithmetic
       const int k0 = min(max((int)floorf((bx_axis(cx, cy, cz, g.a0) - g.o0) * g.inv_h), 1), g.n0 - 2);
       const int k1 = min(max((int)floorf((bx_axis(cx, cy, cz, g.a1) - g.o1) * g.inv_h), 1), g.n1 - 2);
-      const int base = (k1 - 1) * g.n0 + (k0 - 1);
-      const float4* bk = buckets + (size_t)b * BX_MAX_CELLS * BX_CAP * 2;
+      const int base = (k1 - 1) * BX_PITCH + (k0 - 1);
       float4* st = stage[wib];
       if (lane == 0) {
+        // box = 3 buckets (192 floats) x 3 rows of cloud b's bucket plane, landing as three consecutive 768-byte rows
         mbar_arrive_expect_tx(bar, 3 * 3 * BX_CAP * 32);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-          bulk_g2s(smem_u32(st + r * 3 * BX_CAP * 2), bk + (size_t)(base + r * g.n0) * BX_CAP * 2, 3 * BX_CAP * 32, bar);
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(st)), "l"(&tmap), "r"((k0 - 1) * (BX_CAP * 8)), "r"(k1 - 1), "r"(b), "r"(bar) : "memory");
       }
       int fill = 0;                                               // lanes 0..8: fill count of bucket (lane / 3, lane % 3)
-      if (lane < 9) fill = __ldcg(cnt + base + (lane / 3) * g.n0 + (lane % 3));
+      if (lane < 9) fill = __ldcg(cnt + base + (lane / 3) * BX_PITCH + (lane % 3));
       const unsigned over = __ballot_sync(0xffffffffu, fill > BX_CAP);
       mbar_wait_sleep(bar, 0);
       // 72 slots, 32 per pass: slot s belongs to bucket s / 8
@@ -318,13 +303,38 @@ bx_query_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, c
   if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(done + b, 1) == ctas_per_cloud - 1; }
   __syncthreads();
   if (s_last) {
-    const int cells = g.ok ? g.n0 * g.n1 : 0;
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) cnt[i] = 0;
+    const int cells = g.ok ? g.n1 * BX_PITCH : 0;              // rows 0..n1-1 of the fixed-pitch plane
+    for (int i = threadIdx.x; i < cells / 4; i += blockDim.x) reinterpret_cast<int4*>(cnt)[i] = make_int4(0, 0, 0, 0);
     if (threadIdx.x == 0) { ovf_cnt[b] = 0; done[b] = 0; }
   }
 }
 
 float radius_to_tmax_host(float radius);          // ballquery.cu
+
+// Tensor map of the bucket planes: 3-D tensor [B clouds][BX_ROWS rows][BX_PITCH cells x 64 floats], box = 3 cells x 3 rows.
+// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint): the library keeps no link-time
+// dependency on libcuda, so it still loads (and exports its symbols) on a machine without a driver.
+static int bx_tensor_map(CUtensorMap* tm, float4* buckets, int B) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) { set_last_error("ball_group: cuTensorMapEncodeTiled not available"); return e != cudaSuccess ? (int)e : -1; }
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)BX_PITCH * BX_CAP * 8, (cuuint64_t)BX_ROWS, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)BX_PITCH * BX_CAP * 32, (cuuint64_t)BX_MAX_CELLS * BX_CAP * 32};   // bytes, dims 1..2
+  const cuuint32_t box[3] = {3 * BX_CAP * 8, 3, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buckets, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("ball_group: cuTensorMapEncodeTiled failed"); return (int)r; }
+  return 0;
+}
 
 }  // namespace usip
 
@@ -376,7 +386,10 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
   static const bool no_pdl = getenv("USIP_BALL_NO_PDL") != nullptr;            // debug aid: plain stream order instead
   cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
   const BxGrid* grids = sc.grids; const float4* bk = sc.buckets; const float4* ov = sc.ovf;
-  cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_query_kernel, xyz, feat, centers, grids, sc.counts, sc.ovf_cnt, sc.done, bk, ov, t_max,
+  CUtensorMap tmap;
+  int te = bx_tensor_map(&tmap, sc.buckets, B);
+  if (te) return te;
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_query_kernel, tmap, xyz, feat, centers, grids, sc.counts, sc.ovf_cnt, sc.done, bk, ov, t_max,
                                       out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, cpc);
   if (ce != cudaSuccess) { set_last_error("bx_query_kernel"); return (int)ce; }
   return check_launch("bx_query_kernel");
