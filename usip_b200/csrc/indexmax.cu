@@ -16,6 +16,7 @@ namespace usip {
 constexpr int IMS_THREADS = 1024;          // two threads per cluster at K = 512: half a segment each, merged by one shuffle
 constexpr int IMS_MAXN = 16384;            // one row buffer = 64 KB; bucket order as uint16
 constexpr int IMS_MAXK = 4096;
+constexpr int IMS_REG = 24;                // point indices a thread keeps in registers (clusters up to 48 points stay out of smem)
 
 struct ImsLayout {
   int npad; size_t row_bytes, perm_off, seg_off, cur_off, wtot_off, bar_off, total;
@@ -49,7 +50,9 @@ index_max_bucket_kernel(const float* __restrict__ data, const int32_t* __restric
   __syncthreads();
   const uint32_t nbytes = (uint32_t)N * 4u;
   if (tid == 0) { mbar_arrive_expect_tx(bar0, nbytes); bulk_g2s(smem_u32(rowbuf), data + (size_t)row0 * N, nbytes, bar0); }
-  int cur_b = -1;
+  int cur_b = -1, reg_b = -1, my_j0 = 0, my_j1 = 0;
+  const int sub = tid & 1;
+  uint32_t preg[IMS_REG / 2];
   const int ipt = (K + IMS_THREADS - 1) / IMS_THREADS;            // clusters per thread in the scan
   for (int r = row0, it = 0; r < row1; ++r, ++it) {
     const int s = it & 1;
@@ -94,16 +97,47 @@ index_max_bucket_kernel(const float* __restrict__ data, const int32_t* __restric
       __syncthreads();
       cur_b = b;
     }
+    if (b != reg_b) {
+      // this thread's share of its cluster (every other element) is the same for all C rows of the cloud: keep up to
+      // IMS_REG point indices in registers (two 16-bit indices per register) -- per row only the row gather remains
+      reg_b = b;
+#pragma unroll
+      for (int t = 0; t < IMS_REG / 2; ++t) preg[t] = 0xffffffffu;
+      my_j0 = 0; my_j1 = 0;
+      const int k = tid >> 1;
+      if (k < K) {
+        my_j0 = seg[k] + sub; my_j1 = seg[k + 1];
+#pragma unroll
+        for (int t = 0; t < IMS_REG; ++t) {
+          const int j = my_j0 + 2 * t;
+          const uint32_t n = j < my_j1 ? perm[j] : 0xffffu;
+          if (t & 1) preg[t >> 1] = (preg[t >> 1] & 0xffffu) | (n << 16); else preg[t >> 1] = (preg[t >> 1] & 0xffff0000u) | n;
+        }
+      }
+    }
     mbar_wait(bar0 + 8 * s, (it >> 1) & 1);
     const float* row = rowbuf + (size_t)s * L.npad;
-    // lanes 2i and 2i+1 share cluster k: each walks every other element (two independent dependent-load chains per
-    // cluster instead of one), then the pair is merged.  Order: (value, n) lexicographic = the reference's first maximum.
-    const int sub = tid & 1;
+    // lanes 2i and 2i+1 share cluster k: each walks every other element, then the pair is merged.
+    // Order: (value, n) lexicographic = the reference's first maximum, independent of the (unstable) bucket order.
     for (int k0 = 0; k0 < K; k0 += IMS_THREADS / 2) {
       const int k = k0 + (tid >> 1);
       float best = -1000.0f;                                      // index_max_cuda.cu:38 / :71
       int bn = 0x7fffffff;                                        // "nothing above the floor yet"
-      if (k < K) {
+      if (k0 == 0) {
+#pragma unroll
+        for (int t = 0; t < IMS_REG; ++t) {
+          const int n = (int)((preg[t >> 1] >> ((t & 1) * 16)) & 0xffffu);
+          if (n != 0xffff) {                                       // N <= 16384: 0xffff is never a point
+            const float v = row[n];
+            if (v > best || (v == best && n < bn && bn != 0x7fffffff)) { best = v; bn = n; }
+          }
+        }
+        for (int j = my_j0 + 2 * IMS_REG; j < my_j1; j += 2) {      // the tail of an unusually large cluster
+          const int n = perm[j];
+          const float v = row[n];
+          if (v > best || (v == best && n < bn && bn != 0x7fffffff)) { best = v; bn = n; }
+        }
+      } else if (k < K) {                                          // K > IMS_THREADS / 2: further clusters through shared memory
         const int j1 = seg[k + 1];
         for (int j = seg[k] + sub; j < j1; j += 2) {
           const int n = perm[j];
