@@ -1,18 +1,19 @@
-// ballgroup.cu -- fused ball query + group (models/networks.py:355-373 + ball_query_ext/ball_query_cuda.cu:10-49) in TWO
-// launches chained by programmatic dependent launch, with TMA-staged (cp.async.bulk) candidate tiles in shared memory.
+// ballgroup.cu -- fused ball query + group (models/networks.py:355-373 + ball_query_ext/ball_query_cuda.cu:10-49): three
+// small launches chained by programmatic dependent launch, candidate tiles staged by tensor-map TMA in shared memory.
 //
-//   bx_build_kernel  every CTA derives the same 2-D bucket grid from the CENTRES of its cloud (bounding box of the
-//                    keypoints grown by one cell; the axis with the smallest extent is not binned), then drops its points
-//                    into fixed-capacity buckets: slot = atomicAdd(count[cell]); record (x,y,z,index | f0..f3) -> bucket
-//                    [cell][slot], or -> the cloud's overflow list when the bucket is full.  No histogram, no scan, no
-//                    second pass: points farther than a cell from every centre are dropped on the spot.
+//   bx_grid_kernel   one CTA per cloud: 2-D bucket grid from the CENTRES of the cloud (bounding box of the keypoints grown by
+//                    two cells; the axis with the smallest extent is not binned; cell size h >= 1.001 r, fixed row pitch).
+//   bx_build_kernel  one point per thread: slot = atomicAdd(count[cell]); record (x,y,z,index | f0..f3) -> bucket[cell][slot],
+//                    or -> the cloud's overflow list when the bucket is full.  No histogram, no scan, no second pass: points
+//                    farther than a cell from every centre are dropped on the spot.  Point loads are issued BEFORE
+//                    griddepcontrol.wait (they do not depend on the grid).
 //   bx_query_kernel  one warp per keypoint: the 3 x 3 neighbouring buckets are a 768-byte x 3-row box of the cloud's bucket
 //                    plane (fixed pitch of 128 cells); one elected lane fetches the box with ONE tensor-map TMA
-//                    (cp.async.bulk.tensor.3d, mbarrier complete_tx; out-of-range parts are zero-filled by the hardware)
-//                    while nine lanes read the nine fill counts; warp-ballot radius test on the staged records; hits are ranked by point index
-//                    (the reference keeps the FIRST K hits in index order) and index, gathered record and decentred
-//                    group are written in one pass of full 128-byte lines.  The last CTA of a cloud to finish clears the
-//                    counts again, so the scratch is left as it was found: all-zero counters.
+//                    (cp.async.bulk.tensor.3d -> UTMALDG, mbarrier complete_tx) while nine lanes read the nine fill counts;
+//                    warp-ballot radius test on the staged records; hits are ranked by point index (the reference keeps the
+//                    FIRST K hits in index order) and index, gathered record and decentred group are written in one pass of
+//                    full 128-byte lines.  The last CTA of a cloud to finish clears the counts again, so the scratch is left
+//                    as it was found: all-zero counters.
 //
 // Exactness: d^2 with the reference's fp32 op order against t_max (ballquery.cu), cell size h >= 1.001 r so every point
 // within r of a centre lies in the 3 x 3 block around the centre's cell; clouds whose overflow list is full, balls with
@@ -107,24 +108,36 @@ __device__ BxGrid bx_make_grid(const float* __restrict__ cp, int M, float radius
   return g;
 }
 
+// one CTA per cloud: the bucket grid of that cloud.  (Every build CTA deriving it redundantly from the 12 KB of centres was
+// measured at 12-14 us for the build: 64 CTAs per cloud hammering the same L2 lines.)
 __global__ void __launch_bounds__(256)
-bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const float* __restrict__ centers,
-                float radius, BxGrid* __restrict__ grids, int32_t* __restrict__ counts, int32_t* __restrict__ ovf_cnt,
-                float4* __restrict__ buckets, float4* __restrict__ ovf, int S, int N, int M) {
+bx_grid_kernel(const float* __restrict__ centers, float radius, BxGrid* __restrict__ grids, int M) {
   __shared__ float red[6][8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the build CTAs may start loading their points
+  const BxGrid g = bx_make_grid(centers + (size_t)blockIdx.x * 3 * M, M, radius, red);
+  if (threadIdx.x == 0) grids[blockIdx.x] = g;
+}
+
+__global__ void __launch_bounds__(256)
+bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const BxGrid* __restrict__ grids,
+                int32_t* __restrict__ counts, int32_t* __restrict__ ovf_cnt, float4* __restrict__ buckets,
+                float4* __restrict__ ovf, int S, int N) {
   const int b = blockIdx.y, tid = threadIdx.x;
   const float* p = xyz + (size_t)b * 3 * N;
-  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow
+  // the point loads do not depend on the grid: they are in flight while the grid kernel finishes
   const int n = blockIdx.x * BX_CHUNK + tid;
   const bool in = n < N;
   const float x = in ? __ldg(p + n) : NAN, y = in ? __ldg(p + N + n) : NAN, z = in ? __ldg(p + 2 * N + n) : NAN;
   float f[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) f[c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
-  const BxGrid g = bx_make_grid(centers + (size_t)b * 3 * M, M, radius, red);
-  if (blockIdx.x == 0 && tid == 0) grids[b] = g;
+  asm volatile("griddepcontrol.wait;" ::: "memory");                    // grids[] is complete and visible
   // let the query kernel's CTAs start (they wait for this grid's completion before touching the buckets)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int4 g0 = __ldcg(reinterpret_cast<const int4*>(grids + b)), g1 = __ldcg(reinterpret_cast<const int4*>(grids + b) + 1);
+  BxGrid g;
+  g.o0 = __int_as_float(g0.x); g.o1 = __int_as_float(g0.y); g.inv_h = __int_as_float(g0.z); g.n0 = g0.w;
+  g.n1 = g1.x; g.a0 = g1.y; g.a1 = g1.z; g.ok = g1.w;
   if (!g.ok) return;
   if (!(fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f)) return;      // non-finite (and n >= N): never within a finite radius
   const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
@@ -156,8 +169,8 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
   __shared__ __align__(8) uint64_t mbar[8];
   __shared__ int s_last;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTAs never straddle clouds (ctas_per_cloud = ceil(M / 8)), so the arrival counter below is per cloud
-  const int b = blockIdx.x / ctas_per_cloud, m = (blockIdx.x - b * ctas_per_cloud) * 8 + wib;
+  // grid = (ceil(M / 8), B): CTAs never straddle clouds, so the arrival counter below is per cloud
+  const int b = blockIdx.y, m = blockIdx.x * 8 + wib;
   const bool active = m < M;
   const int w = b * M + m;
   const float* cp = centers + (size_t)b * 3 * M;
@@ -167,7 +180,12 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
   if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   __syncwarp();
   asm volatile("griddepcontrol.wait;" ::: "memory");                // the build grid has completed and its writes are visible
-  const BxGrid g = grids[b];
+  BxGrid g;
+  {
+    const int4 g0 = __ldcg(reinterpret_cast<const int4*>(grids + b)), g1 = __ldcg(reinterpret_cast<const int4*>(grids + b) + 1);
+    g.o0 = __int_as_float(g0.x); g.o1 = __int_as_float(g0.y); g.inv_h = __int_as_float(g0.z); g.n0 = g0.w;
+    g.n1 = g1.x; g.a0 = g1.y; g.a1 = g1.z; g.ok = g1.w;
+  }
   const float* p = xyz + (size_t)b * 3 * N;
   int32_t* cnt = counts + (size_t)b * BX_MAX_CELLS;
   const unsigned lt = (1u << lane) - 1u;
@@ -178,7 +196,7 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
   int* hn = hidx[wib][0]; int* sl = hidx[wib][1];
   float4* h0 = hrec[wib][0]; float4* h1 = hrec[wib][1];
   if (active) {
-    const int novf = __ldg(ovf_cnt + b);
+    const int novf = __ldcg(ovf_cnt + b);
     if (novf > BX_OVF) brute = true;
     const bool cfin = fabsf(cx) <= 1e30f && fabsf(cy) <= 1e30f && fabsf(cz) <= 1e30f;
     if (!brute && cfin) {
@@ -195,7 +213,8 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
                      ::"r"(smem_u32(st)), "l"(&tmap), "r"((k0 - 1) * (BX_CAP * 8)), "r"(k1 - 1), "r"(b), "r"(bar) : "memory");
       }
       int fill = 0;                                               // lanes 0..8: fill count of bucket (lane / 3, lane % 3)
-      if (lane < 9) fill = __ldcg(cnt + base + (lane / 3) * BX_PITCH + (lane % 3));
+      const int l3 = (lane * 11) >> 5;                          // lane / 3 for lane < 9
+      if (lane < 9) fill = __ldcg(cnt + base + l3 * BX_PITCH + (lane - 3 * l3));
       const unsigned over = __ballot_sync(0xffffffffu, fill > BX_CAP);
       mbar_wait_sleep(bar, 0);
       // 72 slots, 32 per pass: slot s belongs to bucket s / 8
@@ -261,10 +280,10 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
     }
     // out[k] = hits[k % u] (first u in index order, then the cyclic pad of ball_query_cuda.cu:40-46); no hit -> point 0
     const int u = min(nh, K);
-    const uint32_t um = u > 1 ? (0xffffffffu / (uint32_t)u + 1u) : 0u;
+    const float ru = u > 1 ? __frcp_rn((float)u) : 0.f;        // k, u <= 64: floor((k + 0.5) / u) is exact in fp32
     const float* pfeat = feat + (size_t)b * S * N;
     for (int k = lane; k < K; k += 32) {
-      const int e = u > 1 ? (k - u * (int)__umulhi((uint32_t)k, um)) : 0;   // k % u
+      const int e = u > 1 ? (k - u * (int)(((float)k + 0.5f) * ru)) : 0;    // k % u
       int n = 0;
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (!brute && u > 0) {
@@ -373,24 +392,28 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
                        (!out_rows || (reinterpret_cast<uintptr_t>(out_rows) % 16) == 0);
   if (!grid_ok) return ball_group_brute(xyz, feat, centers, t_max, out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, st);
   BxScratch sc(scratch, B);
-  bx_build_kernel<<<dim3(cdiv(N, BX_CHUNK), B), 256, 0, st>>>(xyz, feat, centers, radius, sc.grids, sc.counts, sc.ovf_cnt,
-                                                              sc.buckets, sc.ovf, S, N, M);
-  int e = check_launch("bx_build_kernel");
-  if (e) return e;
-  // programmatic dependent launch: the query grid is scheduled while the build grid drains; griddepcontrol.wait orders the data
-  const int cpc = cdiv(M, 8);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(cpc * B)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  // three launches chained by programmatic dependent launch: grid (one CTA per cloud) -> build -> query.  Each kernel
+  // issues the loads that do not depend on its predecessor before griddepcontrol.wait, so the launch gaps and the first
+  // HBM round trip of every stage overlap the tail of the stage before it.
+  static const bool no_pdl = getenv("USIP_BALL_NO_PDL") != nullptr;            // debug aid: plain stream order instead
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool no_pdl = getenv("USIP_BALL_NO_PDL") != nullptr;            // debug aid: plain stream order instead
-  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+  bx_grid_kernel<<<B, 256, 0, st>>>(centers, radius, sc.grids, M);
+  int e = check_launch("bx_grid_kernel");
+  if (e) return e;
   const BxGrid* grids = sc.grids; const float4* bk = sc.buckets; const float4* ov = sc.ovf;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cdiv(N, BX_CHUNK), (unsigned)B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_build_kernel, xyz, feat, grids, sc.counts, sc.ovf_cnt, sc.buckets, sc.ovf, S, N);
+  if (ce != cudaSuccess) { set_last_error("bx_build_kernel"); return (int)ce; }
+  const int cpc = cdiv(M, 8);
+  cfg.gridDim = dim3((unsigned)cpc, (unsigned)B);
   CUtensorMap tmap;
   int te = bx_tensor_map(&tmap, sc.buckets, B);
   if (te) return te;
-  cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_query_kernel, tmap, xyz, feat, centers, grids, sc.counts, sc.ovf_cnt, sc.done, bk, ov, t_max,
-                                      out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, cpc);
+  ce = cudaLaunchKernelEx(&cfg, bx_query_kernel, tmap, xyz, feat, centers, grids, sc.counts, sc.ovf_cnt, sc.done, bk, ov, t_max,
+                          out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, cpc);
   if (ce != cudaSuccess) { set_last_error("bx_query_kernel"); return (int)ce; }
   return check_launch("bx_query_kernel");
 }
