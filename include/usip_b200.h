@@ -53,8 +53,8 @@ int usip_ball_query_dist_f32(const float* dist, float radius, int32_t* out_idx,
  * 32-byte records, overflow list).  CONTRACT: its counter region must be all-zero when the call starts -- clear it ONCE with
  * usip_ball_group_scratch_init() -- and every call leaves it all-zero again (the last CTA of each cloud restores it), so a
  * scratch buffer that is kept between calls costs no memset launch.  One scratch per stream.  Without scratch (or for
- * S > 4) the reference's in-order scan runs as a single kernel.  Three small launches (grid, build, query) chained by
- * programmatic dependent launch; the query stages its candidate buckets with one tensor-map TMA per keypoint. */
+ * S > 4) the reference's in-order scan runs as a single kernel.  Two launches (build, query) chained by programmatic
+ * dependent launch; the query stages its candidate buckets with one tensor-map TMA per keypoint. */
 int usip_ball_group_f32(const float* xyz, const float* feat, const float* centers, float radius,
                         int32_t* out_idx, float* out_group, float* out_rows, int ld_rows,
                         void* scratch, int64_t scratch_bytes, int B, int S, int N, int M, int K, void* stream);

@@ -137,7 +137,7 @@ def load():
 WEIGHT_GEN = [0]
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim); default 1
-KERNELS_PER_CALL = {"usip_cluster_sort": 3, "usip_pairwise_min_f32": 3, "usip_layer_fwd_tc": 2, "usip_ball_group_f32": 3}
+KERNELS_PER_CALL = {"usip_cluster_sort": 3, "usip_pairwise_min_f32": 3, "usip_layer_fwd_tc": 2, "usip_ball_group_f32": 2}
 LAUNCHES = [0]
 
 

@@ -1,12 +1,12 @@
-// ballgroup.cu -- fused ball query + group (models/networks.py:355-373 + ball_query_ext/ball_query_cuda.cu:10-49): three
-// small launches chained by programmatic dependent launch, candidate tiles staged by tensor-map TMA in shared memory.
+// ballgroup.cu -- fused ball query + group (models/networks.py:355-373 + ball_query_ext/ball_query_cuda.cu:10-49): two
+// launches chained by programmatic dependent launch, candidate tiles staged by tensor-map TMA in shared memory.
 //
-//   bx_grid_kernel   one CTA per cloud: 2-D bucket grid from the CENTRES of the cloud (bounding box of the keypoints grown by
-//                    two cells; the axis with the smallest extent is not binned; cell size h >= 1.001 r, fixed row pitch).
-//   bx_build_kernel  one point per thread: slot = atomicAdd(count[cell]); record (x,y,z,index | f0..f3) -> bucket[cell][slot],
-//                    or -> the cloud's overflow list when the bucket is full.  No histogram, no scan, no second pass: points
-//                    farther than a cell from every centre are dropped on the spot.  Point loads are issued BEFORE
-//                    griddepcontrol.wait (they do not depend on the grid).
+//   bx_build_kernel  every CTA derives the same 2-D bucket grid from the CENTRES of its cloud (bounding box of the
+//                    keypoints grown by two cells; the axis with the smallest extent is not binned; cell size h >= 1.001 r,
+//                    fixed row pitch), then drops its points into fixed-capacity buckets: slot = atomicAdd(count[cell]);
+//                    record (x,y,z,index | f0..f3) -> bucket[cell][slot], or -> the cloud's overflow list when the bucket
+//                    is full.  No histogram, no scan, no second pass: points farther than a cell from every centre are
+//                    dropped on the spot.  Four points per thread, their four atomics in flight together.
 //   bx_query_kernel  one warp per keypoint: the 3 x 3 neighbouring buckets are a 768-byte x 3-row box of the cloud's bucket
 //                    plane (fixed pitch of 128 cells); one elected lane fetches the box with ONE tensor-map TMA
 //                    (cp.async.bulk.tensor.3d -> UTMALDG, mbarrier complete_tx) while nine lanes read the nine fill counts;
@@ -30,7 +30,7 @@ constexpr int BX_ROWS = 128;              // rows of the bucket plane
 constexpr int BX_MAX_CELLS = BX_PITCH * BX_ROWS;   // per cloud -> 4 MB of buckets
 constexpr int BX_OVF = 4096;              // overflow records per cloud before the cloud falls back to the in-order scan
 constexpr int BX_HITS = 64;               // hits kept per keypoint before the in-order fallback (= max K of the fast path)
-constexpr int BX_CHUNK = 256;             // points per CTA in the build kernel: one per thread, ~7 CTAs per SM hide the L2 round trips
+constexpr int BX_CHUNK = 1024;            // points per CTA in the build kernel (4 per thread: 4 atomics in flight)
 
 struct BxGrid { float o0, o1, inv_h; int n0, n1, a0, a1, ok; };            // 32 bytes
 
@@ -108,52 +108,59 @@ __device__ BxGrid bx_make_grid(const float* __restrict__ cp, int M, float radius
   return g;
 }
 
-// one CTA per cloud: the bucket grid of that cloud.  (Every build CTA deriving it redundantly from the 12 KB of centres was
-// measured at 12-14 us for the build: 64 CTAs per cloud hammering the same L2 lines.)
 __global__ void __launch_bounds__(256)
-bx_grid_kernel(const float* __restrict__ centers, float radius, BxGrid* __restrict__ grids, int M) {
+bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const float* __restrict__ centers,
+                float radius, BxGrid* __restrict__ grids, int32_t* __restrict__ counts, int32_t* __restrict__ ovf_cnt,
+                float4* __restrict__ buckets, float4* __restrict__ ovf, int S, int N, int M) {
   __shared__ float red[6][8];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the build CTAs may start loading their points
-  const BxGrid g = bx_make_grid(centers + (size_t)blockIdx.x * 3 * M, M, radius, red);
-  if (threadIdx.x == 0) grids[blockIdx.x] = g;
-}
-
-__global__ void __launch_bounds__(256)
-bx_build_kernel(const float* __restrict__ xyz, const float* __restrict__ feat, const BxGrid* __restrict__ grids,
-                int32_t* __restrict__ counts, int32_t* __restrict__ ovf_cnt, float4* __restrict__ buckets,
-                float4* __restrict__ ovf, int S, int N) {
   const int b = blockIdx.y, tid = threadIdx.x;
   const float* p = xyz + (size_t)b * 3 * N;
-  // the point loads do not depend on the grid: they are in flight while the grid kernel finishes
-  const int n = blockIdx.x * BX_CHUNK + tid;
-  const bool in = n < N;
-  const float x = in ? __ldg(p + n) : NAN, y = in ? __ldg(p + N + n) : NAN, z = in ? __ldg(p + 2 * N + n) : NAN;
-  float f[4];
+  // the point loads do not depend on the grid: issue them first, the centre reduction runs in their shadow.  Everything
+  // is indexed by compile-time constants (fully unrolled): no local-memory arrays.
+  float px[4], py[4], pz[4], pf[4][4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) f[c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
-  asm volatile("griddepcontrol.wait;" ::: "memory");                    // grids[] is complete and visible
+  for (int j = 0; j < 4; ++j) {
+    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
+    const bool in = n < N;
+    px[j] = in ? __ldg(p + n) : NAN; py[j] = in ? __ldg(p + N + n) : NAN; pz[j] = in ? __ldg(p + 2 * N + n) : NAN;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pf[j][c] = (in && c < S) ? __ldg(feat + ((size_t)b * S + c) * N + n) : 0.f;
+  }
+  const BxGrid g = bx_make_grid(centers + (size_t)b * 3 * M, M, radius, red);
+  if (blockIdx.x == 0 && tid == 0) grids[b] = g;
   // let the query kernel's CTAs start (they wait for this grid's completion before touching the buckets)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int4 g0 = __ldcg(reinterpret_cast<const int4*>(grids + b)), g1 = __ldcg(reinterpret_cast<const int4*>(grids + b) + 1);
-  BxGrid g;
-  g.o0 = __int_as_float(g0.x); g.o1 = __int_as_float(g0.y); g.inv_h = __int_as_float(g0.z); g.n0 = g0.w;
-  g.n1 = g1.x; g.a0 = g1.y; g.a1 = g1.z; g.ok = g1.w;
   if (!g.ok) return;
-  if (!(fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f)) return;      // non-finite (and n >= N): never within a finite radius
-  const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
-  if (!(f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1)) return;    // farther than a cell from every centre
-  const int cell = (int)f1 * BX_PITCH + (int)f0;
-  const int slot = atomicAdd(counts + (size_t)b * BX_MAX_CELLS + cell, 1);
-  float4* dst;
-  if (slot < BX_CAP) {
-    dst = buckets + ((size_t)b * BX_MAX_CELLS + cell) * BX_CAP * 2 + (size_t)slot * 2;
-  } else {
-    const int o = atomicAdd(ovf_cnt + b, 1);
-    if (o >= BX_OVF) return;                                 // the query sees ovf_cnt > BX_OVF and scans the cloud in order
-    dst = ovf + ((size_t)b * BX_OVF + o) * 2;
+  int32_t* cnt = counts + (size_t)b * BX_MAX_CELLS;
+  float4* bk = buckets + (size_t)b * BX_MAX_CELLS * BX_CAP * 2;
+  // all four fill-count atomics are issued before any of their results is used (four L2 round trips in flight)
+  int cell[4], slot[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x = px[j], y = py[j], z = pz[j];
+    cell[j] = -1;
+    if (fabsf(x) <= 1e30f && fabsf(y) <= 1e30f && fabsf(z) <= 1e30f) {            // non-finite (and n >= N): never within a finite radius
+      const float f0 = floorf((bx_axis(x, y, z, g.a0) - g.o0) * g.inv_h), f1 = floorf((bx_axis(x, y, z, g.a1) - g.o1) * g.inv_h);
+      if (f0 >= 0.f && f0 < (float)g.n0 && f1 >= 0.f && f1 < (float)g.n1) cell[j] = (int)f1 * BX_PITCH + (int)f0;   // else: farther than a cell from every centre
+    }
   }
-  dst[0] = make_float4(x, y, z, __int_as_float(n));
-  dst[1] = make_float4(f[0], f[1], f[2], f[3]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) slot[j] = cell[j] >= 0 ? atomicAdd(cnt + cell[j], 1) : 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (cell[j] < 0) continue;
+    const int n = blockIdx.x * BX_CHUNK + j * 256 + tid;
+    float4* dst;
+    if (slot[j] < BX_CAP) {
+      dst = bk + ((size_t)cell[j] * BX_CAP + slot[j]) * 2;
+    } else {
+      const int o = atomicAdd(ovf_cnt + b, 1);
+      if (o >= BX_OVF) continue;                             // the query sees ovf_cnt > BX_OVF and scans the cloud in order
+      dst = ovf + ((size_t)b * BX_OVF + o) * 2;
+    }
+    dst[0] = make_float4(px[j], py[j], pz[j], __int_as_float(n));
+    dst[1] = make_float4(pf[j][0], pf[j][1], pf[j][2], pf[j][3]);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -392,21 +399,21 @@ extern "C" int usip_ball_group_f32(const float* xyz, const float* feat, const fl
                        (!out_rows || (reinterpret_cast<uintptr_t>(out_rows) % 16) == 0);
   if (!grid_ok) return ball_group_brute(xyz, feat, centers, t_max, out_idx, out_group, out_rows, ld_rows, B, S, N, M, K, st);
   BxScratch sc(scratch, B);
-  // three launches chained by programmatic dependent launch: grid (one CTA per cloud) -> build -> query.  Each kernel
-  // issues the loads that do not depend on its predecessor before griddepcontrol.wait, so the launch gaps and the first
-  // HBM round trip of every stage overlap the tail of the stage before it.
+  // two launches chained by programmatic dependent launch: the query grid is scheduled while the build grid drains and
+  // issues its centre loads; griddepcontrol.wait orders the data.  (A third, one-CTA-per-cloud launch that publishes the
+  // grid once -- instead of every build CTA deriving it -- was measured slower: 5 + 10 + 27 us against 12 + 22 us.)
   static const bool no_pdl = getenv("USIP_BALL_NO_PDL") != nullptr;            // debug aid: plain stream order instead
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-  bx_grid_kernel<<<B, 256, 0, st>>>(centers, radius, sc.grids, M);
-  int e = check_launch("bx_grid_kernel");
+  bx_build_kernel<<<dim3(cdiv(N, BX_CHUNK), B), 256, 0, st>>>(xyz, feat, centers, radius, sc.grids, sc.counts, sc.ovf_cnt,
+                                                              sc.buckets, sc.ovf, S, N, M);
+  int e = check_launch("bx_build_kernel");
   if (e) return e;
   const BxGrid* grids = sc.grids; const float4* bk = sc.buckets; const float4* ov = sc.ovf;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)cdiv(N, BX_CHUNK), (unsigned)B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
   cfg.attrs = at; cfg.numAttrs = no_pdl ? 0 : 1;
-  cudaError_t ce = cudaLaunchKernelEx(&cfg, bx_build_kernel, xyz, feat, grids, sc.counts, sc.ovf_cnt, sc.buckets, sc.ovf, S, N);
-  if (ce != cudaSuccess) { set_last_error("bx_build_kernel"); return (int)ce; }
+  cudaError_t ce;
   const int cpc = cdiv(M, 8);
   cfg.gridDim = dim3((unsigned)cpc, (unsigned)B);
   CUtensorMap tmap;

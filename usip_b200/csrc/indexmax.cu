@@ -16,6 +16,7 @@ namespace usip {
 constexpr int IMS_THREADS = 1024;          // two threads per cluster at K = 512: half a segment each, merged by one shuffle
 constexpr int IMS_MAXN = 16384;            // one row buffer = 64 KB; bucket order as uint16
 constexpr int IMS_MAXK = 4096;
+constexpr int IMS_SPLIT = 16;              // concurrent bulk copies per row
 constexpr int IMS_REG = 24;                // point indices a thread keeps in registers (clusters up to 48 points stay out of smem)
 
 struct ImsLayout {
@@ -49,17 +50,26 @@ index_max_bucket_kernel(const float* __restrict__ data, const int32_t* __restric
   if (tid == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_barrier_init(); }
   __syncthreads();
   const uint32_t nbytes = (uint32_t)N * 4u;
-  if (tid == 0) { mbar_arrive_expect_tx(bar0, nbytes); bulk_g2s(smem_u32(rowbuf), data + (size_t)row0 * N, nbytes, bar0); }
+  // a row is fetched as IMS_SPLIT concurrent bulk copies (one per lane of warp 0) on one mbarrier: a single 64 KB
+  // cp.async.bulk per SM leaves the TMA unit latency-bound (measured: ~4 us per row = 16 GB/s per SM)
+  const int nsplit = (N % (4 * IMS_SPLIT) == 0) ? IMS_SPLIT : 1;
+  const uint32_t cbytes = nbytes / (uint32_t)nsplit;
+  auto fetch_row = [&](int r, int buf) {
+    const uint32_t bar = bar0 + 8 * buf;
+    if (tid == 0) mbar_arrive_expect_tx(bar, nbytes);
+    __syncwarp();
+    if (tid < nsplit)
+      bulk_g2s(smem_u32(rowbuf + (size_t)buf * L.npad) + tid * cbytes,
+               reinterpret_cast<const char*>(data + (size_t)r * N) + (size_t)tid * cbytes, cbytes, bar);
+  };
+  if (warp == 0) fetch_row(row0, 0);
   int cur_b = -1, reg_b = -1, my_j0 = 0, my_j1 = 0;
   const int sub = tid & 1;
   uint32_t preg[IMS_REG / 2];
   const int ipt = (K + IMS_THREADS - 1) / IMS_THREADS;            // clusters per thread in the scan
   for (int r = row0, it = 0; r < row1; ++r, ++it) {
     const int s = it & 1;
-    if (tid == 0 && r + 1 < row1) {                               // the other buffer was released by the barrier that ended it-1
-      mbar_arrive_expect_tx(bar0 + 8 * (s ^ 1), nbytes);
-      bulk_g2s(smem_u32(rowbuf + (size_t)(s ^ 1) * L.npad), data + (size_t)(r + 1) * N, nbytes, bar0 + 8 * (s ^ 1));
-    }
+    if (warp == 0 && r + 1 < row1) fetch_row(r + 1, s ^ 1);        // the other buffer was released by the barrier that ended it-1
     const int b = r / C;
     if (b != cur_b) {
       // ---- bucket order of cloud b: counting sort of n by index[b,n] in shared memory
