@@ -531,11 +531,11 @@ def desc_train_inputs(B, N, M, S, seed):
                 neg_idx=((np.arange(B) + 1) % B).astype(np.int64))
 
 
-def ablation_inputs(seed, B=2, N=2048, M=32, S=4):
+def ablation_inputs(seed, B=2, N=4096, M=128, S=4):
     """Inputs of the ablation-detector fixtures (regenerated from the seed by the consumers): a LiDAR-like cloud shrunk in
     x/z so that balls of radius 2 hold a few .. more than 64 points, FPS nodes, fixed loss weights."""
     d = synth_pair(B, N, M, S, kind="lidar", seed=seed)
-    sc = np.array([0.35, 1.0, 0.35], np.float32).reshape(1, 3, 1)
+    sc = np.array([0.5, 1.0, 0.5], np.float32).reshape(1, 3, 1)
     rng = np.random.default_rng(seed + 7)
     return dict(pc=(d["src_pc"] * sc).astype(np.float32), sn=d["src_sn"], node=(d["src_node"] * sc).astype(np.float32),
                 w_kp=rng.normal(size=(B, 3, M)).astype(np.float32), w_sig=rng.normal(size=(B, M)).astype(np.float32))

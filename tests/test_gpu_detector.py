@@ -386,6 +386,7 @@ def test_ablation_detectors_vs_reference_golden(mode, use_tc):
     assert rel_err(kp.detach().cpu().numpy(), g[mode + "/train_kp"]) < REL
     assert rel_err(sig.detach().cpu().numpy(), g[mode + "/train_sig"]) < REL
     assert abs(loss.item() - float(g[mode + "/loss"])) <= 2e-4 * abs(float(g[mode + "/loss"]))
+    bad, worst = [], 0.0
     for k, p in net.named_parameters():
         ref = g[mode + "/grad/" + k]
         gr = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
@@ -395,11 +396,15 @@ def test_ablation_detectors_vs_reference_golden(mode, use_tc):
             continue
         e_norm = abs(np.linalg.norm(gr) - norm) / max(norm, 1e-12)
         e_el = np.abs(gr[:24] - ref[4:4 + min(24, gr.size)]).max() / max(absmax, 1e-12)
-        # element tolerance: two max-pools over K = 64 route whole gradients through single arg-max rows, and this fixture
-        # has only B*M = 64 groups per channel: ONE arg-max decision flipped by a 1e-7 forward difference moves a sum by
-        # 1/64 .. 1/8 of a typical term, i.e. percent level (tests/test_gpu_vs_reference.py measures the reference's own
-        # fp32-vs-fp64 spread: 1.4e-2 with 8192 groups per channel).  The norm is the tight check.
-        assert e_norm < 5e-3 and e_el < 5e-2, (k, e_norm, e_el)
+        # element tolerance: two max-pools over K = 64 route whole gradients through single arg-max rows (256 groups per
+        # channel here): an arg-max decision flipped by a 1e-7 forward difference moves a sum at the percent level
+        # (tests/test_gpu_vs_reference.py measures the reference's own fp32-vs-fp64 spread: 1.4e-2 with 8192 groups per
+        # channel).  The norm is the tight check.
+        worst = max(worst, e_norm)
+        if not (e_norm < 3e-3 and e_el < 3e-2):
+            bad.append((k, e_norm, e_el))
+    print("ablation %s use_tc=%s: worst gradient norm error %.2e" % (mode, use_tc, worst))
+    assert not bad, bad
     sd = net.state_dict()
     for k in sd:
         if k.endswith("running_mean") or k.endswith("running_var"):

@@ -52,7 +52,7 @@ def records(dev, pk, quick=False):
     out["ball_group_fused"] = {"ms_median": med, "ms_min": best, "algorithmic_bytes": alg_bytes,
                                "achieved_GBs": alg_bytes / (med * 1e-3) / 1e9, "peak_GBs": pk["hbm_gbs"],
                                "frac": alg_bytes / (med * 1e-3) / 1e9 / pk["hbm_gbs"],
-                               "note": "4 launches (partial boxes, histogram + last-CTA scan, scatter to cell-sorted records, warp-per-keypoint query); L2 flushed between iterations"}
+                               "note": "2 launches chained by programmatic dependent launch (bucket-grid build; warp-per-keypoint query with one tensor-map TMA per keypoint); L2 flushed between iterations"}
     # --- reference path for the same result: materialise (B,M,N) distances + reference ball_query kernel + gather
     rb = None if quick else ref_ext("ball_query")
     if rb is not None:

@@ -256,7 +256,7 @@ def golden_ablation(ref):
     """RPN_Detector_KNN / RPN_Detector_Ball (models/networks.py:482-738): eval and train forward, and the gradients of
     L = sum(w_kp * keypoints) + sum(w_sig * sigmas) (ModelDetector cannot select these networks -- the lines are commented
     out at keypoint_detector.py:23-24 -- so the fixture drives the networks directly)."""
-    B, N, M, S, Kn, seed = 2, 2048, 32, 4, 16, 1239
+    B, N, M, S, Kn, seed = 2, 4096, 128, 4, 16, 1239          # 256 groups per channel: one flipped arg-max moves a sum by < 1 %
     d = orc.ablation_inputs(seed, B, N, M, S)
     opt = ref_shim.make_opt(batch_size=B, input_pc_num=N, node_num=M, surface_normal_len=S, node_knn_k_1=Kn)
     P = orc.init_ablation_params(S=S, seed=seed, randomize_bn=True)
