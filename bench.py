@@ -399,12 +399,13 @@ def main():
         step_ms = sum(r["ms"] for r in prof.values())
         if rec.get("flops"):
             ach = rec["flops"] / (rec["ms"] * 1e-3) / 1e12
-            tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+            tf32_peak = pk["bf16_tflops"] / 2.0           # the kernel is event-timed on its own: the BURST figure applies
             roof = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s",
                     "frac": ach / tf32_peak, "traffic": None,
-                    "note": "achieved = algorithmic flops (2*P*Cin*Cout) / CUDA-event time; peak = measured sustained bf16 "
-                            "cuBLAS rate / 2 (TF32 runs at half the bf16 rate; %s); the kernel issues 3 TF32 MMAs per "
+                    "note": "achieved = algorithmic flops (2*P*Cin*Cout) / CUDA-event time of that launch; peak = measured BURST "
+                            "bf16 cuBLAS rate / 2 (TF32 runs at half the bf16 rate; %s); the kernel issues 3 TF32 MMAs per "
                             "algorithmic MAC (3xTF32), so its tensor-pipe issue fraction is 3x frac" % pk["source"],
+                    "frac_vs_sustained_peak": ach / (pk["bf16_tflops_sustained"] / 2.0),
                     "frac_issued_tf32": 3 * ach / tf32_peak, "kernel_ms": rec["ms"], "kernel_share_of_step": rec["ms"] / step_ms,
                     "precision": rec.get("precision", "fp32")}
         else:
