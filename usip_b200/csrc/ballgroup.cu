@@ -187,12 +187,8 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
   if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   __syncwarp();
   asm volatile("griddepcontrol.wait;" ::: "memory");                // the build grid has completed and its writes are visible
-  BxGrid g;
-  {
-    const int4 g0 = __ldcg(reinterpret_cast<const int4*>(grids + b)), g1 = __ldcg(reinterpret_cast<const int4*>(grids + b) + 1);
-    g.o0 = __int_as_float(g0.x); g.o1 = __int_as_float(g0.y); g.inv_h = __int_as_float(g0.z); g.n0 = g0.w;
-    g.n1 = g1.x; g.a0 = g1.y; g.a1 = g1.z; g.ok = g1.w;
-  }
+  const BxGrid g = grids[b];                    // L1-cached: 8 warps x ~14 CTAs per SM read the same 32 bytes (measured: the
+                                                // L2-only load cost 4 us on the whole kernel)
   const float* p = xyz + (size_t)b * 3 * N;
   int32_t* cnt = counts + (size_t)b * BX_MAX_CELLS;
   const unsigned lt = (1u << lane) - 1u;
@@ -203,7 +199,7 @@ bx_query_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restric
   int* hn = hidx[wib][0]; int* sl = hidx[wib][1];
   float4* h0 = hrec[wib][0]; float4* h1 = hrec[wib][1];
   if (active) {
-    const int novf = __ldcg(ovf_cnt + b);
+    const int novf = __ldg(ovf_cnt + b);
     if (novf > BX_OVF) brute = true;
     const bool cfin = fabsf(cx) <= 1e30f && fabsf(cy) <= 1e30f && fabsf(cz) <= 1e30f;
     if (!brute && cfin) {
