@@ -231,28 +231,36 @@ groupmax_bwd_select_kernel(const float* __restrict__ Gout, int ldg, const float*
                            const float* __restrict__ shift, const float* __restrict__ mean,
                            const float* __restrict__ invstd, float* __restrict__ gz, int32_t* __restrict__ argsel,
                            float* __restrict__ part, int Q, int C) {
-  // CTA = 128 q-rows x 128 channels, thread = (row slice, channel)
-  __shared__ float red[2][2][128];
-  const int tile = blockIdx.x, c = blockIdx.y * 128 + (threadIdx.x & 127), rs = threadIdx.x >> 7;
+  // CTA = 128 q-rows x 32 channels, thread = (row slice of 8, channel): 4x the CTAs of the 128-channel tiling (the
+  // 8192 x 512 head only made 256 CTAs, each thread walking 64 rows in turn -- 70 us of exposed load latency)
+  __shared__ float red[2][8][32];
+  const int tile = blockIdx.x, cl = threadIdx.x & 31, c = blockIdx.y * 32 + cl, rs = threadIdx.x >> 5;
   float s1 = 0.f, s2 = 0.f;
   if (c < C) {
     const float sc = scale[c], sh = shift[c], mu = mean ? mean[c] : 0.f, is = invstd ? invstd[c] : 0.f;
+    const bool up = sc >= 0.f;
+    const float* __restrict__ ysrc = up ? gmax : gmin;
+    const int32_t* __restrict__ asrc = up ? amax : amin;
     const int qend = min(Q, (tile + 1) * BW_ROWS);
-    for (int q = tile * BW_ROWS + rs; q < qend; q += 2) {
+#pragma unroll 4
+    for (int q = tile * BW_ROWS + rs; q < qend; q += 8) {
       const size_t i = (size_t)q * C + c;
-      const bool up = sc >= 0.f;
-      const float ys = up ? gmax[i] : gmin[i];
-      const float z = fmaf(ys, sc, sh);
-      const float g = z > 0.f ? Gout[(size_t)q * ldg + c] : 0.f;
-      gz[i] = g; argsel[i] = up ? amax[i] : amin[i];
+      const float ys = ysrc[i];
+      const float go = Gout[(size_t)q * ldg + c];
+      const int a = asrc[i];
+      const float g = fmaf(ys, sc, sh) > 0.f ? go : 0.f;
+      gz[i] = g; argsel[i] = a;
       s1 += g; s2 = fmaf(g, (ys - mu) * is, s2);
     }
   }
-  red[0][rs][threadIdx.x & 127] = s1; red[1][rs][threadIdx.x & 127] = s2;
+  red[0][rs][cl] = s1; red[1][rs][cl] = s2;
   __syncthreads();
-  if (part && threadIdx.x < 128 && c < C) {
-    part[((size_t)tile * 2 + 0) * C + c] = red[0][0][threadIdx.x] + red[0][1][threadIdx.x];
-    part[((size_t)tile * 2 + 1) * C + c] = red[1][0][threadIdx.x] + red[1][1][threadIdx.x];
+  if (part && threadIdx.x < 32 && c < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a += red[0][j][cl]; b += red[1][j][cl]; }
+    part[((size_t)tile * 2 + 0) * C + c] = a;
+    part[((size_t)tile * 2 + 1) * C + c] = b;
   }
 }
 
@@ -280,11 +288,17 @@ groupmax_bwd_apply_kernel(const float* __restrict__ Y, int ldy, const float* __r
     const int4 a4 = *reinterpret_cast<const int4*>(argsel + (size_t)q * C + c);
     const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
     const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+    // per-channel constants as five 16-byte loads (they were twenty scalar loads: the LSU queue was the top stall)
+    const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c)), m4 = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 i4 = __ldg(reinterpret_cast<const float4*>(invstd + c)), p4 = __ldg(reinterpret_cast<const float4*>(c1 + c));
+    const float4 q4 = __ldg(reinterpret_cast<const float4*>(c2 + c));
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, mv[4] = {m4.x, m4.y, m4.z, m4.w}, iv[4] = {i4.x, i4.y, i4.z, i4.w};
+    const float c1v[4] = {p4.x, p4.y, p4.z, p4.w}, c2v[4] = {q4.x, q4.y, q4.z, q4.w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float g = (av[j] == k) ? gv[j] : 0.f;
-      o[j] = scale[c + j] * (g - c1[c + j] - (yv[j] - mean[c + j]) * invstd[c + j] * c2[c + j]);
+      o[j] = sv[j] * (g - c1v[j] - (yv[j] - mv[j]) * iv[j] * c2v[j]);
     }
     *reinterpret_cast<float4*>(GY + (size_t)r * ldo + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -346,6 +360,7 @@ knn_combine_bwd_kernel(const float* __restrict__ GY, int ldg, const float* __res
   __syncthreads();
   const int row0 = blockIdx.x * BW_ROWS, G = B * M * K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(GZ) & 15) == 0);
   for (int c4 = lane; c4 * 4 < C; c4 += 32) {
     float a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
     for (int r = row0 + warp; r < min(row0 + BW_ROWS, G); r += 8) {
@@ -355,9 +370,14 @@ knn_combine_bwd_kernel(const float* __restrict__ GY, int ldg, const float* __res
       const float4 g = *reinterpret_cast<const float4*>(GY + (size_t)r * ldg + c4 * 4);
       const float gv[4] = {g.x, g.y, g.z, g.w};
       float* z = GZ + ((size_t)b * M + j) * ldz + c4 * 4;
+      if (vec) {                                             // one 16-byte L2 reduction instead of four (sm_90+)
+        atomicAdd(reinterpret_cast<float4*>(z), g);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) atomicAdd(z + t, gv[t]);
+      }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        atomicAdd(z + t, gv[t]);
         a0[t] = fmaf(gv[t], dx, a0[t]); a1[t] = fmaf(gv[t], dy, a1[t]); a2[t] = fmaf(gv[t], dz, a2[t]);
       }
     }
@@ -410,29 +430,35 @@ colsum_slow_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out
 }
 
 // wgrad for a NARROW input (Cin <= 8, e.g. the first layer of a point stack: xyz + normals):
-//   gW[m, j] += sum_r GY[r, m] * act(X)[r, j].   HBM-bound on GY ([P, Cout] read once); thread = one output channel m of
-// one row subset, 8 accumulators; GY loads are coalesced across m, the X row is a 32-byte broadcast.
-__global__ void __launch_bounds__(256)
+//   gW[m, j] += sum_r GY[r, m] * act(X)[r, j].   HBM-bound on GY ([P, Cout] read once).  Thread = FOUR output channels of
+// one row subset (one 16-byte GY load per row, 4 x 8 accumulators); the X row is a 32-byte broadcast shared by the Cout/4
+// threads of the row and its activation is computed once per thread and row.  (Round 2, first version: one channel per
+// thread = one 4-byte load and 30 instructions per GY element, 137 us for the 262144 x 64 first layer = 0.55 TB/s.)
+__global__ void __launch_bounds__(256, 2)
 wgrad_narrow_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__ X, int ldx,
                     const float* __restrict__ in_scale, const float* __restrict__ in_shift, int in_relu,
                     float* __restrict__ gW, int ldw, int P, int Cout, int Cin) {
-  __shared__ float red[256][9];
-  const int m = threadIdx.x % Cout, rl = threadIdx.x / Cout, rpp = 256 / Cout;      // host: Cout in {32, 64, 128, 256}
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  __shared__ float red[256][33];
+  const int tpr = Cout >> 2, rpp = 256 / tpr;                  // host: Cout in {32, 64, 128, 256}
+  const int c4 = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = (in_scale && j < Cin) ? in_scale[j] : 1.f; sh[j] = (in_shift && j < Cin) ? in_shift[j] : 0.f; }
   const bool x8 = (ldx == 8) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   const long long step = (long long)gridDim.x * rpp;
   for (long long r0 = (long long)blockIdx.x * rpp + rl; r0 < P; r0 += 4 * step) {
-    float g[4];
-    float4 xa[4], xb[4];
+    float4 g[4], xa[4], xb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {                              // four independent rows in flight per thread
       const long long r = r0 + u * step;
-      g[u] = 0.f; xa[u] = xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      g[u] = xa[u] = xb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < P) {
-        g[u] = __ldcs(GY + (size_t)r * ldg + m);
+        g[u] = __ldcs(reinterpret_cast<const float4*>(GY + (size_t)r * ldg + c4 * 4));
         if (x8) {
           xa[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8)); xb[u] = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * 8 + 4));
         } else {
@@ -445,23 +471,27 @@ wgrad_narrow_kernel(const float* __restrict__ GY, int ldg, const float* __restri
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float x[8] = {xa[u].x, xa[u].y, xa[u].z, xa[u].w, xb[u].x, xb[u].y, xb[u].z, xb[u].w};
+      const float gq[4] = {g[u].x, g[u].y, g[u].z, g[u].w};   // rows past P carry g = 0
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = fmaf(x[j], sc[j], sh[j]);
         if (in_relu) v = fmaxf(v, 0.f);
-        acc[j] = fmaf(g[u], j < Cin ? v : 0.f, acc[j]);      // rows past P carry g = 0
+        v = j < Cin ? v : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q][j] = fmaf(gq[q], v, acc[q][j]);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][q * 8 + j] = acc[q][j];
   __syncthreads();
-  if (threadIdx.x < Cout) {
-    for (int j = 0; j < Cin; ++j) {
-      float t = 0.f;
-      for (int k = 0; k < rpp; ++k) t += red[k * Cout + threadIdx.x][j];
-      atomicAdd(gW + (size_t)threadIdx.x * ldw + j, t);
-    }
+  for (int i = threadIdx.x; i < Cout * Cin; i += 256) {
+    const int m = i / Cin, j = i - m * Cin;
+    float t = 0.f;
+    for (int k = 0; k < rpp; ++k) t += red[k * tpr + (m >> 2)][(m & 3) * 8 + j];
+    atomicAdd(gW + (size_t)m * ldw + j, t);
   }
 }
 
@@ -689,7 +719,7 @@ extern "C" int usip_groupmax_bwd_select(const float* Gout, int ldg, const float*
                                         const float* shift, const float* mean, const float* invstd, float* gz,
                                         int32_t* argsel, float* part, int Q, int C, void* stream) {
   USIP_REQUIRE(Gout && gmax && gmin && amax && amin && scale && shift && gz && argsel, "groupmax_bwd_select: bad args");
-  dim3 grid(cdiv(Q, BW_ROWS), cdiv(C, 128));
+  dim3 grid(cdiv(Q, BW_ROWS), cdiv(C, 32));
   groupmax_bwd_select_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Gout, ldg, gmax, gmin, amax, amin, scale, shift, mean,
                                                                      invstd, gz, argsel, part, Q, C);
   return check_launch("groupmax_bwd_select_kernel");
@@ -707,6 +737,9 @@ extern "C" int usip_groupmax_bwd_apply(const float* Y, int ldy, const float* gz,
                                        const float* scale, const float* mean, const float* invstd, const float* c1,
                                        const float* c2, float* GY, int ldo, int K, int P, int C, void* stream) {
   USIP_REQUIRE(Y && gz && argsel && GY && C % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0, "groupmax_bwd_apply: bad args");
+  USIP_REQUIRE(((reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(invstd) |
+                 reinterpret_cast<uintptr_t>(c1) | reinterpret_cast<uintptr_t>(c2)) & 15) == 0,
+               "groupmax_bwd_apply: per-channel vectors must be 16-byte aligned");
   size_t total = (size_t)P * (C / 4);
   int blocks = (int)min((size_t)148 * 16, cdiv64(total, 256));
   groupmax_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Y, ldy, gz, argsel, scale, mean, invstd, c1, c2, GY,
@@ -778,8 +811,9 @@ extern "C" int usip_wgrad(const float* GY, int ldg, const float* X, int ldx, con
     int rc = wgrad_tc(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin, precision == 4, (cudaStream_t)stream);
     if (rc != -2) return rc;
   }
-  if (Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) && P >= 4096) {
-    const int rpp = 256 / Cout;
+  if (Cin <= 8 && (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) && P >= 4096 && ldg % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(GY) & 15) == 0) {
+    const int rpp = 1024 / Cout;
     const int blocks = (int)min((long long)cdiv(P, rpp * 8), 148LL * 2);      // few CTAs: each ends in Cout*Cin atomics on the same words
     wgrad_narrow_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(GY, ldg, X, ldx, in_scale, in_shift, in_relu, gW, ldw, P, Cout, Cin);
     return check_launch("wgrad_narrow_kernel");

@@ -109,20 +109,37 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
       sc = __ldg(reinterpret_cast<const float4*>(in_scale + n0 + cb * 4));
       sh = __ldg(reinterpret_cast<const float4*>(in_shift + n0 + cb * 4));
     }
-    for (int it = grp; it < nst; it += 2) {
-      const int s = it % STAGES;
-      wt_mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
-      const uint32_t a_hi = base + s * SM::STAGE, a_lo = a_hi + SM::A_HALF;
-      const uint32_t b_hi = a_lo + SM::A_HALF, b_lo = b_hi + SM::B_HALF;
-      const int r0 = r_begin + it * WT_BK;
-      {   // ---- A: 8 float4 per thread
-        float4 x[8];
+    // The group's work is a stream of batches of <= 8 float4 per thread: batch 0 of an iteration is the A operand, the rest
+    // are the B operand.  Two register sets alternate: the loads of batch g+1 are in flight while batch g is converted and
+    // stored (round 1 waited for every batch of 8 loads in turn -- three exposed memory latencies per 32-row stage).
+    constexpr int NBB = (NJB + 7) / 8, NB = 1 + NBB;
+    const int niter = nst > grp ? (nst - grp + 1) / 2 : 0;
+    const int total = niter * NB;
+    const bool a_cols = m0 + ca * 4 < Cout;
+    auto load = [&](float4 (&x)[8], int g) {
+      const int b = g % NB, r0 = r_begin + (grp + 2 * (g / NB)) * WT_BK;
+      if (b == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = r0 + ra + 4 * j;
           // output channels past Cout (a 64-wide layer in the 128-row UMMA tile) are zero rows of the operand
-          x[j] = (r < r_end && m0 + ca * 4 < Cout) ? __ldg(reinterpret_cast<const float4*>(GY + (size_t)r * ldg + m0 + ca * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x[j] = (r < r_end && a_cols) ? __ldg(reinterpret_cast<const float4*>(GY + (size_t)r * ldg + m0 + ca * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      } else {
+        const int jb = (b - 1) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = r0 + rb + RPPB * (jb + j);
+          x[j] = (jb + j < NJB && r < r_end) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldx + n0 + cb * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto process = [&](const float4 (&x)[8], int g) {
+      const int b = g % NB, it = grp + 2 * (g / NB), s = it % STAGES;
+      const uint32_t a_hi = base + s * SM::STAGE, a_lo = a_hi + SM::A_HALF;
+      const uint32_t b_hi = a_lo + SM::A_HALF, b_lo = b_hi + SM::B_HALF;
+      if (b == 0) {
+        wt_mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rl = ra + 4 * j;
@@ -134,34 +151,38 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
-      }
-      // ---- B: NJB float4 per thread, in batches of 8
-#pragma unroll
-      for (int jb = 0; jb < NJB; jb += 8) {
-        float4 x[8];
+      } else {
+        const int jb = (b - 1) * 8, r0 = r_begin + it * WT_BK;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = r0 + rb + RPPB * (jb + j);
-          x[j] = (jb + j < NJB && r < r_end) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldx + n0 + cb * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          if (jb + j < NJB) {
+            const int rl = rb + RPPB * (jb + j);
+            float v[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+            if (in_scale) { v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y); v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w); }
+            if (in_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+            if (r0 + rl >= r_end) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+            uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (jb + j >= NJB) break;
-          const int rl = rb + RPPB * (jb + j);
-          float v[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
-          if (in_scale) { v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y); v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w); }
-          if (in_relu) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-          if (r0 + rl >= r_end) { v[0] = v[1] = v[2] = v[3] = 0.f; }
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { hi[q] = wt_tf32(v[q]); lo[q] = wt_tf32(v[q] - __uint_as_float(hi[q])); }
-          const uint32_t off = wt_off(rl, cb >> 3, MBB, cb & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            for (int q = 0; q < 4; ++q) { hi[q] = wt_tf32(v[q]); lo[q] = wt_tf32(v[q] - __uint_as_float(hi[q])); }
+            const uint32_t off = wt_off(rl, cb >> 3, MBB, cb & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          }
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      wt_mbar_arrive(full_bar(s));
+      if (b == NB - 1) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        wt_mbar_arrive(full_bar(s));
+      }
+    };
+    float4 x0[8], x1[8];
+    if (total > 0) load(x0, 0);
+#pragma unroll 1
+    for (int g = 0; g < total; g += 2) {
+      if (g + 1 < total) load(x1, g + 1);
+      process(x0, g);
+      if (g + 2 < total) load(x0, g + 2);
+      if (g + 1 < total) process(x1, g + 1);
     }
   } else if (warp == 4) {
     // ================================ MMA issuer ===============================================
@@ -196,6 +217,7 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
     wt_mbar_wait(done_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = m0 + warp * 32 + lane;                  // gW row (output channel) of this thread
+    const bool vec = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(gW) & 15) == 0);
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
@@ -219,8 +241,15 @@ wgrad_tc_kernel(const float* __restrict__ GY, int ldg, const float* __restrict__
                    : "memory");
       if (m < Cout) {
         float* dst = gW + (size_t)m * ldw + n0 + ch * 32;
+        if (vec) {                                         // 16-byte L2 reductions (REDG.ADD.F32x4): a quarter of the atomic traffic
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
       }
     }
   }
