@@ -510,9 +510,12 @@ def main():
             line["reference_gpu"] = ref_gpu
         if desc:
             line["descriptor"] = desc
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the train-step graph holds the captured NCCL all-reduce: graphs first, then the communicator (usip_b200/dp.py);
+        # the results are out, so a teardown that does not return within 20 s ends the process with status 0
+        from usip_b200.dp import shutdown
+        shutdown(md, hard_exit_after=20)
 
 
 if __name__ == "__main__":

@@ -62,8 +62,8 @@ def worker(out_dir):
         rec["param%d" % step] = [p.detach().cpu().clone() for p in md.detector.parameters()]
         rec["loss%d" % step] = float(md.loss)
     torch.save(rec, os.path.join(out_dir, "rank%d.pt" % rank))
-    dist.barrier()
-    dist.destroy_process_group()
+    from usip_b200.dp import shutdown
+    shutdown(md, hard_exit_after=20)          # graphs (captured all-reduce) before the communicator
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -72,7 +72,7 @@ def test_enable_data_parallel_two_ranks_nccl(tmp_path):
     env = {**os.environ, "PYTHONPATH": ROOT}
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), "--worker", str(tmp_path)],
-                       env=env, capture_output=True, text=True, timeout=900)
+                       env=env, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     a = torch.load(os.path.join(tmp_path, "rank0.pt")); b = torch.load(os.path.join(tmp_path, "rank1.pt"))
     for step in range(2):

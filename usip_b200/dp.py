@@ -6,6 +6,10 @@ exchange on the path is the gradient sum, so all parameter `.grad`s are made vie
 (1,198,724 floats = 4.79 MB for RPN_Detector) that is all-reduced once (NCCL over NVLink/NVSwitch on the GPU box,
 gloo in the CPU tests).  BatchNorm statistics stay per rank, which is exactly DataParallel's per-replica semantics.
 """
+import gc
+import os
+import threading
+
 import torch
 import torch.distributed as dist
 
@@ -56,3 +60,30 @@ class FlatGradAllReduce:
         base = self.flat.data_ptr()
         end = base + self.flat.numel() * self.flat.element_size()
         return all(p.grad is not None and base <= p.grad.data_ptr() < end for p in self.params)
+
+
+def shutdown(*models, hard_exit_after=None):
+    """Orderly end of a data-parallel job: the models' CUDA graphs (which hold the captured NCCL all-reduce) are destroyed
+    first, then the device is drained, then the process group.  Destroying the communicator under a live graph deadlocks
+    (seen on 2xB200: both ranks hung in destroy_process_group after a finished run).  `hard_exit_after` (seconds) arms a
+    watchdog that ends the process with status 0 if the teardown itself does not return -- for benchmark / test drivers
+    whose results are already written."""
+    for m in models:
+        if hasattr(m, "release_cuda_graphs"):
+            m.release_cuda_graphs()
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not dist.is_initialized():
+        return
+    timer = None
+    if hard_exit_after:
+        timer = threading.Timer(float(hard_exit_after), lambda: os._exit(0))
+        timer.daemon = True
+        timer.start()
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        if timer is not None:
+            timer.cancel()

@@ -72,6 +72,16 @@ class ModelDetector():
         if self._dp is not None:
             self._dp.allreduce_mean()
 
+    def release_cuda_graphs(self):
+        """Drop the captured step graphs (they are re-captured on demand).  A graph that holds an NCCL all-reduce must be
+        destroyed BEFORE its communicator: call this (or usip_b200.dp.shutdown) ahead of destroy_process_group()."""
+        for k in ("_tgraph", "_tgraph_in", "_tgraph_out", "_graph", "_graph_in", "_graph_out"):
+            self.__dict__.pop(k, None)
+        if self._train_graph_key != "failed":
+            self._train_graph_key = None
+        if hasattr(self, "_graph_key"):
+            self._graph_key = None
+
     # ------------------------------------------------------------------ reference API
     _INPUT_FIELDS = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "src_R_dst", "src_scale_dst", "src_shift_dst")
 
