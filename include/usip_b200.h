@@ -96,6 +96,13 @@ int usip_knn_gather_f32(const float* src, const int32_t* idx, float* out,
 int usip_som_assign_f32(const float* xyz, const float* node, int32_t* min_idx, int32_t* count,
                         int B, int N, int M, void* stream);
 
+/* The same result through a cell grid over the M <= 1024 nodes of each cloud (csrc/nngrid.cu): the nodes are counting-sorted
+ * into ~M/2 cells, every point searches the cell shells around it until nothing outside can be closer -- ~50 distance
+ * evaluations per point instead of M.  scratch: usip_som_assign_grid_scratch_bytes(B, M) bytes, 16-byte aligned. */
+size_t usip_som_assign_grid_scratch_bytes(int B, int M);
+int usip_som_assign_grid_f32(const float* xyz, const float* node, int32_t* min_idx, int32_t* count, void* scratch,
+                             size_t scratch_bytes, int B, int N, int M, void* stream);
+
 /* Stable counting sort of the points of every cloud by node id.
  *   seg_off (B,M+1) i32 : rows [seg_off[m], seg_off[m+1]) of cloud b belong to node m
  *   perm    (B,N)   i32 : sorted position -> original point index n (ascending n inside a node)
@@ -201,6 +208,15 @@ int usip_l2norm_to_bcm(const float* X, int ldx, float* out, float* norm_out, int
  * min_d (B,Ma) f32, arg (B,Ma) i32.  packed: B*Ma u64 scratch. */
 int usip_pairwise_min_f32(const float* a, const float* b, float* min_d, int32_t* arg,
                           unsigned long long* packed, int B, int Ma, int Nb, void* stream);
+
+/* The same result (bit-identical min_d and arg, same tie rule) for FEW queries against a LARGE point set -- the
+ * keypoint-on-point-cloud searches of keypoint_detector.py:187-197 (512 keypoints against 16384 points per cloud): the
+ * cloud is counting-sorted into a cell grid (one CTA per cloud) and every query scans the cell shells around it until
+ * nothing outside can be closer.  scratch: usip_pairwise_min_grid_scratch_bytes(B, Nb) bytes, 16-byte aligned, contents
+ * irrelevant on entry. */
+size_t usip_pairwise_min_grid_scratch_bytes(int B, int Nb);
+int usip_pairwise_min_grid_f32(const float* a, const float* b, float* min_d, int32_t* arg, void* scratch,
+                               size_t scratch_bytes, int B, int Ma, int Nb, void* stream);
 
 /* ChamferLoss_Brute sigma branch (losses.py:79-97) from the two pairwise-min results:
  * out[0]=loss, out[1]=chamfer_pure, out[2]=chamfer_weighted. */

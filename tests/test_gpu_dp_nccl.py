@@ -103,9 +103,12 @@ def test_enable_data_parallel_two_ranks_nccl(tmp_path):
             md.loss.backward()
             grads.append([p.grad.detach().clone() for p in md.detector.parameters()])
         mean = [(g0 + g1) * 0.5 for g0, g1 in zip(*grads)]
+        gmax = max(float(m.abs().max()) for m in mean)
         for k, (m, got) in enumerate(zip(mean, a["grad%d" % step])):
             scale = max(float(m.abs().max()), 1e-12)
-            assert float((m.cpu() - got).abs().max()) <= 2e-5 * scale + 1e-9, (step, k)
+            # conv biases in front of a BatchNorm have an analytically zero gradient: what is left there is summation
+            # noise (1e-7 of the largest gradient), so the bound has a floor relative to the whole gradient
+            assert float((m.cpu() - got).abs().max()) <= 2e-5 * scale + 1e-6 * gmax, (step, k, scale, gmax)
         # continue the single-process trajectory from the data-parallel parameters (Adam state is per process)
         with torch.no_grad():
             for p, v in zip(md.detector.parameters(), a["param%d" % step]):
@@ -115,6 +118,8 @@ def test_enable_data_parallel_two_ranks_nccl(tmp_path):
             lr = md.opt.lr
             for s0, m, v in zip(start, mean, a["param0"]):
                 want = s0 - lr * m / (m.abs() + 1e-8)
+                if float(m.abs().max()) < 1e-5 * gmax:      # analytic-zero gradient (noise only): sign(g) is arbitrary
+                    continue
                 solid = m.abs() > 1e-3 * m.abs().max()
                 assert float((want.cpu() - v).abs()[solid.cpu()].max()) <= 0.02 * lr + 1e-7
 

@@ -462,6 +462,86 @@ def test_pairwise_min_all_paths_vs_oracle(B, Ma, Nb):
     assert np.array_equal(arg.cpu().numpy(), ra) and np.array_equal(d.cpu().numpy(), rd)
 
 
+@pytest.mark.parametrize("case", ["lidar", "ties", "flat", "identical", "far_queries", "nonfinite", "small", "volume"])
+def test_pairwise_min_grid_equals_brute_force(case):
+    """usip_pairwise_min_grid_f32 (cell grid + shell search) against the brute-force kernels on the same inputs: distances
+    and first-index arg-min bit for bit -- exact ties, duplicated points, degenerate extents, queries far outside the cloud
+    (ring fallback), non-finite points and queries."""
+    from usip_b200 import ops
+    rng = np.random.default_rng(["lidar", "ties", "flat", "identical", "far_queries", "nonfinite", "small", "volume"].index(case))
+    B, Ma, Nb = 4, 512, 16384
+    if case == "lidar":
+        r = np.abs(rng.normal(0, 15, (B, Nb))) + 1; th = rng.uniform(0, 2 * np.pi, (B, Nb))
+        b = np.stack([r * np.cos(th), rng.normal(-1.5, 0.3, (B, Nb)), r * np.sin(th)], 1).astype(np.float32)
+        a = b[:, :, rng.integers(0, Nb, Ma)] + rng.normal(0, 0.5, (B, 3, Ma)).astype(np.float32)
+    elif case == "ties":
+        b = np.round(rng.normal(size=(B, 3, Nb)) * 3).astype(np.float32)             # integer lattice: masses of exact ties
+        a = np.round(rng.normal(size=(B, 3, Ma)) * 3).astype(np.float32) + 0.5
+    elif case == "flat":
+        b = rng.uniform(-30, 30, (B, 3, Nb)).astype(np.float32); b[:, 1] = 2.0        # zero extent along y
+        a = rng.uniform(-35, 35, (B, 3, Ma)).astype(np.float32)
+    elif case == "identical":
+        b = np.full((B, 3, Nb), 1.25, np.float32)
+        a = rng.normal(size=(B, 3, Ma)).astype(np.float32)
+    elif case == "far_queries":
+        b = rng.uniform(-1, 1, (B, 3, Nb)).astype(np.float32)
+        a = (rng.normal(size=(B, 3, Ma)) * 50).astype(np.float32)
+        a[:, :, :64] = rng.uniform(-1, 1, (B, 3, 64)).astype(np.float32)
+    elif case == "nonfinite":
+        b = rng.uniform(-10, 10, (B, 3, Nb)).astype(np.float32)
+        b[0, 0, ::7] = np.nan; b[1, 2, ::5] = np.inf; b[2, :, :] = np.nan; b[3, 1, 3] = -np.inf
+        a = rng.uniform(-10, 10, (B, 3, Ma)).astype(np.float32)
+        a[:, 0, 5] = np.nan; a[:, 1, 9] = np.inf
+    elif case == "small":
+        B, Ma, Nb = 3, 37, 301
+        b = rng.normal(size=(B, 3, Nb)).astype(np.float32); a = rng.normal(size=(B, 3, Ma)).astype(np.float32)
+    else:                                                                             # uniform volume, many cells per axis
+        b = rng.uniform(-1, 1, (B, 3, Nb)).astype(np.float32)
+        a = rng.uniform(-1.2, 1.2, (B, 3, Ma)).astype(np.float32)
+    dg, ag = ops.pairwise_min(cu(a), cu(b), method="grid")
+    db, ab = ops.pairwise_min(cu(a), cu(b), method="brute")
+    assert torch.equal(ag, ab), int((ag != ab).sum())
+    assert torch.equal(dg.view(torch.int32), db.view(torch.int32))
+
+
+@pytest.mark.parametrize("case", ["kitti", "modelnet", "ties", "flat", "outliers", "nonfinite", "tiny"])
+def test_som_assign_grid_equals_brute_force(case):
+    """usip_som_assign_grid_f32 against the brute-force scan: nearest-node index (smallest m on ties) and per-node counts
+    identical -- node sets from FPS-like subsets, lattice ties, degenerate extents, points far from every node, non-finite
+    points and nodes."""
+    from usip_b200 import ops
+    rng = np.random.default_rng(["kitti", "modelnet", "ties", "flat", "outliers", "nonfinite", "tiny"].index(case) + 10)
+    B, N, M = 4, 16384, 512
+    if case == "kitti":
+        r = np.abs(rng.normal(0, 15, (B, N))) + 1; th = rng.uniform(0, 2 * np.pi, (B, N))
+        x = np.stack([r * np.cos(th), rng.normal(-1.5, 0.3, (B, N)), r * np.sin(th)], 1).astype(np.float32)
+        node = x[:, :, rng.choice(N, M, replace=False)] + rng.normal(0, 0.05, (B, 3, M)).astype(np.float32)
+    elif case == "modelnet":
+        B, N, M = 6, 5000, 64
+        x = rng.normal(size=(B, 3, N)).astype(np.float32); x /= np.linalg.norm(x, axis=1, keepdims=True)
+        node = x[:, :, rng.choice(N, M, replace=False)].copy()
+    elif case == "ties":
+        x = np.round(rng.normal(size=(B, 3, N)) * 3).astype(np.float32) + 0.5
+        node = np.round(rng.normal(size=(B, 3, M)) * 3).astype(np.float32)
+        node[:, :, M // 2:M // 2 + 40] = node[:, :, :40]                              # duplicated nodes
+    elif case == "flat":
+        x = rng.uniform(-30, 30, (B, 3, N)).astype(np.float32); x[:, 1] = 0.0
+        node = rng.uniform(-30, 30, (B, 3, M)).astype(np.float32); node[:, 1] = 0.0
+    elif case == "outliers":
+        x = (rng.normal(size=(B, 3, N)) * 40).astype(np.float32)
+        node = rng.uniform(-1, 1, (B, 3, M)).astype(np.float32)
+    elif case == "nonfinite":
+        x = rng.uniform(-10, 10, (B, 3, N)).astype(np.float32); x[0, 0, ::9] = np.nan; x[1, 2, ::11] = np.inf
+        node = rng.uniform(-10, 10, (B, 3, M)).astype(np.float32); node[2, 1, ::3] = np.nan; node[3] = np.inf
+    else:
+        B, N, M = 2, 1500, 70
+        x = rng.normal(size=(B, 3, N)).astype(np.float32); node = rng.normal(size=(B, 3, M)).astype(np.float32)
+    ig, cg = ops.som_assign(cu(x), cu(node), method="grid")
+    ib, cb = ops.som_assign(cu(x), cu(node), method="brute")
+    assert torch.equal(ig, ib), int((ig != ib).sum())
+    assert torch.equal(cg, cb)
+
+
 def test_knn_gather_matches_reference_semantics():
     """operations.knn_gather_by_indexing / knn_gather_wrapper (operations.py:243-287): out[b,c,n,k] = src[b,c,I[b,n,k]],
     i.e. the expand + torch.gather of the reference, bit for bit (pure data movement)."""

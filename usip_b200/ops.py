@@ -158,14 +158,23 @@ def knn_gather(src, idx):
 
 
 # ----------------------------------------------------------------------------- grouping
-def som_assign(xyz, node, count=None):
+def som_assign(xyz, node, count=None, method="auto"):
+    """Nearest node of every point (som.query_topk, k = 1).  method: "auto" | "brute" | "grid" (identical results): the grid
+    path bins the nodes into cells and searches the shells around each point (usip_som_assign_grid_f32)."""
     _req(xyz, f32, "x"); _req(node, f32, "node")
     B, _, N = xyz.shape
     M = node.shape[2]
     min_idx = torch.empty((B, N), dtype=i32, device=xyz.device)
     if count is None:
         count = torch.zeros((B, M), dtype=i32, device=xyz.device)
-    check(_lib.load().usip_som_assign_f32(_p(xyz), _p(node), _p(min_idx), _p(count), B, N, M, _stream()),
+    lib = _lib.load()
+    if method == "grid" or (method == "auto" and 64 <= M <= 1024 and N >= 1024):
+        nbytes = int(lib.usip_som_assign_grid_scratch_bytes(B, M))
+        scratch = torch.empty(((nbytes + 15) // 16, 4), dtype=i32, device=xyz.device)
+        check(lib.usip_som_assign_grid_f32(_p(xyz), _p(node), _p(min_idx), _p(count), _p(scratch), nbytes, B, N, M, _stream()),
+              "usip_som_assign_grid_f32")
+        return min_idx, count
+    check(lib.usip_som_assign_f32(_p(xyz), _p(node), _p(min_idx), _p(count), B, N, M, _stream()),
           "usip_som_assign_f32")
     return min_idx, count
 
@@ -281,15 +290,26 @@ def head_finalize(out4, cluster_mean, lb, B, M):
 
 
 # ----------------------------------------------------------------------------- losses
-def pairwise_min(a, b):
-    """a (B,3,Ma), b (B,3,Nb) -> (min_d (B,Ma) f32, arg (B,Ma) i32)."""
+# databases at least this large go through the cell grid (usip_pairwise_min_grid_f32); smaller ones stay brute force
+PAIRWISE_MIN_GRID_FROM = 4096
+
+
+def pairwise_min(a, b, method="auto"):
+    """a (B,3,Ma), b (B,3,Nb) -> (min_d (B,Ma) f32, arg (B,Ma) i32).  method: "auto" | "brute" | "grid" (same result)."""
     _req(a, f32, "a"); _req(b, f32, "b")
     B, _, Ma = a.shape
     Nb = b.shape[2]
     d = torch.empty((B, Ma), dtype=f32, device=a.device)
     arg = torch.empty((B, Ma), dtype=i32, device=a.device)
+    lib = _lib.load()
+    if method == "grid" or (method == "auto" and Nb >= PAIRWISE_MIN_GRID_FROM):
+        nbytes = int(lib.usip_pairwise_min_grid_scratch_bytes(B, Nb))
+        scratch = torch.empty(((nbytes + 15) // 16, 4), dtype=i32, device=a.device)
+        check(lib.usip_pairwise_min_grid_f32(_p(a), _p(b), _p(d), _p(arg), _p(scratch), nbytes, B, Ma, Nb, _stream()),
+              "usip_pairwise_min_grid_f32")
+        return d, arg
     packed = torch.empty((B, Ma), dtype=torch.int64, device=a.device)
-    check(_lib.load().usip_pairwise_min_f32(_p(a), _p(b), _p(d), _p(arg), _p(packed), B, Ma, Nb, _stream()),
+    check(lib.usip_pairwise_min_f32(_p(a), _p(b), _p(d), _p(arg), _p(packed), B, Ma, Nb, _stream()),
           "usip_pairwise_min_f32")
     if Nb <= 2048:
         _lib.LAUNCHES[0] -= 2          # small databases take the single-kernel path (no init / finish launches)
