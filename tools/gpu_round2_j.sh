@@ -11,6 +11,7 @@ try:
 except Exception as e: print('ERR', e)
 PY
 tail -2 gpurun_out/wgrad_new_$TAG.err
+python tools/nn_microbench.py > gpurun_out/nn_micro_$TAG.json 2> gpurun_out/nn_micro_$TAG.err; cat gpurun_out/nn_micro_$TAG.json; tail -2 gpurun_out/nn_micro_$TAG.err
 for f in test_gpu_ops test_gpu_detector test_gpu_vs_reference; do
   timeout 1500 python -m pytest tests/$f.py -m gpu -q -s --timeout=900 -p no:cacheprovider > gpurun_out/pytest_${f}_$TAG.log 2>&1
   echo "== $f: $(tail -1 gpurun_out/pytest_${f}_$TAG.log)"

@@ -208,7 +208,35 @@ __device__ __forceinline__ void ng_search(float ax, float ay, float az, const Ng
   if (!done) { scan(0, cnt); reduce(); }                          // far query: the whole sorted set (duplicates are harmless)
 }
 
-// One warp per query.
+// One warp per query.  The cell ranges of a shell are fetched by all lanes at once (lane = one range: a face row's whole x
+// span, or one end cell of an interior row), then the candidates of up to 32 ranges are walked as ONE flattened list -- a
+// warp prefix sum over the range lengths, a 5-step shuffle search for the owner of candidate k -- so a ring costs two
+// dependent memory round trips (cell bounds, then points) however its points are spread over the cells.
+__device__ __forceinline__ void ng_warp_ranges(int s, int len, int lane, const float4* __restrict__ pts, float ax, float ay,
+                                               float az, float& best, int& bidx) {
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  const int excl = incl - len;
+  for (int k0 = 0; k0 < total; k0 += 32) {
+    const int k = k0 + lane;
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+      const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+      if (k >= v) lo += step;
+    }
+    const int sj = __shfl_sync(0xffffffffu, s, lo), ej = __shfl_sync(0xffffffffu, excl, lo);
+    if (k < total) {
+      const float4 p = __ldg(pts + sj + (k - ej));
+      const float d = sqdist_rn(ax, ay, az, p.x, p.y, p.z);
+      const int n = __float_as_int(p.w);
+      if (d < best || (d == best && n < bidx)) { best = d; bidx = n; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ng_query_kernel(const float* __restrict__ a, int Ma, const float4* __restrict__ sorted, const int32_t* __restrict__ cell_start,
                 const NgGrid* __restrict__ grids, int N, float* __restrict__ min_d, int32_t* __restrict__ arg, int total) {
@@ -219,9 +247,61 @@ ng_query_kernel(const float* __restrict__ a, int Ma, const float4* __restrict__ 
   const float ax = __ldg(pa + i), ay = __ldg(pa + Ma + i), az = __ldg(pa + 2 * Ma + i);
   const NgGrid g = ng_load_grid(grids + b);
   const int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
+  const float4* pts = sorted + (size_t)b * N;
   const int cnt = __ldg(cs + g.nx * g.ny * g.nz);
   float best = INFINITY; int bidx = 0x7fffffff;
-  if (ng_finite3(ax, ay, az) && cnt > 0) ng_search<true>(ax, ay, az, g, cs, sorted + (size_t)b * N, cnt, lane, best, bidx);
+  auto reduce = [&]() {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+  };
+  if (ng_finite3(ax, ay, az) && cnt > 0) {
+    const int cx = ng_cell1(ax, g.ox, g.inv_h, g.nx), cy = ng_cell1(ay, g.oy, g.inv_h, g.ny), cz = ng_cell1(az, g.oz, g.inv_h, g.nz);
+    bool done = false;
+    for (int r = 1; r <= NG_MAXRING && !done; ++r) {             // r = 1 scans the whole 3x3x3 cube, r > 1 the shell only
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1), y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+      const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+      const int ny_r = y1 - y0 + 1, nslots = 2 * (z1 - z0 + 1) * ny_r;     // two range slots per (z, y) row
+      for (int j0 = 0; j0 < nslots; j0 += 32) {
+        const int j = j0 + lane;
+        int s = 0, len = 0;
+        if (j < nslots) {
+          const int row = j >> 1, which = j & 1, z = z0 + row / ny_r, y = y0 + row % ny_r;
+          const int base = (z * g.ny + y) * g.nx;
+          const bool face = (r == 1) || z == cz - r || z == cz + r || y == cy - r || y == cy + r;
+          int ca = -1, cb = -1;                                   // cells [ca, cb] of this row
+          if (face) { if (which == 0) { ca = x0; cb = x1; } }
+          else if (which == 0) { if (cx - r >= 0) ca = cb = cx - r; }
+          else { if (cx + r < g.nx) ca = cb = cx + r; }
+          if (ca >= 0) { s = __ldg(cs + base + ca); len = __ldg(cs + base + cb + 1) - s; }
+        }
+        ng_warp_ranges(s, len, lane, pts, ax, ay, az, best, bidx);
+      }
+      reduce();
+      // everything outside the cube of half-width r is at least `lb` away (faces beyond the grid do not count)
+      float lb = INFINITY;
+      if (cx - r > 0) lb = fminf(lb, ax - (g.ox + (float)(cx - r) * g.h));
+      if (cx + r < g.nx - 1) lb = fminf(lb, (g.ox + (float)(cx + r + 1) * g.h) - ax);
+      if (cy - r > 0) lb = fminf(lb, ay - (g.oy + (float)(cy - r) * g.h));
+      if (cy + r < g.ny - 1) lb = fminf(lb, (g.oy + (float)(cy + r + 1) * g.h) - ay);
+      if (cz - r > 0) lb = fminf(lb, az - (g.oz + (float)(cz - r) * g.h));
+      if (cz + r < g.nz - 1) lb = fminf(lb, (g.oz + (float)(cz + r + 1) * g.h) - az);
+      if (lb == INFINITY) { done = true; break; }                 // the cube covers the grid: every point was seen
+      lb = fmaxf(lb - 1e-3f * g.h, 0.f);                          // cell assignment rounds: keep a margin of h/1000
+      if (best < lb * lb) done = true;
+    }
+    if (!done) {                                                  // far query: the whole sorted cloud (duplicates are harmless)
+      for (int t = lane; t < cnt; t += 32) {
+        const float4 p = __ldg(pts + t);
+        const float d = sqdist_rn(ax, ay, az, p.x, p.y, p.z);
+        const int n = __float_as_int(p.w);
+        if (d < best || (d == best && n < bidx)) { best = d; bidx = n; }
+      }
+      reduce();
+    }
+  }
   if (lane == 0) {
     const bool none = !(best < INFINITY);
     const size_t o = (size_t)b * Ma + i;

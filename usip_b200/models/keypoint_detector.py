@@ -122,11 +122,15 @@ class ModelDetector():
 
     def forward_siamese(self, pc_tuple, sn_tuple, node_tuple, is_train=False, epoch=None):
         size_of_single_chunk = pc_tuple[0].size()[0]
-        node_recomputed, keypoints, sigmas, descriptors = self.detector(torch.cat(pc_tuple, dim=0),
+        pc_cat = torch.cat(pc_tuple, dim=0)
+        node_recomputed, keypoints, sigmas, descriptors = self.detector(pc_cat,
                                                                         torch.cat(sn_tuple, dim=0),
                                                                         torch.cat(node_tuple, dim=0), is_train, epoch)
         node_recomputed_tuple = torch.split(node_recomputed, split_size_or_sections=size_of_single_chunk, dim=0)
         keypoints_tuple = torch.split(keypoints, split_size_or_sections=size_of_single_chunk, dim=0)
+        # both clouds / both keypoint sets as one tensor each: _losses() searches them in ONE nearest-neighbour call
+        self._siamese_cat = (pc_tuple[0], pc_tuple[1], pc_cat, keypoints, keypoints_tuple[0], keypoints_tuple[1]) \
+            if len(pc_tuple) == 2 else None
         sigmas_tuple = torch.split(sigmas, split_size_or_sections=size_of_single_chunk, dim=0)
         descriptors_tuple = (None, None)
         return node_recomputed_tuple, keypoints_tuple, sigmas_tuple, descriptors_tuple
@@ -137,7 +141,16 @@ class ModelDetector():
                                                                     self.src_scale_dst, self.src_shift_dst)
         self.loss_chamfer, self.chamfer_pure, self.chamfer_weighted = self.chamfer_criteria(
             self.src_keypoints_transformed, self.dst_keypoints, self.src_sigmas, self.dst_sigmas)
-        if self.opt.keypoint_on_pc_type == 'point_to_point':
+        cat = getattr(self, "_siamese_cat", None)
+        if (self.opt.keypoint_on_pc_type == 'point_to_point' and not torch.is_grad_enabled() and cat is not None
+                and cat[0] is self.src_pc and cat[1] is self.dst_pc and cat[4] is self.src_keypoints
+                and cat[5] is self.dst_keypoints):
+            # no autograd graph wanted (test_model / forward_loss): one search over the 2B clouds instead of two over B
+            B = self.src_pc.shape[0]
+            d, _ = ops.pairwise_min(cat[3].contiguous(), cat[2])
+            self.loss_keypoint_on_pc_src = losses.mean_scale(d[:B], self.opt.keypoint_on_pc_alpha)
+            self.loss_keypoint_on_pc_dst = losses.mean_scale(d[B:], self.opt.keypoint_on_pc_alpha)
+        elif self.opt.keypoint_on_pc_type == 'point_to_point':
             self.loss_keypoint_on_pc_src = losses.mean_scale(
                 self.keypoint_on_pc_criteria(self.src_keypoints, self.src_pc, None), self.opt.keypoint_on_pc_alpha)
             self.loss_keypoint_on_pc_dst = losses.mean_scale(
@@ -218,13 +231,17 @@ class ModelDetector():
         if not plane and opt.keypoint_on_pc_type != 'point_to_point':
             raise NotImplementedError("keypoint_on_pc_type=%r" % opt.keypoint_on_pc_type)
         sides = []
-        for kps, pc, snn in ((self.src_keypoints, self.src_pc, self.src_sn), (self.dst_keypoints, self.dst_pc, self.dst_sn)):
+        d_all = arg_all = None
+        if not plane:                                    # both sides in ONE nearest-neighbour call over the 2B clouds
+            d_all, arg_all = ops.pairwise_min(kp, x)
+        for side, (kps, pc, snn) in enumerate(((self.src_keypoints, self.src_pc, self.src_sn),
+                                               (self.dst_keypoints, self.dst_pc, self.dst_sn))):
             pc = pc.contiguous()
             if plane:
                 snn = snn.contiguous()
                 d, arg = losses.point_on_surface_fwd(kps, pc, snn)
             else:
-                d, arg = ops.pairwise_min(kps, pc)
+                d, arg = d_all[side * B:(side + 1) * B], arg_all[side * B:(side + 1) * B]
             sides.append((kps, pc, snn, d, arg, ops.mean_scale(d, alpha)[0]))
         self.loss_keypoint_on_pc_src, self.loss_keypoint_on_pc_dst = sides[0][5], sides[1][5]
         self.loss = self.loss_chamfer + self.loss_keypoint_on_pc_src + self.loss_keypoint_on_pc_dst
