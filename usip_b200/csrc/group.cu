@@ -301,6 +301,46 @@ knn_nodes_kernel(const float* __restrict__ pts, int32_t* __restrict__ knn_idx, i
   }
 }
 
+// Register variant for M <= 32*KPL nodes: lane l keeps the fp32 distance bits of nodes l, l+32, ... in registers (the node
+// index is implied by the slot), so a selection round is 16 register compares + one (distance, index) warp reduction instead
+// of 16 eight-byte shared-memory loads per lane (the shared-memory kernel above spends its time in that traffic: 512
+// wavefronts per query).  Same order as the packed key: ascending sqrt-distance bits, ties by ascending node index.
+template <int KPL>
+__global__ void __launch_bounds__(256)
+knn_nodes_reg_kernel(const float* __restrict__ pts, int32_t* __restrict__ knn_idx, int B, int M, int K) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + wib;
+  if (w >= B * M) return;
+  const int b = w / M, m = w - b * M;
+  const float* p = pts + (size_t)b * 3 * M;
+  const float qx = __ldg(p + m), qy = __ldg(p + M + m), qz = __ldg(p + 2 * M + m);
+  uint32_t d[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int j = lane + 32 * i;
+    d[i] = j < M ? __float_as_uint(__fsqrt_rn(sqdist_rn(qx, qy, qz, __ldg(p + j), __ldg(p + M + j), __ldg(p + 2 * M + j)))) : 0xffffffffu;
+  }
+  for (int k = 0; k < K; ++k) {
+    uint32_t bd = d[0]; int bi = 0;
+#pragma unroll
+    for (int i = 1; i < KPL; ++i) if (d[i] < bd) { bd = d[i]; bi = i; }   // strict: the smallest slot (= index) on ties
+    int bj = lane + 32 * bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o); const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+    }
+    int j = bj;
+    if (k >= M) j = 0;                             // K > M: undefined in the reference (topk would throw)
+    if (lane == 0) knn_idx[(size_t)w * K + k] = j;
+    if (lane == (bj & 31) && k < M) {
+      const int slot = bj >> 5;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) if (i == slot) d[i] = 0xffffffffu;   // taken (a padded slot can never win again either)
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stand-alone index_max (reference operator).  CTA = (cloud, CPB channels); running maxima live in
 // shared memory as packed u64 (ordered value << 32 | ~n) with a 32-bit filter word read first, so
@@ -508,6 +548,10 @@ extern "C" int usip_segmax(const float* X, int ldx, const int32_t* seg_off, cons
 
 extern "C" int usip_knn_nodes(const float* pts, int32_t* knn_idx, int B, int M, int K, void* stream) {
   USIP_REQUIRE(pts && knn_idx && K > 0 && M > 0, "knn_nodes: bad args");
+  if (M <= 512 && K <= M) {                       // keys in registers (16 per lane)
+    knn_nodes_reg_kernel<16><<<cdiv(B * M, 8), 256, 0, (cudaStream_t)stream>>>(pts, knn_idx, B, M, K);
+    return check_launch("knn_nodes_reg_kernel");
+  }
   size_t smem = (size_t)8 * M * sizeof(unsigned long long);
   USIP_REQUIRE(smem <= 200 * 1024, "knn_nodes: M too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(knn_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -153,6 +153,185 @@ ng_build_kernel(const float* __restrict__ pts, int N, float4* __restrict__ sorte
   }
 }
 
+// ---- the same structure for a LARGE cloud, built by many CTAs (the one-CTA build above moves the whole cloud through one
+// SM: 33 us for 16384 points).  The grid is derived from the bounding box of the QUERIES -- a few hundred values that every
+// CTA reduces for itself -- and cloud points outside it are clamped into the border cells (the search never uses a grid
+// border as a distance bound, so clamping keeps it exact).  bin: cell id per point + global histogram; scan: one CTA per
+// cloud; scatter: cursor[cell]++ gives the slot.  Counters are zeroed by a memset node ahead of the three launches.
+constexpr int NGB_THREADS = 256;
+constexpr int NGB_PTS = 4;
+
+__device__ __forceinline__ NgGrid ng_grid_from_box(const float* l, const float* h3, int max_cells) {
+  NgGrid g;
+  if (!(l[0] <= h3[0])) {                                        // no finite value at all
+    g.ox = g.oy = g.oz = 0.f; g.h = 1.f; g.inv_h = 1.f; g.nx = g.ny = g.nz = 1;
+    return g;
+  }
+  const float ex = h3[0] - l[0], ey = h3[1] - l[1], ez = h3[2] - l[2];
+  const float me = fmaxf(ex, fmaxf(ey, ez));
+  float h = me > 0.f ? me / (float)NG_AXIS : 1.f;
+  if (!(h >= 1e-30f) || !(h <= 3.0e38f)) h = fmaxf(fminf(h, 3.0e38f), 1e-30f);
+  int nx = 1, ny = 1, nz = 1;
+  for (int it = 0; it < 64; ++it) {
+    nx = min(NG_AXIS, (int)(ex / h) + 1); ny = min(NG_AXIS, (int)(ey / h) + 1); nz = min(NG_AXIS, (int)(ez / h) + 1);
+    if ((long long)nx * ny * nz <= max_cells) break;
+    h *= 1.25f;
+  }
+  if ((long long)nx * ny * nz > max_cells) { nx = ny = nz = 1; h = fmaxf(me, 1e-30f) * 2.f; }
+  g.ox = l[0]; g.oy = l[1]; g.oz = l[2]; g.h = h; g.inv_h = 1.f / h; g.nx = nx; g.ny = ny; g.nz = nz;
+  return g;
+}
+
+__global__ void __launch_bounds__(NGB_THREADS)
+ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ pts, int N, int32_t* __restrict__ cellid,
+              int32_t* cnt, NgGrid* __restrict__ grids, int32_t* __restrict__ cell_start, int32_t* __restrict__ ticket) {
+  __shared__ float red[6][NGB_THREADS / 32];
+  __shared__ NgGrid sg;
+  __shared__ int wsum[NGB_THREADS / 32];
+  __shared__ int is_last;
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* qx = qry + (size_t)b * 3 * Ma;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < Ma; i += NGB_THREADS) {
+    const float x = __ldg(qx + i), y = __ldg(qx + Ma + i), z = __ldg(qx + 2 * Ma + i);
+    if (ng_finite3(x, y, z)) {
+      lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+      hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+    }
+  }
+  // the points of this CTA are fetched while the box is reduced
+  const float* px = pts + (size_t)b * 3 * N;
+  float x[NGB_PTS], y[NGB_PTS], z[NGB_PTS];
+  const int n0 = blockIdx.x * (NGB_THREADS * NGB_PTS) + tid;
+#pragma unroll
+  for (int j = 0; j < NGB_PTS; ++j) {
+    const int n = n0 + j * NGB_THREADS;
+    const bool ok = n < N;
+    x[j] = ok ? __ldg(px + n) : NAN; y[j] = ok ? __ldg(px + N + n) : NAN; z[j] = ok ? __ldg(px + 2 * N + n) : NAN;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if (lane == 0) { red[a][warp] = lo[a]; red[3 + a][warp] = hi[a]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float l[3], h3[3];
+    for (int a = 0; a < 3; ++a) {
+      l[a] = INFINITY; h3[a] = -INFINITY;
+      for (int w = 0; w < NGB_THREADS / 32; ++w) { l[a] = fminf(l[a], red[a][w]); h3[a] = fmaxf(h3[a], red[3 + a][w]); }
+    }
+    sg = ng_grid_from_box(l, h3, NG_MAXC);
+    if (blockIdx.x == 0) grids[b] = sg;
+  }
+  __syncthreads();
+  const NgGrid g = sg;
+  int32_t* cb = cnt + (size_t)b * (NG_MAXC + 1);
+#pragma unroll
+  for (int j = 0; j < NGB_PTS; ++j) {
+    const int n = n0 + j * NGB_THREADS;
+    if (n < N) {
+      int c = -1;
+      if (ng_finite3(x[j], y[j], z[j])) {
+        c = (ng_cell1(z[j], g.oz, g.inv_h, g.nz) * g.ny + ng_cell1(y[j], g.oy, g.inv_h, g.ny)) * g.nx + ng_cell1(x[j], g.ox, g.inv_h, g.nx);
+        atomicAdd(cb + c, 1);
+      }
+      cellid[(size_t)b * N + n] = c;
+    }
+  }
+  // ---- the last CTA of the cloud turns the histogram into cell_start[] and into the scatter cursors (in place): no scan
+  // launch between bin and scatter
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(ticket + b, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int ncell = g.nx * g.ny * g.nz;
+  constexpr int PER = NG_MAXC / NGB_THREADS;
+  int loc[PER], s = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { const int k = tid * PER + j; loc[j] = k < ncell ? __ldcg(cb + k) : 0; s += loc[j]; }
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int run = inc - s;
+  for (int w2 = 0; w2 < warp; ++w2) run += wsum[w2];
+  int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int k = tid * PER + j;
+    if (k < ncell) { cs[k] = run; cb[k] = run; }
+    run += loc[j];
+  }
+  if (tid == NGB_THREADS - 1) cs[ncell] = run;
+}
+
+// one CTA per cloud: cnt[0..ncell) -> exclusive prefix in cell_start[0..ncell] and in cursor[0..ncell)  (stand-alone variant,
+// unused since the bin kernel's last CTA does it)
+__global__ void __launch_bounds__(NG_BT)
+ng_scan_kernel(const int32_t* cnt, int32_t* __restrict__ cell_start, int32_t* cursor,      // cursor may alias cnt
+               const NgGrid* __restrict__ grids) {
+  __shared__ int wsum[NG_BT / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const NgGrid g = ng_load_grid(grids + b);
+  const int ncell = g.nx * g.ny * g.nz;
+  const int32_t* c = cnt + (size_t)b * (NG_MAXC + 1);
+  constexpr int PER = NG_MAXC / NG_BT;
+  int loc[PER], s = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { const int k = tid * PER + j; loc[j] = k < ncell ? c[k] : 0; s += loc[j]; }
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
+  int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
+  int32_t* cu = cursor + (size_t)b * (NG_MAXC + 1);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int k = tid * PER + j;
+    if (k < ncell) { cs[k] = run; cu[k] = run; }
+    run += loc[j];
+  }
+  if (tid == NG_BT - 1) cs[ncell] = run;
+}
+
+__global__ void __launch_bounds__(NGB_THREADS)
+ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restrict__ cellid, int32_t* __restrict__ cursor,
+                  float4* __restrict__ sorted) {
+  const int b = blockIdx.y;
+  const float* px = pts + (size_t)b * 3 * N;
+  int32_t* cu = cursor + (size_t)b * (NG_MAXC + 1);
+  float4* out = sorted + (size_t)b * N;
+  const int n0 = blockIdx.x * (NGB_THREADS * NGB_PTS) + threadIdx.x;
+  float x[NGB_PTS], y[NGB_PTS], z[NGB_PTS]; int c[NGB_PTS];
+#pragma unroll
+  for (int j = 0; j < NGB_PTS; ++j) {
+    const int n = n0 + j * NGB_THREADS;
+    const bool ok = n < N;
+    c[j] = ok ? __ldg(cellid + (size_t)b * N + n) : -1;
+    x[j] = ok ? __ldg(px + n) : 0.f; y[j] = ok ? __ldg(px + N + n) : 0.f; z[j] = ok ? __ldg(px + 2 * N + n) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < NGB_PTS; ++j)
+    if (c[j] >= 0) out[atomicAdd(cu + c[j], 1)] = make_float4(x[j], y[j], z[j], __int_as_float(n0 + j * NGB_THREADS));
+}
+
 // Shell search around (ax, ay, az): cells of ring r = 0, 1, ... until the best squared distance is smaller than the distance
 // to everything outside the scanned cube.  WARP: the 32 lanes stride over every cell range and merge after each ring;
 // otherwise one thread walks the ranges alone.  (best, bidx) = lexicographic minimum of (d2, original index).
@@ -347,9 +526,12 @@ ng_assign_kernel(const float* __restrict__ xyz, int N, int M, const float4* __re
 
 using namespace usip;
 
+// scratch layout: sorted float4 [B][N] | cell_start i32 [B][MAXC+1] | grids [B] | cnt / cursor i32 [B][MAXC+1] | ticket i32 [B] |
+// cellid i32 [B][N]
 extern "C" size_t usip_pairwise_min_grid_scratch_bytes(int B, int Nb) {
   if (B <= 0 || Nb <= 0) return 0;
-  return (size_t)B * Nb * sizeof(float4) + (size_t)B * (NG_MAXC + 1) * sizeof(int32_t) + (size_t)B * sizeof(NgGrid) + 64;
+  return (size_t)B * Nb * sizeof(float4) + 2 * (size_t)B * (NG_MAXC + 1) * sizeof(int32_t) + (size_t)B * sizeof(NgGrid) +
+         (size_t)B * sizeof(int32_t) + (size_t)B * Nb * sizeof(int32_t) + 128;
 }
 
 extern "C" int usip_pairwise_min_grid_f32(const float* a, const float* b, float* min_d, int32_t* arg, void* scratch,
@@ -362,26 +544,29 @@ extern "C" int usip_pairwise_min_grid_f32(const float* a, const float* b, float*
   int32_t* cell_start = reinterpret_cast<int32_t*>(sorted + (size_t)B * Nb);
   NgGrid* grids = reinterpret_cast<NgGrid*>(cell_start + (size_t)B * (NG_MAXC + 1));
   grids = reinterpret_cast<NgGrid*>((reinterpret_cast<uintptr_t>(grids) + 15) & ~(uintptr_t)15);
-  static bool attr = false;
-  const size_t smem = (size_t)(2 * NG_MAXC + 1) * sizeof(int);
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ng_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_last_error("pairwise_min_grid: smem attribute"); return (int)e; }
-    attr = true;
-  }
-  ng_build_kernel<<<B, NG_BT, smem, st>>>(b, Nb, sorted, cell_start, grids, NG_MAXC);
+  int32_t* cnt = reinterpret_cast<int32_t*>(grids + B);
+  int32_t* ticket = cnt + (size_t)B * (NG_MAXC + 1);
+  int32_t* cellid = ticket + B;
+  cudaError_t e = cudaMemsetAsync(cnt, 0, ((size_t)B * (NG_MAXC + 1) + B) * sizeof(int32_t), st);
+  if (e != cudaSuccess) { set_last_error("pairwise_min_grid: memset"); return (int)e; }
+  const dim3 pgrid(cdiv(Nb, NGB_THREADS * NGB_PTS), B);
+  ng_bin_kernel<<<pgrid, NGB_THREADS, 0, st>>>(a, Ma, b, Nb, cellid, cnt, grids, cell_start, ticket);   // counters -> cursors
+  ng_scatter_kernel<<<pgrid, NGB_THREADS, 0, st>>>(b, Nb, cellid, cnt, sorted);
   const int total = B * Ma;
   ng_query_kernel<<<cdiv(total * 32, 256), 256, 0, st>>>(a, Ma, sorted, cell_start, grids, Nb, min_d, arg, total);
   return check_launch("pairwise_min_grid");
 }
 
-extern "C" size_t usip_som_assign_grid_scratch_bytes(int B, int M) { return usip_pairwise_min_grid_scratch_bytes(B, M); }
+extern "C" size_t usip_som_assign_grid_scratch_bytes(int B, int M) {
+  if (B <= 0 || M <= 0) return 0;
+  return (size_t)B * M * sizeof(float4) + (size_t)B * (NG_MAXC + 1) * sizeof(int32_t) + (size_t)B * sizeof(NgGrid) + 64;
+}
 
 extern "C" int usip_som_assign_grid_f32(const float* xyz, const float* node, int32_t* min_idx, int32_t* count, void* scratch,
                                         size_t scratch_bytes, int B, int N, int M, void* stream) {
   USIP_REQUIRE(xyz && node && min_idx && scratch && B > 0 && N > 0 && M > 0, "som_assign_grid: bad args");
   USIP_REQUIRE(M <= NGA_MAXM, "som_assign_grid: more than 1024 nodes per cloud (use usip_som_assign_f32)");
-  USIP_REQUIRE(scratch_bytes >= usip_pairwise_min_grid_scratch_bytes(B, M), "som_assign_grid: scratch too small");
+  USIP_REQUIRE(scratch_bytes >= usip_som_assign_grid_scratch_bytes(B, M), "som_assign_grid: scratch too small");
   USIP_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "som_assign_grid: scratch must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   float4* sorted = reinterpret_cast<float4*>(scratch);
