@@ -182,7 +182,7 @@ __device__ __forceinline__ NgGrid ng_grid_from_box(const float* l, const float* 
   return g;
 }
 
-__global__ void __launch_bounds__(NGB_THREADS)
+__global__ void __launch_bounds__(NGB_THREADS, 8)
 ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ pts, int N, int32_t* __restrict__ cellid,
               int32_t* cnt, NgGrid* __restrict__ grids, int32_t* __restrict__ cell_start, int32_t* __restrict__ ticket) {
   __shared__ float red[6][NGB_THREADS / 32];
@@ -252,10 +252,13 @@ ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ p
   if (!is_last) return;
   __threadfence();
   const int ncell = g.nx * g.ny * g.nz;
+  // two passes over the thread's 32 counters (sum, then prefix) instead of 32 live registers: the scan tail must not
+  // cost the other 63 CTAs of the cloud their occupancy (at 79 registers the kernel ran 3 CTAs per SM: 6 -> 21 us)
   constexpr int PER = NG_MAXC / NGB_THREADS;
-  int loc[PER], s = 0;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) { const int k = tid * PER + j; loc[j] = k < ncell ? __ldcg(cb + k) : 0; s += loc[j]; }
+  const int k0 = tid * PER;
+  int s = 0;
+#pragma unroll 8
+  for (int j = 0; j < PER; ++j) s += (k0 + j < ncell) ? __ldcg(cb + k0 + j) : 0;
   int inc = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -264,11 +267,10 @@ ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ p
   int run = inc - s;
   for (int w2 = 0; w2 < warp; ++w2) run += wsum[w2];
   int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
-#pragma unroll
+#pragma unroll 8
   for (int j = 0; j < PER; ++j) {
-    const int k = tid * PER + j;
-    if (k < ncell) { cs[k] = run; cb[k] = run; }
-    run += loc[j];
+    const int k = k0 + j;
+    if (k < ncell) { const int v = __ldcg(cb + k); cs[k] = run; cb[k] = run; run += v; }
   }
   if (tid == NGB_THREADS - 1) cs[ncell] = run;
 }
