@@ -214,6 +214,19 @@ cluster_mean_decenter_kernel(const float* __restrict__ xyz, const float* __restr
     cluster_mean[(size_t)b * 3 * M + 2 * M + m] = mz;
   }
   const float* pf = feat ? feat + (size_t)b * S * N : nullptr;
+  if (ldx == 8 && S <= 5 && (reinterpret_cast<uintptr_t>(x_aug) & 15) == 0) {
+    // the usual row (xyz + <= 5 features, padded to 8 floats): two 16-byte stores per row instead of eight 4-byte ones
+    for (int r = s + lane; r < e; r += 32) {
+      const int n = pp[r];
+      float v[8];
+      v[0] = px[n] - mx; v[1] = px[N + n] - my; v[2] = px[2 * N + n] - mz;   // networks.py:105-107
+#pragma unroll
+      for (int c = 0; c < 5; ++c) v[3 + c] = c < S ? pf[(size_t)c * N + n] : 0.f;
+      float4* o = reinterpret_cast<float4*>(x_aug + ((size_t)b * N + r) * 8);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]); o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    return;
+  }
   for (int r = s + lane; r < e; r += 32) {
     int n = pp[r];
     float* o = x_aug + ((size_t)b * N + r) * ldx;
@@ -237,15 +250,31 @@ segmax_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ 
   const int b = w / M, m = w - b * M;
   const int s = seg_off[(size_t)b * (M + 1) + m], e = seg_off[(size_t)b * (M + 1) + m + 1];
   const size_t row0 = (size_t)b * N;
-  for (int c4 = lane; c4 * 4 < C; c4 += 32) {
+  // C <= 64: the 16 float4 groups of a row occupy half a warp, so the two halves take alternating rows and merge at the end
+  // (larger value, then smaller row: the first maximum, as the single ascending scan gives it)
+  const bool split = C <= 64;
+  const int nsub = split ? 2 : 1, sub = split ? (lane >> 4) : 0;
+  for (int c4 = split ? (lane & 15) : lane; c4 * 4 < C; c4 += split ? 16 : 32) {
     float4 best = make_float4(-1000.f, -1000.f, -1000.f, -1000.f);
     int4 bi = make_int4(-1, -1, -1, -1);
-    for (int r = s; r < e; ++r) {
+    for (int r = s + sub; r < e; r += nsub) {
       float4 v = *reinterpret_cast<const float4*>(X + (row0 + r) * ldx + c4 * 4);
       if (v.x > best.x) { best.x = v.x; bi.x = r; }
       if (v.y > best.y) { best.y = v.y; bi.y = r; }
       if (v.z > best.z) { best.z = v.z; bi.z = r; }
       if (v.w > best.w) { best.w = v.w; bi.w = r; }
+    }
+    if (split) {
+      const float4 ob = make_float4(__shfl_xor_sync(0xffffffffu, best.x, 16), __shfl_xor_sync(0xffffffffu, best.y, 16),
+                                    __shfl_xor_sync(0xffffffffu, best.z, 16), __shfl_xor_sync(0xffffffffu, best.w, 16));
+      const int4 oi = make_int4(__shfl_xor_sync(0xffffffffu, bi.x, 16), __shfl_xor_sync(0xffffffffu, bi.y, 16),
+                                __shfl_xor_sync(0xffffffffu, bi.z, 16), __shfl_xor_sync(0xffffffffu, bi.w, 16));
+      // bi < 0 means "nothing above the floor" on that side; a real row always beats it
+      if (oi.x >= 0 && (bi.x < 0 || ob.x > best.x || (ob.x == best.x && oi.x < bi.x))) { best.x = ob.x; bi.x = oi.x; }
+      if (oi.y >= 0 && (bi.y < 0 || ob.y > best.y || (ob.y == best.y && oi.y < bi.y))) { best.y = ob.y; bi.y = oi.y; }
+      if (oi.z >= 0 && (bi.z < 0 || ob.z > best.z || (ob.z == best.z && oi.z < bi.z))) { best.z = ob.z; bi.z = oi.z; }
+      if (oi.w >= 0 && (bi.w < 0 || ob.w > best.w || (ob.w == best.w && oi.w < bi.w))) { best.w = ob.w; bi.w = oi.w; }
+      if (sub != 0) continue;                               // the lower half writes
     }
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 oa = make_int4(-1, -1, -1, -1);

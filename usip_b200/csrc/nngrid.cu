@@ -156,8 +156,9 @@ ng_build_kernel(const float* __restrict__ pts, int N, float4* __restrict__ sorte
 // ---- the same structure for a LARGE cloud, built by many CTAs (the one-CTA build above moves the whole cloud through one
 // SM: 33 us for 16384 points).  The grid is derived from the bounding box of the QUERIES -- a few hundred values that every
 // CTA reduces for itself -- and cloud points outside it are clamped into the border cells (the search never uses a grid
-// border as a distance bound, so clamping keeps it exact).  bin: cell id per point + global histogram; scan: one CTA per
-// cloud; scatter: cursor[cell]++ gives the slot.  Counters are zeroed by a memset node ahead of the three launches.
+// border as a distance bound, so clamping keeps it exact).  bin: cell id per point + global histogram; scatter: prefix of the
+// histogram (scanned by every CTA for itself) + fill[cell]++ gives the slot.  Both counter arrays are zeroed by one memset
+// node ahead of the launches.
 constexpr int NGB_THREADS = 256;
 constexpr int NGB_PTS = 4;
 
@@ -182,13 +183,11 @@ __device__ __forceinline__ NgGrid ng_grid_from_box(const float* l, const float* 
   return g;
 }
 
-__global__ void __launch_bounds__(NGB_THREADS, 8)
+__global__ void __launch_bounds__(NGB_THREADS)
 ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ pts, int N, int32_t* __restrict__ cellid,
-              int32_t* cnt, NgGrid* __restrict__ grids, int32_t* __restrict__ cell_start, int32_t* __restrict__ ticket) {
+              int32_t* __restrict__ cnt, NgGrid* __restrict__ grids) {
   __shared__ float red[6][NGB_THREADS / 32];
   __shared__ NgGrid sg;
-  __shared__ int wsum[NGB_THREADS / 32];
-  __shared__ int is_last;
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* qx = qry + (size_t)b * 3 * Ma;
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -243,84 +242,24 @@ ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ p
       cellid[(size_t)b * N + n] = c;
     }
   }
-  // ---- the last CTA of the cloud turns the histogram into cell_start[] and into the scatter cursors (in place): no scan
-  // launch between bin and scatter
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(ticket + b, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const int ncell = g.nx * g.ny * g.nz;
-  // two passes over the thread's 32 counters (sum, then prefix) instead of 32 live registers: the scan tail must not
-  // cost the other 63 CTAs of the cloud their occupancy (at 79 registers the kernel ran 3 CTAs per SM: 6 -> 21 us)
-  constexpr int PER = NG_MAXC / NGB_THREADS;
-  const int k0 = tid * PER;
-  int s = 0;
-#pragma unroll 8
-  for (int j = 0; j < PER; ++j) s += (k0 + j < ncell) ? __ldcg(cb + k0 + j) : 0;
-  int inc = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  int run = inc - s;
-  for (int w2 = 0; w2 < warp; ++w2) run += wsum[w2];
-  int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
-#pragma unroll 8
-  for (int j = 0; j < PER; ++j) {
-    const int k = k0 + j;
-    if (k < ncell) { const int v = __ldcg(cb + k); cs[k] = run; cb[k] = run; run += v; }
-  }
-  if (tid == NGB_THREADS - 1) cs[ncell] = run;
 }
 
-// one CTA per cloud: cnt[0..ncell) -> exclusive prefix in cell_start[0..ncell] and in cursor[0..ncell)  (stand-alone variant,
-// unused since the bin kernel's last CTA does it)
-__global__ void __launch_bounds__(NG_BT)
-ng_scan_kernel(const int32_t* cnt, int32_t* __restrict__ cell_start, int32_t* cursor,      // cursor may alias cnt
-               const NgGrid* __restrict__ grids) {
-  __shared__ int wsum[NG_BT / 32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Every CTA scans the cloud's histogram for itself in shared memory (32 KB of L2-resident counters, ~1 us, all CTAs at once)
+// instead of waiting for a one-CTA-per-cloud scan launch (12 us under ncu) or for a last-CTA tail (which ran at the memory
+// parallelism of a single CTA: 15-40 us).  CTA 0 of a cloud publishes cell_start[] for the query kernel.
+__global__ void __launch_bounds__(NGB_THREADS)
+ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restrict__ cellid, const int32_t* __restrict__ cnt,
+                  int32_t* __restrict__ fill, const NgGrid* __restrict__ grids, int32_t* __restrict__ cell_start,
+                  float4* __restrict__ sorted) {
+  extern __shared__ int ngs_start[];                             // [NG_MAXC + NG_MAXC / 32] padded: index k -> k + (k >> 5)
+  __shared__ int wsum[NGB_THREADS / 32];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const NgGrid g = ng_load_grid(grids + b);
   const int ncell = g.nx * g.ny * g.nz;
-  const int32_t* c = cnt + (size_t)b * (NG_MAXC + 1);
-  constexpr int PER = NG_MAXC / NG_BT;
-  int loc[PER], s = 0;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) { const int k = tid * PER + j; loc[j] = k < ncell ? c[k] : 0; s += loc[j]; }
-  int inc = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  if (lane == 31) wsum[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    int v = wsum[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-    wsum[lane] = v;
-  }
-  __syncthreads();
-  int run = inc - s + (warp > 0 ? wsum[warp - 1] : 0);
-  int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
-  int32_t* cu = cursor + (size_t)b * (NG_MAXC + 1);
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int k = tid * PER + j;
-    if (k < ncell) { cs[k] = run; cu[k] = run; }
-    run += loc[j];
-  }
-  if (tid == NG_BT - 1) cs[ncell] = run;
-}
-
-__global__ void __launch_bounds__(NGB_THREADS)
-ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restrict__ cellid, int32_t* __restrict__ cursor,
-                  float4* __restrict__ sorted) {
-  const int b = blockIdx.y;
+  const int32_t* cb = cnt + (size_t)b * (NG_MAXC + 1);
+  // the points of this CTA are fetched while the histogram is scanned
   const float* px = pts + (size_t)b * 3 * N;
-  int32_t* cu = cursor + (size_t)b * (NG_MAXC + 1);
-  float4* out = sorted + (size_t)b * N;
-  const int n0 = blockIdx.x * (NGB_THREADS * NGB_PTS) + threadIdx.x;
+  const int n0 = blockIdx.x * (NGB_THREADS * NGB_PTS) + tid;
   float x[NGB_PTS], y[NGB_PTS], z[NGB_PTS]; int c[NGB_PTS];
 #pragma unroll
   for (int j = 0; j < NGB_PTS; ++j) {
@@ -329,9 +268,40 @@ ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restric
     c[j] = ok ? __ldg(cellid + (size_t)b * N + n) : -1;
     x[j] = ok ? __ldg(px + n) : 0.f; y[j] = ok ? __ldg(px + N + n) : 0.f; z[j] = ok ? __ldg(px + 2 * N + n) : 0.f;
   }
+  for (int k = tid; k < NG_MAXC; k += NGB_THREADS) ngs_start[k + (k >> 5)] = k < ncell ? __ldg(cb + k) : 0;   // coalesced
+  __syncthreads();
+  constexpr int PER = NG_MAXC / NGB_THREADS;                     // 32 consecutive cells per thread; the padding spreads the banks
+  const int k0 = tid * PER;
+  int s = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) s += ngs_start[k0 + j + ((k0 + j) >> 5)];
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int run = inc - s;
+  for (int w2 = 0; w2 < warp; ++w2) run += wsum[w2];
+  int32_t* cs = cell_start + (size_t)b * (NG_MAXC + 1);
+  const bool publish = blockIdx.x == 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int k = k0 + j, idx = k + (k >> 5);
+    const int v = ngs_start[idx];
+    ngs_start[idx] = run;
+    if (publish && k < ncell) cs[k] = run;
+    run += v;
+  }
+  if (publish && tid == NGB_THREADS - 1) cs[ncell] = run;
+  __syncthreads();
+  int32_t* fl = fill + (size_t)b * (NG_MAXC + 1);
+  float4* out = sorted + (size_t)b * N;
 #pragma unroll
   for (int j = 0; j < NGB_PTS; ++j)
-    if (c[j] >= 0) out[atomicAdd(cu + c[j], 1)] = make_float4(x[j], y[j], z[j], __int_as_float(n0 + j * NGB_THREADS));
+    if (c[j] >= 0) {
+      const int pos = ngs_start[c[j] + (c[j] >> 5)] + atomicAdd(fl + c[j], 1);
+      out[pos] = make_float4(x[j], y[j], z[j], __int_as_float(n0 + j * NGB_THREADS));
+    }
 }
 
 // Shell search around (ax, ay, az): cells of ring r = 0, 1, ... until the best squared distance is smaller than the distance
@@ -528,12 +498,12 @@ ng_assign_kernel(const float* __restrict__ xyz, int N, int M, const float4* __re
 
 using namespace usip;
 
-// scratch layout: sorted float4 [B][N] | cell_start i32 [B][MAXC+1] | grids [B] | cnt / cursor i32 [B][MAXC+1] | ticket i32 [B] |
+// scratch layout: sorted float4 [B][N] | cell_start i32 [B][MAXC+1] | grids [B] | cnt i32 [B][MAXC+1] | fill i32 [B][MAXC+1] |
 // cellid i32 [B][N]
 extern "C" size_t usip_pairwise_min_grid_scratch_bytes(int B, int Nb) {
   if (B <= 0 || Nb <= 0) return 0;
-  return (size_t)B * Nb * sizeof(float4) + 2 * (size_t)B * (NG_MAXC + 1) * sizeof(int32_t) + (size_t)B * sizeof(NgGrid) +
-         (size_t)B * sizeof(int32_t) + (size_t)B * Nb * sizeof(int32_t) + 128;
+  return (size_t)B * Nb * sizeof(float4) + 3 * (size_t)B * (NG_MAXC + 1) * sizeof(int32_t) + (size_t)B * sizeof(NgGrid) +
+         (size_t)B * Nb * sizeof(int32_t) + 128;
 }
 
 extern "C" int usip_pairwise_min_grid_f32(const float* a, const float* b, float* min_d, int32_t* arg, void* scratch,
@@ -547,13 +517,20 @@ extern "C" int usip_pairwise_min_grid_f32(const float* a, const float* b, float*
   NgGrid* grids = reinterpret_cast<NgGrid*>(cell_start + (size_t)B * (NG_MAXC + 1));
   grids = reinterpret_cast<NgGrid*>((reinterpret_cast<uintptr_t>(grids) + 15) & ~(uintptr_t)15);
   int32_t* cnt = reinterpret_cast<int32_t*>(grids + B);
-  int32_t* ticket = cnt + (size_t)B * (NG_MAXC + 1);
-  int32_t* cellid = ticket + B;
-  cudaError_t e = cudaMemsetAsync(cnt, 0, ((size_t)B * (NG_MAXC + 1) + B) * sizeof(int32_t), st);
+  int32_t* fill = cnt + (size_t)B * (NG_MAXC + 1);
+  int32_t* cellid = fill + (size_t)B * (NG_MAXC + 1);
+  cudaError_t e = cudaMemsetAsync(cnt, 0, 2 * (size_t)B * (NG_MAXC + 1) * sizeof(int32_t), st);
   if (e != cudaSuccess) { set_last_error("pairwise_min_grid: memset"); return (int)e; }
+  static bool attr = false;
+  const size_t smem = (size_t)(NG_MAXC + NG_MAXC / 32) * sizeof(int);
+  if (!attr) {
+    e = cudaFuncSetAttribute(ng_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error("pairwise_min_grid: smem attribute"); return (int)e; }
+    attr = true;
+  }
   const dim3 pgrid(cdiv(Nb, NGB_THREADS * NGB_PTS), B);
-  ng_bin_kernel<<<pgrid, NGB_THREADS, 0, st>>>(a, Ma, b, Nb, cellid, cnt, grids, cell_start, ticket);   // counters -> cursors
-  ng_scatter_kernel<<<pgrid, NGB_THREADS, 0, st>>>(b, Nb, cellid, cnt, sorted);
+  ng_bin_kernel<<<pgrid, NGB_THREADS, 0, st>>>(a, Ma, b, Nb, cellid, cnt, grids);
+  ng_scatter_kernel<<<pgrid, NGB_THREADS, smem, st>>>(b, Nb, cellid, cnt, fill, grids, cell_start, sorted);
   const int total = B * Ma;
   ng_query_kernel<<<cdiv(total * 32, 256), 256, 0, st>>>(a, Ma, sorted, cell_start, grids, Nb, min_d, arg, total);
   return check_launch("pairwise_min_grid");
