@@ -158,11 +158,22 @@ sort_scan_kernel(int32_t* __restrict__ hist, int32_t* __restrict__ seg_off, int 
   const int lo = min(tid * per, M), hi = min(lo + per, M);
   int s = 0;
   for (int m = lo; m < hi; ++m) s += tot[m];
-  part[tid] = s;
+  // block-wide exclusive scan of the per-thread sums by warp shuffles (a serial pass of thread 0 over the 1024 partials
+  // was most of this kernel's 13 us)
+  const int lane = tid & 31, warp = tid >> 5;
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) part[warp] = inc;
   __syncthreads();
-  if (tid == 0) { int run = 0; for (int t = 0; t < nt; ++t) { int v = part[t]; part[t] = run; run += v; } }
+  if (warp == 0) {
+    int v = lane < (nt >> 5) ? part[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    part[lane] = v;
+  }
   __syncthreads();
-  int run = part[tid];
+  int run = inc - s + (warp > 0 ? part[warp - 1] : 0);
   for (int m = lo; m < hi; ++m) { seg_off[(size_t)b * (M + 1) + m] = run; run += tot[m]; }
   if (tid == 0) seg_off[(size_t)b * (M + 1) + M] = N;
 }
@@ -250,32 +261,16 @@ segmax_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ 
   const int b = w / M, m = w - b * M;
   const int s = seg_off[(size_t)b * (M + 1) + m], e = seg_off[(size_t)b * (M + 1) + m + 1];
   const size_t row0 = (size_t)b * N;
-  // C <= 64: the 16 float4 groups of a row occupy half a warp, so the two halves take alternating rows and merge at the end
-  // (larger value, then smaller row: the first maximum, as the single ascending scan gives it)
-  const bool split = C <= 64;
-  const int nsub = split ? 2 : 1, sub = split ? (lane >> 4) : 0;
-  for (int c4 = split ? (lane & 15) : lane; c4 * 4 < C; c4 += split ? 16 : 32) {
-    float4 best = make_float4(-1000.f, -1000.f, -1000.f, -1000.f);
-    int4 bi = make_int4(-1, -1, -1, -1);
-    for (int r = s + sub; r < e; r += nsub) {
+  auto scan = [&](int c4, int first, int step, float4& best, int4& bi) {
+    for (int r = first; r < e; r += step) {
       float4 v = *reinterpret_cast<const float4*>(X + (row0 + r) * ldx + c4 * 4);
       if (v.x > best.x) { best.x = v.x; bi.x = r; }
       if (v.y > best.y) { best.y = v.y; bi.y = r; }
       if (v.z > best.z) { best.z = v.z; bi.z = r; }
       if (v.w > best.w) { best.w = v.w; bi.w = r; }
     }
-    if (split) {
-      const float4 ob = make_float4(__shfl_xor_sync(0xffffffffu, best.x, 16), __shfl_xor_sync(0xffffffffu, best.y, 16),
-                                    __shfl_xor_sync(0xffffffffu, best.z, 16), __shfl_xor_sync(0xffffffffu, best.w, 16));
-      const int4 oi = make_int4(__shfl_xor_sync(0xffffffffu, bi.x, 16), __shfl_xor_sync(0xffffffffu, bi.y, 16),
-                                __shfl_xor_sync(0xffffffffu, bi.z, 16), __shfl_xor_sync(0xffffffffu, bi.w, 16));
-      // bi < 0 means "nothing above the floor" on that side; a real row always beats it
-      if (oi.x >= 0 && (bi.x < 0 || ob.x > best.x || (ob.x == best.x && oi.x < bi.x))) { best.x = ob.x; bi.x = oi.x; }
-      if (oi.y >= 0 && (bi.y < 0 || ob.y > best.y || (ob.y == best.y && oi.y < bi.y))) { best.y = ob.y; bi.y = oi.y; }
-      if (oi.z >= 0 && (bi.z < 0 || ob.z > best.z || (ob.z == best.z && oi.z < bi.z))) { best.z = ob.z; bi.z = oi.z; }
-      if (oi.w >= 0 && (bi.w < 0 || ob.w > best.w || (ob.w == best.w && oi.w < bi.w))) { best.w = ob.w; bi.w = oi.w; }
-      if (sub != 0) continue;                               // the lower half writes
-    }
+  };
+  auto finish = [&](int c4, float4 best, int4 bi) {
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 oa = make_int4(-1, -1, -1, -1);
     if (e > s) {
@@ -294,6 +289,32 @@ segmax_kernel(const float* __restrict__ X, int ldx, const int32_t* __restrict__ 
     }
     *reinterpret_cast<float4*>(pooled + (size_t)w * ldp + c4 * 4) = out;
     if (arg) *reinterpret_cast<int4*>(arg + (size_t)w * C + c4 * 4) = oa;
+  };
+  if (C <= 64) {
+    // the <= 16 float4 groups of a row occupy half a warp: the two halves take alternating rows and merge at the end
+    // (larger value, then smaller row = the first maximum, as the single ascending scan gives it)
+    const int c4 = lane & 15, sub = lane >> 4;
+    const bool active = c4 * 4 < C;
+    float4 best = make_float4(-1000.f, -1000.f, -1000.f, -1000.f);
+    int4 bi = make_int4(-1, -1, -1, -1);
+    if (active) scan(c4, s + sub, 2, best, bi);
+    const float4 ob = make_float4(__shfl_xor_sync(0xffffffffu, best.x, 16), __shfl_xor_sync(0xffffffffu, best.y, 16),
+                                  __shfl_xor_sync(0xffffffffu, best.z, 16), __shfl_xor_sync(0xffffffffu, best.w, 16));
+    const int4 oi = make_int4(__shfl_xor_sync(0xffffffffu, bi.x, 16), __shfl_xor_sync(0xffffffffu, bi.y, 16),
+                              __shfl_xor_sync(0xffffffffu, bi.z, 16), __shfl_xor_sync(0xffffffffu, bi.w, 16));
+    // an index < 0 means "nothing above the floor" on that side; a real row always beats it
+    if (oi.x >= 0 && (bi.x < 0 || ob.x > best.x || (ob.x == best.x && oi.x < bi.x))) { best.x = ob.x; bi.x = oi.x; }
+    if (oi.y >= 0 && (bi.y < 0 || ob.y > best.y || (ob.y == best.y && oi.y < bi.y))) { best.y = ob.y; bi.y = oi.y; }
+    if (oi.z >= 0 && (bi.z < 0 || ob.z > best.z || (ob.z == best.z && oi.z < bi.z))) { best.z = ob.z; bi.z = oi.z; }
+    if (oi.w >= 0 && (bi.w < 0 || ob.w > best.w || (ob.w == best.w && oi.w < bi.w))) { best.w = ob.w; bi.w = oi.w; }
+    if (active && sub == 0) finish(c4, best, bi);
+    return;
+  }
+  for (int c4 = lane; c4 * 4 < C; c4 += 32) {
+    float4 best = make_float4(-1000.f, -1000.f, -1000.f, -1000.f);
+    int4 bi = make_int4(-1, -1, -1, -1);
+    scan(c4, s, 1, best, bi);
+    finish(c4, best, bi);
   }
 }
 

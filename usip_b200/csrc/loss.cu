@@ -136,18 +136,34 @@ chamfer_prob_reduce_kernel(const float* __restrict__ d_sd, const int32_t* __rest
                            float* __restrict__ out3, int B, int M, int N) {
   __shared__ double sh[8][32];
   double r[8] = {0, 0, 0, 0, 0, 0, 0, 0};          // forward: loss, d, 1/s, d/s; backward: the same
-  for (int t = threadIdx.x; t < B * M; t += blockDim.x) {
-    const int b = t / M;
-    const float s = 0.5f * (sig_src[t] + sig_dst[(size_t)b * N + i_sd[t]]);
-    const float d = d_sd[t], ds = d / s;
-    r[0] += (double)(logf(s) + ds); r[1] += (double)d; r[2] += (double)(1.0f / s); r[3] += (double)ds;
-  }
-  for (int t = threadIdx.x; t < B * N; t += blockDim.x) {
-    const int b = t / N;
-    const float s = 0.5f * (sig_dst[t] + sig_src[(size_t)b * M + i_ds[t]]);
-    const float d = d_ds[t], ds = d / s;
-    r[4] += (double)(logf(s) + ds); r[5] += (double)d; r[6] += (double)(1.0f / s); r[7] += (double)ds;
-  }
+  // four elements per thread and pass: the index -> sigma gathers are two dependent loads per element, so the loads of a
+  // batch are issued together (B*M = 4096 elements on 1024 threads: one batch per direction instead of four round trips)
+  auto side = [&](const float* dd, const int32_t* ii, const float* s_own, const float* s_other, int n_own, int n_other, int q0) {
+    const int total = B * n_own;
+    for (int t0 = threadIdx.x; t0 < total; t0 += 4 * blockDim.x) {
+      int idx[4]; float so[4], d[4], sg[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * blockDim.x; const bool ok = t < total;
+        idx[u] = ok ? ii[t] : 0; so[u] = ok ? s_own[t] : 1.f; d[u] = ok ? dd[t] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * blockDim.x;
+        sg[u] = t < total ? s_other[(size_t)(t / n_own) * n_other + idx[u]] : 1.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (t0 + u * (int)blockDim.x < total) {
+          const float s = 0.5f * (so[u] + sg[u]);
+          const float ds = d[u] / s;
+          r[q0 + 0] += (double)(logf(s) + ds); r[q0 + 1] += (double)d[u]; r[q0 + 2] += (double)(1.0f / s); r[q0 + 3] += (double)ds;
+        }
+      }
+    }
+  };
+  side(d_sd, i_sd, sig_src, sig_dst, M, N, 0);
+  side(d_ds, i_ds, sig_dst, sig_src, N, M, 4);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
   for (int q = 0; q < 8; ++q) { r[q] = warp_sum_d(r[q]); if (lane == 0) sh[q][w] = r[q]; }

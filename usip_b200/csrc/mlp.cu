@@ -255,16 +255,18 @@ layer_fwd_simt_kernel(const usip_layer_desc d) {
 
 // ------------------------------------------------------------------------------------------------
 constexpr int BNF_C = 8;       // channels per CTA: one 32-byte sector per partial row, C/8 CTAs
-__global__ void __launch_bounds__(1024)
+constexpr int BNF_T = 256;     // threads: 8 channels x 32 partial-row slices
+__global__ void __launch_bounds__(BNF_T)
 bn_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int C,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var,
                    float* __restrict__ scale, float* __restrict__ shift,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  // block = 8 channels x 128 partial-row slices; every thread keeps 8 independent loads in flight per batch so the
-  // reduction is bandwidth- not latency-bound
-  constexpr int SL = 1024 / BNF_C;
-  __shared__ double sh[2][SL][BNF_C + 1];
+  // block = 8 channels x 32 partial-row slices; every thread keeps 8 independent loads in flight per batch; the slices
+  // meet by two warp shuffles and ONE barrier (round 1: 1024 threads and a seven-level shared-memory tree of doubles --
+  // 8 us per launch, ten launches per forward step).  Fixed order -> deterministic.
+  constexpr int SL = BNF_T / BNF_C;
+  __shared__ double sh[2][BNF_T / 32][BNF_C];
   const int cl = threadIdx.x % BNF_C, sl = threadIdx.x / BNF_C;
   const int c = blockIdx.x * BNF_C + cl;
   double s = 0.0, ss = 0.0;
@@ -280,20 +282,26 @@ bn_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int
 #pragma unroll
       for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
     }
-    for (; t < ntiles; t += SL) {
-      s += (double)part[((size_t)t * 2 + 0) * C + c];
-      ss += (double)part[((size_t)t * 2 + 1) * C + c];
+    float a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool ok = t + u * SL < ntiles;
+      a[u] = ok ? __ldg(part + ((size_t)(t + u * SL) * 2 + 0) * C + c) : 0.f;
+      b[u] = ok ? __ldg(part + ((size_t)(t + u * SL) * 2 + 1) * C + c) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
   }
-  sh[0][sl][cl] = s; sh[1][sl][cl] = ss;
+  // a warp holds 4 slices x 8 channels (lane = 8*slice + channel): fold the slices, then the 8 warps
+  s += __shfl_xor_sync(0xffffffffu, s, 8); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < BNF_C) { sh[0][warp][lane] = s; sh[1][warp][lane] = ss; }
   __syncthreads();
-  // tree over the 128 slices (fixed order -> deterministic)
-  for (int off = SL / 2; off > 0; off >>= 1) {
-    if (sl < off) { sh[0][sl][cl] += sh[0][sl + off][cl]; sh[1][sl][cl] += sh[1][sl + off][cl]; }
-    __syncthreads();
-  }
   if (sl == 0 && c < C) {
-    const double S = sh[0][0][cl], SS = sh[1][0][cl];
+    double S = 0.0, SS = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < BNF_T / 32; ++w2) { S += sh[0][w2][cl]; SS += sh[1][w2][cl]; }
     double mean = S / count;
     double var = SS / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -579,7 +587,7 @@ extern "C" int usip_bn_finalize(const float* stat_partial, int ntiles, int64_t c
                                 float* running_var, float* scale, float* shift, float* save_mean,
                                 float* save_invstd, void* stream) {
   USIP_REQUIRE(stat_partial && scale && shift && ntiles > 0 && count > 0 && C > 0, "bn_finalize: bad args");
-  bn_finalize_kernel<<<cdiv(C, BNF_C), 1024, 0, (cudaStream_t)stream>>>(stat_partial, ntiles, (double)count, C, gamma,
+  bn_finalize_kernel<<<cdiv(C, BNF_C), BNF_T, 0, (cudaStream_t)stream>>>(stat_partial, ntiles, (double)count, C, gamma,
                                                                     beta, eps, momentum, running_mean, running_var,
                                                                     scale, shift, save_mean, save_invstd);
   return check_launch("bn_finalize_kernel");

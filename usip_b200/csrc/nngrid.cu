@@ -247,6 +247,7 @@ ng_bin_kernel(const float* __restrict__ qry, int Ma, const float* __restrict__ p
 // Every CTA scans the cloud's histogram for itself in shared memory (32 KB of L2-resident counters, ~1 us, all CTAs at once)
 // instead of waiting for a one-CTA-per-cloud scan launch (12 us under ncu) or for a last-CTA tail (which ran at the memory
 // parallelism of a single CTA: 15-40 us).  CTA 0 of a cloud publishes cell_start[] for the query kernel.
+constexpr int NGS_PTS = 8;            // points per scatter thread: 33 KB of shared memory per CTA -> half the CTAs, one wave
 __global__ void __launch_bounds__(NGB_THREADS)
 ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restrict__ cellid, const int32_t* __restrict__ cnt,
                   int32_t* __restrict__ fill, const NgGrid* __restrict__ grids, int32_t* __restrict__ cell_start,
@@ -259,10 +260,10 @@ ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restric
   const int32_t* cb = cnt + (size_t)b * (NG_MAXC + 1);
   // the points of this CTA are fetched while the histogram is scanned
   const float* px = pts + (size_t)b * 3 * N;
-  const int n0 = blockIdx.x * (NGB_THREADS * NGB_PTS) + tid;
-  float x[NGB_PTS], y[NGB_PTS], z[NGB_PTS]; int c[NGB_PTS];
+  const int n0 = blockIdx.x * (NGB_THREADS * NGS_PTS) + tid;
+  float x[NGS_PTS], y[NGS_PTS], z[NGS_PTS]; int c[NGS_PTS];
 #pragma unroll
-  for (int j = 0; j < NGB_PTS; ++j) {
+  for (int j = 0; j < NGS_PTS; ++j) {
     const int n = n0 + j * NGB_THREADS;
     const bool ok = n < N;
     c[j] = ok ? __ldg(cellid + (size_t)b * N + n) : -1;
@@ -297,7 +298,7 @@ ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restric
   int32_t* fl = fill + (size_t)b * (NG_MAXC + 1);
   float4* out = sorted + (size_t)b * N;
 #pragma unroll
-  for (int j = 0; j < NGB_PTS; ++j)
+  for (int j = 0; j < NGS_PTS; ++j)
     if (c[j] >= 0) {
       const int pos = ngs_start[c[j] + (c[j] >> 5)] + atomicAdd(fl + c[j], 1);
       out[pos] = make_float4(x[j], y[j], z[j], __int_as_float(n0 + j * NGB_THREADS));
@@ -530,7 +531,8 @@ extern "C" int usip_pairwise_min_grid_f32(const float* a, const float* b, float*
   }
   const dim3 pgrid(cdiv(Nb, NGB_THREADS * NGB_PTS), B);
   ng_bin_kernel<<<pgrid, NGB_THREADS, 0, st>>>(a, Ma, b, Nb, cellid, cnt, grids);
-  ng_scatter_kernel<<<pgrid, NGB_THREADS, smem, st>>>(b, Nb, cellid, cnt, fill, grids, cell_start, sorted);
+  const dim3 sgrid(cdiv(Nb, NGB_THREADS * NGS_PTS), B);
+  ng_scatter_kernel<<<sgrid, NGB_THREADS, smem, st>>>(b, Nb, cellid, cnt, fill, grids, cell_start, sorted);
   const int total = B * Ma;
   ng_query_kernel<<<cdiv(total * 32, 256), 256, 0, st>>>(a, Ma, sorted, cell_start, grids, Nb, min_d, arg, total);
   return check_launch("pairwise_min_grid");
