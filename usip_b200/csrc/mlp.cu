@@ -343,32 +343,51 @@ knn_combine_kernel(const float* __restrict__ Z, int ldz, const float* __restrict
   const int tile = blockIdx.x, row0 = tile * L_BM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = B * M * K;
-  for (int c4 = lane; c4 * 4 < Cout; c4 += 32) {
-    float w0[4], w1[4], w2[4], bs[4], s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float* wr = W + (size_t)(c4 * 4 + j) * ldw;
-      w0[j] = wr[0]; w1[j] = wr[1]; w2[j] = wr[2]; bs[j] = bias ? bias[c4 * 4 + j] : 0.f;
-    }
-    for (int r = row0 + warp; r < min(row0 + L_BM, G); r += 8) {
+  // the neighbour offsets of the warp's rows (row0 + warp + 8 i, i < 16) are computed ONCE, by lane i, and broadcast by
+  // shuffles inside the channel loop -- every lane used to redo the two integer divisions, the index load and the six
+  // coordinate loads for every row and every 128-channel pass
+  static_assert(L_BM / 8 <= 32, "one lane per row of the warp");
+  int nb_row = 0; float ndx = 0.f, ndy = 0.f, ndz = 0.f;
+  {
+    const int r = row0 + warp + 8 * lane;
+    if (lane < L_BM / 8 && r < G) {
       const int q = r / K;                                   // global node id b*M+m
       const int b = q / M, m = q - b * M;
       const int j = knn_idx[r];
       const float* p = pts + (size_t)b * 3 * M;
-      const float dx = p[j] - p[m], dy = p[M + j] - p[M + m], dz = p[2 * M + j] - p[2 * M + m];   // layers.py:428
-      float4 z = *reinterpret_cast<const float4*>(Z + ((size_t)b * M + j) * ldz + c4 * 4);
-      float y[4] = {z.x, z.y, z.z, z.w};
+      ndx = p[j] - p[m]; ndy = p[M + j] - p[M + m]; ndz = p[2 * M + j] - p[2 * M + m];            // layers.py:428
+      nb_row = b * M + j;
+    }
+  }
+  for (int c4 = lane; c4 * 4 < ((Cout + 127) / 128) * 128; c4 += 32) {       // uniform trip count: the shuffles need every lane
+    const bool act = c4 * 4 < Cout;
+    float w0[4], w1[4], w2[4], bs[4], s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* wr = W + (size_t)(act ? c4 * 4 + j : 0) * ldw;
+      w0[j] = wr[0]; w1[j] = wr[1]; w2[j] = wr[2]; bs[j] = (bias && act) ? bias[c4 * 4 + j] : 0.f;
+    }
+    int i = 0;
+    for (int r = row0 + warp; r < min(row0 + L_BM, G); r += 8, ++i) {
+      const int zr = __shfl_sync(0xffffffffu, nb_row, i);
+      const float dx = __shfl_sync(0xffffffffu, ndx, i), dy = __shfl_sync(0xffffffffu, ndy, i), dz = __shfl_sync(0xffffffffu, ndz, i);
+      if (act) {
+        float4 z = *reinterpret_cast<const float4*>(Z + (size_t)zr * ldz + c4 * 4);
+        float y[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          y[t] += fmaf(w2[t], dz, fmaf(w1[t], dy, w0[t] * dx)) + bs[t];
+          s[t] += y[t]; ss[t] = fmaf(y[t], y[t], ss[t]);
+        }
+        *reinterpret_cast<float4*>(Y + (size_t)r * ldy + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+      }
+    }
+    if (act) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        y[t] += fmaf(w2[t], dz, fmaf(w1[t], dy, w0[t] * dx)) + bs[t];
-        s[t] += y[t]; ss[t] = fmaf(y[t], y[t], ss[t]);
+        red[(0 * 8 + warp) * Cout + c4 * 4 + t] = s[t];
+        red[(1 * 8 + warp) * Cout + c4 * 4 + t] = ss[t];
       }
-      *reinterpret_cast<float4*>(Y + (size_t)r * ldy + c4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      red[(0 * 8 + warp) * Cout + c4 * 4 + t] = s[t];
-      red[(1 * 8 + warp) * Cout + c4 * 4 + t] = ss[t];
     }
   }
   __syncthreads();
@@ -391,6 +410,25 @@ __global__ void group_select_kernel(const float* __restrict__ gmax, const float*
   float sc = scale[c];
   float v = sc >= 0.f ? gmax[i] : gmin[i];
   out[(size_t)q * ldo + c] = fmaxf(fmaf(v, sc, shift[c]), 0.f);
+}
+
+// four channels per thread (C % 4 == 0, 16-byte aligned rows): three 16-byte loads and one 16-byte store per thread
+__global__ void group_select4_kernel(const float* __restrict__ gmax, const float* __restrict__ gmin,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     float* __restrict__ out, int ldo, int Q, int C) {
+  const int c4n = C >> 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Q * c4n) return;
+  const int q = (int)(i / c4n), c = (int)(i - (size_t)q * c4n) * 4;
+  const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(gmax + (size_t)q * C + c));
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(gmin + (size_t)q * C + c));
+  float4 o;
+  o.x = fmaxf(fmaf(sc.x >= 0.f ? hi.x : lo.x, sc.x, sh.x), 0.f);
+  o.y = fmaxf(fmaf(sc.y >= 0.f ? hi.y : lo.y, sc.y, sh.y), 0.f);
+  o.z = fmaxf(fmaf(sc.z >= 0.f ? hi.z : lo.z, sc.z, sh.z), 0.f);
+  o.w = fmaxf(fmaf(sc.w >= 0.f ? hi.w : lo.w, sc.w, sh.w), 0.f);
+  *reinterpret_cast<float4*>(out + (size_t)q * ldo + c) = o;
 }
 
 __global__ void head_finalize_kernel(const float* __restrict__ out4, int ld, const float* __restrict__ cmean,
@@ -618,6 +656,12 @@ extern "C" int usip_group_select(const float* gmax, const float* gmin, const flo
                                  float* out, int ldo, int Q, int C, void* stream) {
   USIP_REQUIRE(gmax && gmin && scale && shift && out && ldo >= C, "group_select: bad args");
   size_t n = (size_t)Q * C;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(gmax) | reinterpret_cast<uintptr_t>(gmin) | reinterpret_cast<uintptr_t>(scale) |
+                       reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(out);
+  if (C % 4 == 0 && ldo % 4 == 0 && (al & 15) == 0) {
+    group_select4_kernel<<<(unsigned)cdiv64(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(gmax, gmin, scale, shift, out, ldo, Q, C);
+    return check_launch("group_select4_kernel");
+  }
   group_select_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, (cudaStream_t)stream>>>(gmax, gmin, scale, shift, out, ldo, Q, C);
   return check_launch("group_select_kernel");
 }
