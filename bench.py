@@ -45,7 +45,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  `nvidia-smi -lms` needs ~0.1 s before its
+    first line and the timed region of a 1.3 ms step is a few tens of ms, so the sampler is started before the warm-up,
+    every line is time-stamped, and the caller keeps the SAME steps running (untimed) after the timed region until at
+    least three samples lie inside the load window; `window_ms` says how long that window was."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,9 +68,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def count_between(self, t0, t1):
+        return sum(1 for (t, _) in list(self.lines) if t0 <= t <= t1)
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -77,7 +83,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for (t, ln) in self.lines:
+            if t0 is not None and not (t0 <= t <= t1):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -88,8 +96,11 @@ class ClockSampler:
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if t0 is not None:
+            out["window_ms"] = round((t1 - t0) * 1e3, 1)
+        return out
 
 
 def make_batches(nb, cfg, seed0):
@@ -348,11 +359,20 @@ def main():
         md.forward_loss(epoch=0, train_bn=True, graph=use_graph)
 
     use_graph = not args.no_graph
+    sampler = ClockSampler(local); sampler.start()     # before the warm-up: nvidia-smi -lms takes ~0.1 s to its first line
     for i in range(W):
         step_resident(i)
-    sampler = ClockSampler(local); sampler.start()
+    t_load0 = time.time()
     ms, launches = timed(step_resident, K)
-    clocks = sampler.stop()
+    # the timed region is over (ms is final); the same steps keep the GPU under the same load until the sampler has seen it
+    t_load1 = time.time()
+    while sampler.count_between(t_load0, t_load1) < 3 and time.time() - t_load0 < 2.0:
+        for i in range(max(K, 20)):
+            step_resident(i)
+        torch.cuda.synchronize()
+        t_load1 = time.time()
+    clocks = sampler.stop(t_load0, t_load1)
+    clocks["timed_region_ms"] = round(ms, 2)
     clouds = 2 * cfg["B"] * world
     value = clouds * K / (ms * 1e-3)
 

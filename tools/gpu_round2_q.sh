@@ -1,0 +1,24 @@
+#!/bin/bash
+mkdir -p gpurun_out
+TAG=${1:-r02q}
+for f in test_gpu_detector test_gpu_vs_reference; do
+  timeout 1500 python -m pytest tests/$f.py -m gpu -q --timeout=900 -p no:cacheprovider > gpurun_out/pytest_${f}_$TAG.log 2>&1
+  echo "== $f: $(tail -1 gpurun_out/pytest_${f}_$TAG.log)"
+done
+SECONDS=0
+timeout 1200 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_$TAG.err
+echo "bench default rc=$? [${SECONDS}s]"
+python - <<PY
+import json
+j=json.loads(open('gpurun_out/bench_$TAG.json').read().strip().splitlines()[-1])
+print({k:j.get(k) for k in ('value','ms_per_step','steps','warmup','gpu_launches')}, 'e2e', j['e2e']['value']); print(j.get('train_step')); print(j.get('train_step_tf32_backward'))
+print(j.get('roofline',{}).get('kernel'), j.get('roofline',{}).get('frac'), j.get('clocks'))
+d=j.get('descriptor',{}); print({k:d.get(k) for k in ('ball_group_fused','index_max_op','descriptor_forward_eval','descriptor_train_step')})
+print(j.get('reference_gpu',{}).get('tf32_off')); print(j.get('reference_gpu',{}).get('torch_default'))
+PY
+tail -3 gpurun_out/bench_$TAG.err
+timeout 300 python bench.py --steps 20 --warmup 5 --no-train --no-reference-gpu --no-descriptor > gpurun_out/bench_${TAG}_s20.json 2>/dev/null
+python - <<PY
+import json
+j=json.loads(open('gpurun_out/bench_${TAG}_s20.json').read().strip().splitlines()[-1]); print('steps20', j['value'], j['clocks'])
+PY

@@ -282,15 +282,20 @@ bn_finalize_kernel(const float* __restrict__ part, int ntiles, double count, int
 #pragma unroll
       for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
     }
-    float a[8], b[8];
+    if (t < ntiles) {                                          // tail batch: clamped addresses, no branch around the loads
+      float a[8], b[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool ok = t + u * SL < ntiles;
-      a[u] = ok ? __ldg(part + ((size_t)(t + u * SL) * 2 + 0) * C + c) : 0.f;
-      b[u] = ok ? __ldg(part + ((size_t)(t + u * SL) * 2 + 1) * C + c) : 0.f;
+      for (int u = 0; u < 8; ++u) {
+        const int tt = min(t + u * SL, ntiles - 1);
+        a[u] = __ldg(part + ((size_t)tt * 2 + 0) * C + c);
+        b[u] = __ldg(part + ((size_t)tt * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = t + u * SL < ntiles;
+        s += ok ? (double)a[u] : 0.0; ss += ok ? (double)b[u] : 0.0;
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { s += (double)a[u]; ss += (double)b[u]; }
   }
   // a warp holds 4 slices x 8 channels (lane = 8*slice + channel): fold the slices, then the 8 warps
   s += __shfl_xor_sync(0xffffffffu, s, 8); ss += __shfl_xor_sync(0xffffffffu, ss, 8);
