@@ -157,6 +157,11 @@ typedef struct usip_layer_desc {
 } usip_layer_desc;
 
 int usip_layer_fwd(const usip_layer_desc* d, void* stream);
+/* Packs the tensor-core weight tiles of n layers (precision != 0 descriptors: W, ldw, w_transposed, Cin, Cout, P, group /
+ * gmax / gmin, debug_flags and tc_workspace are read) in ONE launch, exactly as usip_layer_fwd does on a call with
+ * tc_weights_packed == 0; afterwards those layers may be launched with tc_weights_packed = 1.  The train step uses it to
+ * re-pack all weight matrices after the optimizer update (26 launches -> 1). */
+int usip_layer_tc_pack_many(const usip_layer_desc* descs, int n, void* stream);
 /* number of [2,Cout] partial rows usip_layer_fwd writes into stat_partial for this descriptor (P, Cout, precision,
    group and whether group outputs are requested must already be filled in): one per 128-row tile for the SIMT kernel,
    one per (CTA, 32-lane quarter) for the persistent tcgen05 kernel.  usip_bn_finalize sums them in a fixed order. */

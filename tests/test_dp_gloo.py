@@ -38,7 +38,16 @@ def _worker(rank, world, port, out_dir):
         dp.allreduce_mean()
         opt.step()
     torch.save([p.detach().clone() for p in net.parameters()], os.path.join(out_dir, "rank%d.pt" % rank))
-    dist.destroy_process_group()
+
+    class _Holder:                                       # stands in for a model that holds captured step graphs
+        released = False
+
+        def release_cuda_graphs(self):
+            self.released = True
+    from usip_b200.dp import shutdown
+    h = _Holder()
+    shutdown(h, hard_exit_after=60)                      # graphs first, then barrier + destroy_process_group
+    assert h.released and not dist.is_initialized()
 
 
 def test_flat_grad_allreduce_two_ranks(tmp_path):

@@ -224,6 +224,43 @@ def test_forward_loss_cuda_graph_matches_eager():
         assert torch.equal(torch.cat([md.src_sigmas, md.dst_sigmas]), eager[2])
 
 
+def test_train_steps_graph_prepack_and_eager_agree():
+    """Four optimize() steps three ways -- (a) eager with every layer packing its own weights, (b) eager with the one-launch
+    re-pack of all stale weight matrices (engine.prepack_weights / usip_layer_tc_pack_many), (c) the captured CUDA graph --
+    must leave the same parameters: the kernels and their order are identical, only who launches the weight packing differs.
+    Scatter-type gradient kernels use atomics, so the comparison allows summation noise."""
+    from usip_b200 import engine
+    keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
+    batches = [orc.synth_pair(2, 2048, 64, 4, kind="lidar", seed=700 + i) for i in range(4)]
+    results, packed_jobs = [], []
+    for mode in ("inline", "prepack", "graph"):
+        g, d, P, md = _setup("detector_kitti_small.npz", True)
+        md.use_cuda_graph = mode == "graph"
+        orig = engine.prepack_weights
+        if mode == "inline":
+            engine.prepack_weights = lambda module: 0
+        else:
+            def counted(module, _orig=orig):
+                n = _orig(module); packed_jobs.append((mode, n)); return n
+            engine.prepack_weights = counted
+        try:
+            for data in batches:
+                md.set_input(*[torch.from_numpy(data[k]) for k in keys])
+                md.optimize(epoch=0)
+            torch.cuda.synchronize()
+        finally:
+            engine.prepack_weights = orig
+        results.append([(n, p.detach().clone()) for n, p in md.detector.named_parameters()])
+    assert any(n > 0 for m, n in packed_jobs if m == "prepack")      # the batched path really ran
+    for other in results[1:]:
+        for (name, a), (_, b) in zip(results[0], other):
+            scale = float(a.abs().max()) + 1e-12
+            # conv biases in front of a BatchNorm have an analytically zero gradient: Adam turns their summation noise into
+            # +-lr steps, so biases only get a "did not run away" bound (4 steps x lr = 4e-3)
+            slack = 1e-2 if name.endswith("bias") else 0.0
+            assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-6 + slack, name
+
+
 def test_prefetch_input_matches_set_input():
     """prefetch_input() stages the next batch on a copy stream; set_input() with the same tensors adopts it, with other
     tensors it copies as usual.  The loss must be the one of the batch passed to set_input either way."""

@@ -57,6 +57,7 @@ SIGNATURES = {
     "usip_cluster_mean_decenter": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
                                            c_int, c_int, c_int, c_int, c_ptr]),
     "usip_layer_fwd": (c_int, [ctypes.POINTER(LayerDesc), c_ptr]),
+    "usip_layer_tc_pack_many": (c_int, [ctypes.POINTER(LayerDesc), c_int, c_ptr]),
     "usip_layer_tile_rows": (c_int, []),
     "usip_fps_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr]),
     "usip_nms_f32": (c_int, [c_ptr, c_ptr, ctypes.c_float, c_ptr, c_ptr, c_int, c_int, c_ptr]),

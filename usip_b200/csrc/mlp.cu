@@ -585,6 +585,7 @@ static int launch_layer_simt(const usip_layer_desc& d, cudaStream_t st) {
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st);   // mlp_tc.cu
 int tc_stat_slots(const usip_layer_desc& d);
+int tc_pack_many(const usip_layer_desc* descs, int n, cudaStream_t st);
 
 }  // namespace usip
 
@@ -596,6 +597,12 @@ extern "C" int usip_layer_stat_slots(const usip_layer_desc* dp) {
   return dp->precision != 0 ? tc_stat_slots(*dp) : cdiv(dp->P, L_BM);
 }
 extern "C" int64_t usip_layer_tc_workspace_bytes(int Cin, int Cout) { return (int64_t)2 * Cin * Cout * 4; }
+
+extern "C" int usip_layer_tc_pack_many(const usip_layer_desc* descs, int n, void* stream) {
+  USIP_REQUIRE(descs && n > 0, "layer_tc_pack_many: bad args");
+  for (int i = 0; i < n; ++i) USIP_REQUIRE(descs[i].precision != 0, "layer_tc_pack_many: descriptor is not a tensor-core layer");
+  return tc_pack_many(descs, n, (cudaStream_t)stream);
+}
 
 extern "C" int usip_layer_fwd(const usip_layer_desc* dp, void* stream) {
   USIP_REQUIRE(dp, "layer_fwd: null desc");

@@ -71,11 +71,10 @@ __device__ __forceinline__ uint32_t bf16_tile_off(int r, int c) {
 //   mixed == 1 (this kernel):             [w_hi TF32, BN x 128 B, SWIZZLE_128B | bf16(w_hi), BN x 64 B, SWIZZLE_64B |
 //                                          bf16(w - w_hi), BN x 64 B, SWIZZLE_64B]          (same 256 B per row)
 // ------------------------------------------------------------------------------------------------
-__global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int transposed, int Cout, int Cin, int BN,
-                                       int mixed, uint32_t* __restrict__ out) {
+__device__ __forceinline__ void tc_pack_one(const float* __restrict__ W, int ldw, int transposed, int Cout, int Cin, int BN,
+                                            int mixed, uint32_t* __restrict__ out, int t) {
   const int KC = Cin / TC_BK;
   const int total = Cout * (Cin / 4);                 // one thread per 4 consecutive k
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int n = t / (Cin / 4), k4 = t - n * (Cin / 4);
   const int kc = k4 / 8, c = k4 & 7;                  // 16-byte chunk c of K chunk kc
@@ -101,6 +100,28 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int
     *reinterpret_cast<uint2*>(base + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
     *reinterpret_cast<uint2*>(base + (size_t)BN * 64 + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
   }
+}
+
+__global__ void tc_pack_weights_kernel(const float* __restrict__ W, int ldw, int transposed, int Cout, int Cin, int BN,
+                                       int mixed, uint32_t* __restrict__ out) {
+  tc_pack_one(W, ldw, transposed, Cout, Cin, BN, mixed, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// Many layers in ONE launch (the train step re-packs all 26 weight matrices after every Adam update): the block index is
+// mapped to (layer, block of that layer) through a prefix table that travels in the kernel parameters.
+constexpr int TC_PACK_MANY = 32;
+struct TcPackMany {
+  int n;
+  int blk0[TC_PACK_MANY + 1];
+  const float* W[TC_PACK_MANY];
+  uint32_t* out[TC_PACK_MANY];
+  int ldw[TC_PACK_MANY], transposed[TC_PACK_MANY], Cout[TC_PACK_MANY], Cin[TC_PACK_MANY], BN[TC_PACK_MANY], mixed[TC_PACK_MANY];
+};
+__global__ void tc_pack_many_kernel(const __grid_constant__ TcPackMany pm) {
+  int i = 0;
+  while (i + 1 < pm.n && (int)blockIdx.x >= pm.blk0[i + 1]) ++i;
+  tc_pack_one(pm.W[i], pm.ldw[i], pm.transposed[i], pm.Cout[i], pm.Cin[i], pm.BN[i], pm.mixed[i], pm.out[i],
+              ((int)blockIdx.x - pm.blk0[i]) * (int)blockDim.x + (int)threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,6 +642,31 @@ static int tc_pick_bn(const usip_layer_desc& d) {
 int tc_stat_slots(const usip_layer_desc& d) {
   const int BN = tc_pick_bn(d);
   return tc_grid(d.P, d.Cout, BN, tc_sm_count()) / (d.Cout / BN) * 4;
+}
+
+// Packs the weights of n tensor-core layers exactly as layer_fwd_tc() would on a call with tc_weights_packed == 0 (same
+// column-tile choice, same hi/lo or mixed layout), in ceil(n / 32) launches.
+int tc_pack_many(const usip_layer_desc* descs, int n, cudaStream_t st) {
+  for (int i0 = 0; i0 < n; i0 += TC_PACK_MANY) {
+    TcPackMany pm;
+    pm.n = min(TC_PACK_MANY, n - i0);
+    int blocks = 0;
+    for (int i = 0; i < pm.n; ++i) {
+      const usip_layer_desc& d = descs[i0 + i];
+      USIP_REQUIRE(d.W && d.tc_workspace && d.Cin % TC_BK == 0 && d.Cout % 64 == 0 &&
+                   d.tc_workspace_bytes >= (int64_t)2 * d.Cout * d.Cin * 4, "tc_pack_many: bad descriptor");
+      pm.blk0[i] = blocks;
+      pm.W[i] = d.W; pm.out[i] = reinterpret_cast<uint32_t*>(d.tc_workspace);
+      pm.ldw[i] = d.ldw; pm.transposed[i] = d.w_transposed; pm.Cout[i] = d.Cout; pm.Cin[i] = d.Cin;
+      pm.BN[i] = tc_pick_bn(d); pm.mixed[i] = (d.debug_flags & 16) ? 1 : 0;
+      blocks += cdiv(d.Cout * (d.Cin / 4), 256);
+    }
+    pm.blk0[pm.n] = blocks;
+    tc_pack_many_kernel<<<blocks, 256, 0, st>>>(pm);
+    int e = check_launch("tc_pack_many_kernel");
+    if (e) return e;
+  }
+  return 0;
 }
 
 int layer_fwd_tc(const usip_layer_desc& d, cudaStream_t st) {

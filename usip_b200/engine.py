@@ -78,19 +78,61 @@ class BNState:
 # Packed (hi/lo TF32, pre-swizzled) weight tiles are cached per weight view and re-used while the parameter's
 # autograd version counter is unchanged (inference / fwd-only loops); an optimizer step bumps the version and the
 # next launch re-packs into the same workspace.
+class _PackEntry:
+    """One packed-weight workspace: the version it was packed at, and -- once the layer has run -- a copy of its descriptor,
+    so that prepack_weights() can re-pack it together with all the others in one launch."""
+    __slots__ = ("ver", "ws", "ptr", "desc", "keep", "used_step")
+
+    def __init__(self, ver, ws, ptr):
+        self.ver, self.ws, self.ptr, self.desc, self.keep, self.used_step = ver, ws, ptr, None, None, -1
+
+
+_PACK_STEP = [0]
+
+
 def _tc_workspace(W, P, Cin, Cout, group, transposed, prec=1):
+    """-> (workspace, already_packed, entry or None)"""
     owner = getattr(W, "_owner", None)
     if owner is None:                                  # unknown provenance: never reuse packed tiles
-        return torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device), False
+        return torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device), False, None
     cache = owner.__dict__.setdefault("_usip_tc", {})  # lives and dies with the Parameter object
     key = (W.data_ptr() - owner.data_ptr(), W.stride(0), P, Cin, Cout, bool(transposed), group > 32, prec)
     ver = (owner._version, _lib.WEIGHT_GEN[0])
     ent = cache.get(key)
-    if ent is not None and ent[0] == ver and ent[2] == owner.data_ptr():
-        return ent[1], True
-    ws = ent[1] if ent is not None else torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device)
-    cache[key] = (ver, ws, owner.data_ptr())
-    return ws, False
+    if ent is not None and ent.ver == ver and ent.ptr == owner.data_ptr():
+        ent.used_step = _PACK_STEP[0]
+        return ent.ws, True, ent
+    if ent is None or ent.ptr != owner.data_ptr():
+        ent = _PackEntry(ver, ent.ws if ent is not None else torch.empty((2 * Cin * Cout,), dtype=f32, device=W.device),
+                         owner.data_ptr())
+        cache[key] = ent
+    ent.ver = ver
+    ent.used_step = _PACK_STEP[0]
+    return ent.ws, False, ent
+
+
+def prepack_weights(module):
+    """Re-pack, in ONE launch (usip_layer_tc_pack_many), every tensor-core weight matrix of `module` that went stale since it
+    was last packed (an optimizer step moved the weights) and was used by the previous step.  The train step calls this first:
+    its 26 per-layer pack launches become one.  Layers that have not run yet are packed by their own first launch."""
+    jobs = []
+    step = _PACK_STEP[0]
+    for p in module.parameters():
+        cache = p.__dict__.get("_usip_tc")
+        if not cache:
+            continue
+        ver = (p._version, _lib.WEIGHT_GEN[0])
+        for ent in cache.values():
+            if ent.desc is not None and ent.used_step == step and ent.ver != ver and ent.ptr == p.data_ptr():
+                jobs.append((ent, ver))
+    _PACK_STEP[0] = step + 1
+    if not jobs:
+        return 0
+    arr = (ops.LayerDesc * len(jobs))(*[ent.desc for ent, _ in jobs])
+    ops.check(_lib.load().usip_layer_tc_pack_many(arr, len(jobs), ops._stream()), "usip_layer_tc_pack_many")
+    for ent, ver in jobs:
+        ent.ver = ver
+    return len(jobs)
 
 
 def invalidate_packed_weights(module):
@@ -163,7 +205,7 @@ class LayerRunner:
             if want_arg:
                 grp["amax"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
                 grp["amin"] = torch.empty((Q, Cout), dtype=i32, device=self.dev)
-        ws, packed = _tc_workspace(W, P, Cin, Cout, group if want_group else 0, False, prec) if prec else (None, False)
+        ws, packed, pack_ent = _tc_workspace(W, P, Cin, Cout, group if want_group else 0, False, prec) if prec else (None, False, None)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cin, Cout), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(X, W, bias, P, Cin, Cout,
@@ -174,7 +216,7 @@ class LayerRunner:
                           gmax=None if grp is None else grp["gmax"], gmin=None if grp is None else grp["gmin"],
                           garg_max=None if grp is None else grp.get("amax"),
                           garg_min=None if grp is None else grp.get("amin"),
-                          group=group, precision=prec, tc_ws=ws, tc_packed=packed)
+                          group=group, precision=prec, tc_ws=ws, tc_packed=packed, pack_entry=pack_ent)
         st = None
         if norm is not None:
             with _Prof("bn_finalize"):
@@ -439,11 +481,11 @@ class _Bwd:
         if out is None:
             out = torch.empty((P, Cin), dtype=f32, device=self.dev)
         prec = _precision_for(P, Cout, Cin, self.use_tc)
-        ws, packed = _tc_workspace(W2d, P, Cout, Cin, 0, True, prec) if prec else (None, False)
+        ws, packed, pack_ent = _tc_workspace(W2d, P, Cout, Cin, 0, True, prec) if prec else (None, False, None)
         with _Prof("%s[%dx%d->%d]" % (name, P, Cout, Cin), flops=2.0 * P * Cin * Cout,
                    precision="3xTF32 tcgen05" if prec else "fp32 SIMT"):
             ops.layer_fwd(GY, W2d, None, P, Cout, Cin, Y=out, precision=prec, w_transposed=True, tc_ws=ws, tc_packed=packed,
-                          debug_flags=8 if (self.tf32_bwd and prec) else 0)
+                          debug_flags=8 if (self.tf32_bwd and prec) else 0, pack_entry=pack_ent)
         return out
 
     def colsum(self, G, out, P, C):

@@ -208,6 +208,7 @@ class ModelDetector():
         """keypoint_detector.py:170-205 without autograd: same kernels as the autograd Functions in losses.py / networks.py."""
         net, opt = self.detector, self.opt
         B = self.src_pc.shape[0]
+        engine.prepack_weights(net)                     # all weight matrices the last Adam step made stale: one launch
         x = torch.cat((self.src_pc, self.dst_pc), dim=0)
         sn = torch.cat((self.src_sn, self.dst_sn), dim=0)
         node = torch.cat((self.src_node, self.dst_node), dim=0)
