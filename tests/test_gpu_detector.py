@@ -228,7 +228,9 @@ def test_train_steps_graph_prepack_and_eager_agree():
     """Four optimize() steps three ways -- (a) eager with every layer packing its own weights, (b) eager with the one-launch
     re-pack of all stale weight matrices (engine.prepack_weights / usip_layer_tc_pack_many), (c) the captured CUDA graph --
     must leave the same parameters: the kernels and their order are identical, only who launches the weight packing differs.
-    Scatter-type gradient kernels use atomics, so the comparison allows summation noise."""
+    The bound is relative to how far the four steps moved each tensor (~4 lr): arg-max routing and atomic summation order make
+    single gradient elements differ at the 1e-2 level between two runs of the SAME mode, which Adam turns into a few percent of
+    a step; a layer that ran on stale packed weights would be off by a whole step."""
     from usip_b200 import engine
     keys = ("src_pc", "src_sn", "src_node", "dst_pc", "dst_sn", "dst_node", "R", "scale", "shift")
     batches = [orc.synth_pair(2, 2048, 64, 4, kind="lidar", seed=700 + i) for i in range(4)]
@@ -236,6 +238,7 @@ def test_train_steps_graph_prepack_and_eager_agree():
     for mode in ("inline", "prepack", "graph"):
         g, d, P, md = _setup("detector_kitti_small.npz", True)
         md.use_cuda_graph = mode == "graph"
+        init = {n: p.detach().clone() for n, p in md.detector.named_parameters()}
         orig = engine.prepack_weights
         if mode == "inline":
             engine.prepack_weights = lambda module: 0
@@ -254,11 +257,11 @@ def test_train_steps_graph_prepack_and_eager_agree():
     assert any(n > 0 for m, n in packed_jobs if m == "prepack")      # the batched path really ran
     for other in results[1:]:
         for (name, a), (_, b) in zip(results[0], other):
-            scale = float(a.abs().max()) + 1e-12
+            moved = float((a - init[name]).abs().max())
             # conv biases in front of a BatchNorm have an analytically zero gradient: Adam turns their summation noise into
             # +-lr steps, so biases only get a "did not run away" bound (4 steps x lr = 4e-3)
             slack = 1e-2 if name.endswith("bias") else 0.0
-            assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-6 + slack, name
+            assert float((a - b).abs().max()) <= 0.15 * moved + 1e-6 + slack, (name, moved)
 
 
 def test_prefetch_input_matches_set_input():

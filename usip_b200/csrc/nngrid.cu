@@ -1,14 +1,17 @@
-// nngrid.cu -- exact nearest neighbour of a few queries in a large point set through a per-cloud cell grid.
+// nngrid.cu -- exact nearest neighbour through a per-cloud cell grid (cubic cells, counting-sorted entries).
 //
-// Replaces the brute-force pairwise_min_kernel for the "keypoint on point cloud" searches of the detector loss
-// (models/keypoint_detector.py:187-197 -> losses.py:125-143: min_j ||kp_i - pc_j||, 512 keypoints against 16384 points per
-// cloud): 8.4 M distance evaluations per cloud become a counting sort of the cloud into <= 8192 cells (one CTA per cloud,
-// histogram / scan / scatter in shared memory) and, per query, a scan of the cell shells around it until the best distance
-// is provably smaller than anything outside the scanned cube.
+// Two users on the detector path, both replacing brute-force scans that sat at their fp32-issue bound:
+//   * usip_pairwise_min_grid_f32: the "keypoint on point cloud" searches of the loss (models/keypoint_detector.py:187-197 ->
+//     losses.py:125-143: min_j ||kp_i - pc_j||, 512 keypoints against 16384 points per cloud).  The cloud is binned by many
+//     CTAs (ng_bin_kernel / ng_scatter_kernel), one warp per keypoint walks the cell shells (ng_query_kernel).
+//   * usip_som_assign_grid_f32: nearest node of every point (util/som.py:17-54, k = 1).  The <= 1024 nodes are sorted by one
+//     CTA per cloud (ng_build_kernel) and staged in shared memory, one thread per point searches (ng_assign_kernel).
+// A search scans the cells of ring r = 0, 1, ... around the query and stops when the best distance is provably smaller than
+// anything outside the scanned cube.
 //
-// Same arithmetic and tie rule as the brute-force kernels (csrc/loss.cu): d2 = (dx*dx + dy*dy) + dz*dz without FMA,
-// smaller distance first, then smaller point index; non-finite points are never selected (their d2 is NaN or inf, which
-// `d < best` rejects in the reference formulation as well), a query with no selectable point yields (inf, 0).
+// Same arithmetic and tie rule as the brute-force kernels (csrc/loss.cu, csrc/group.cu): d2 = (dx*dx + dy*dy) + dz*dz without
+// FMA, smaller distance first, then smaller index; non-finite entries are never selected (their d2 is NaN or inf, which
+// `d < best` rejects in the reference formulation as well); a query with no selectable entry yields (inf, 0) / node 0.
 #include "common.cuh"
 
 namespace usip {
@@ -305,27 +308,17 @@ ng_scatter_kernel(const float* __restrict__ pts, int N, const int32_t* __restric
     }
 }
 
-// Shell search around (ax, ay, az): cells of ring r = 0, 1, ... until the best squared distance is smaller than the distance
-// to everything outside the scanned cube.  WARP: the 32 lanes stride over every cell range and merge after each ring;
-// otherwise one thread walks the ranges alone.  (best, bidx) = lexicographic minimum of (d2, original index).
-template <bool WARP>
+// Shell search of ONE thread around (ax, ay, az): cells of ring r = 0, 1, ... until the best squared distance is smaller than
+// the distance to everything outside the scanned cube (the warp-per-query kernel below has its own, flattened form).
+// (best, bidx) = lexicographic minimum of (d2, original index).
 __device__ __forceinline__ void ng_search(float ax, float ay, float az, const NgGrid g, const int32_t* cs, const float4* pts,
-                                          int cnt, int lane, float& best, int& bidx) {
+                                          int cnt, float& best, int& bidx) {
   auto scan = [&](int s, int e) {
-    for (int t = s + (WARP ? lane : 0); t < e; t += (WARP ? 32 : 1)) {
+    for (int t = s; t < e; ++t) {
       const float4 p = pts[t];
       const float d = sqdist_rn(ax, ay, az, p.x, p.y, p.z);
       const int n = __float_as_int(p.w);
       if (d < best || (d == best && n < bidx)) { best = d; bidx = n; }
-    }
-  };
-  auto reduce = [&]() {
-    if (WARP) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-      }
     }
   };
   const int cx = ng_cell1(ax, g.ox, g.inv_h, g.nx), cy = ng_cell1(ay, g.oy, g.inv_h, g.ny), cz = ng_cell1(az, g.oz, g.inv_h, g.nz);
@@ -344,7 +337,6 @@ __device__ __forceinline__ void ng_search(float ax, float ay, float az, const Ng
         }
       }
     }
-    reduce();
     // everything outside the cube of half-width r is at least `lb` away (faces beyond the grid do not count)
     float lb = INFINITY;
     if (cx - r > 0) lb = fminf(lb, ax - (g.ox + (float)(cx - r) * g.h));
@@ -357,7 +349,7 @@ __device__ __forceinline__ void ng_search(float ax, float ay, float az, const Ng
     lb = fmaxf(lb - 1e-3f * g.h, 0.f);                            // cell assignment rounds: keep a margin of h/1000
     if (best < lb * lb) done = true;
   }
-  if (!done) { scan(0, cnt); reduce(); }                          // far query: the whole sorted set (duplicates are harmless)
+  if (!done) scan(0, cnt);                                        // far query: the whole sorted set (duplicates are harmless)
 }
 
 // One warp per query.  The cell ranges of a shell are fetched by all lanes at once (lane = one range: a face row's whole x
@@ -489,7 +481,7 @@ ng_assign_kernel(const float* __restrict__ xyz, int N, int M, const float4* __re
   const float* px = xyz + (size_t)b * 3 * N;
   const float x = px[n], y = px[N + n], z = px[2 * N + n];
   float best = INFINITY; int bi = 0x7fffffff;
-  if (ng_finite3(x, y, z) && cnt > 0) ng_search<false>(x, y, z, g, scs, snode, cnt, 0, best, bi);
+  if (ng_finite3(x, y, z) && cnt > 0) ng_search(x, y, z, g, scs, snode, cnt, best, bi);
   if (!(best < INFINITY)) bi = 0;
   min_idx[(size_t)b * N + n] = bi;
   if (count) atomicAdd(&count[(size_t)b * M + bi], 1);
