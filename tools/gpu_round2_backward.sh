@@ -1,8 +1,10 @@
 #!/bin/bash
+# backward pass of the round-2 loop: wgrad micro-benchmark (A/B against usip_b200/lib/libusip_b200_prev.so when that older build
+# is present), nearest-neighbour micro-benchmark, GPU tests, default bench, ball-group launch list, ncu capture of one train step
 mkdir -p gpurun_out
 TAG=${1:-r02j}
 python tools/wgrad_microbench.py > gpurun_out/wgrad_new_$TAG.json 2> gpurun_out/wgrad_new_$TAG.err
-python tools/wgrad_microbench.py usip_b200/lib/libusip_b200_prev.so > gpurun_out/wgrad_prev_$TAG.json 2> gpurun_out/wgrad_prev_$TAG.err
+[ -f usip_b200/lib/libusip_b200_prev.so ] && python tools/wgrad_microbench.py usip_b200/lib/libusip_b200_prev.so > gpurun_out/wgrad_prev_$TAG.json 2> gpurun_out/wgrad_prev_$TAG.err
 python - <<PY
 import json
 try:

@@ -1,4 +1,6 @@
 #!/bin/bash
+# forward pass of the round-2 loop: GPU tests, ncu launch list of the nearest-neighbour kernels, quick bench, ncu launch list of
+# one eager fwd+loss step
 mkdir -p gpurun_out
 TAG=${1:-r02l}
 for f in test_gpu_ops test_gpu_detector test_gpu_vs_reference; do
