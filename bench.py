@@ -137,13 +137,37 @@ def _ref_fwd_loss_train_bn(rmd):
     return rmd.loss
 
 
+def _calibrate_cpu_threads(cfg, step_fn):
+    """Thread count for the reference's CPU run.  ~90 % of its time is `torch.norm(diff, dim=1)` over the (B,3,N,M) tensors of
+    som.query_topk / the chamfer losses (util/som.py:30-34, losses.py:62-66) -- a reduction over a dimension of size 3 that
+    torch parallelises badly: with all 128 threads of the GPU box one pair took 19.5 s, with 8 threads of another host 2.7 s.
+    The arm therefore times ONE quarter-size step (N/4 points, same M) of the reference itself at a few thread counts and
+    keeps the fastest; it reports the count it used."""
+    import torch
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (n, n // 2, n // 4, n // 8, 16, 8) if 1 <= c <= n}, reverse=True)
+    best_t, best_c, log = float("inf"), n, []
+    for c in cands:
+        torch.set_num_threads(c)
+        step_fn()
+        t0 = time.perf_counter()
+        step_fn()
+        dt = time.perf_counter() - t0
+        log.append("%d: %.2f s" % (c, dt))
+        if dt < best_t:
+            best_t, best_c = dt, c
+    return best_c, ", ".join(log)
+
+
 def cpu_reference_run(cfg, steps, warmup, threads=None):
     """The reference's CPU path on a bounded sample: ONE pair (2 clouds) of the same workload per step.
     kind="reference": the unmodified reference (oracle/_ref/py, its own C++ index_max.forward_cpu) through oracle/ref_shim;
     kind="port": the numpy/C oracle restatement, only when the reference is not staged."""
     from oracle import usip_oracle as orc
     import torch
-    threads = threads or os.cpu_count()
+    tried = None
+    calibrate = threads is None
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     d = orc.synth_pair(1, cfg["N"], cfg["M"], cfg["S"], kind=cfg["kind"], seed=999)
     P = orc.init_detector_params(S=cfg["S"], seed=0)
@@ -157,6 +181,15 @@ def cpu_reference_run(cfg, steps, warmup, threads=None):
             load_params(rmd.detector, P)
             rmd.set_input(*[torch.from_numpy(d[k]) for k in KEYS])
             kind = "reference"
+            if calibrate:
+                cal = dict(cfg); cal["N"] = max(1024, cfg["N"] // 4)
+                dc = orc.synth_pair(1, cal["N"], cal["M"], cal["S"], kind=cal["kind"], seed=998)
+                cmd = ref.keypoint_detector.ModelDetector(_ref_opt(ref_shim, cal, 1))
+                load_params(cmd.detector, P)
+                cmd.set_input(*[torch.from_numpy(dc[k]) for k in KEYS])
+                threads, tried = _calibrate_cpu_threads(cfg, lambda: float(_ref_fwd_loss_train_bn(cmd)))
+                torch.set_num_threads(threads)
+                del cmd
     except Exception as e:  # pragma: no cover
         print("[bench] reference CPU path unavailable (%s); timing the oracle port" % e, file=sys.stderr)
         kind = "port"
@@ -182,8 +215,9 @@ def cpu_reference_run(cfg, steps, warmup, threads=None):
     del limiter
     t = float(np.mean(times))
     what = ("unmodified reference ModelDetector (models/keypoint_detector.py:209-241, train-mode BN, no_grad) on CPU, "
-            "torch %d threads, its own C++ index_max.forward_cpu" % threads) if kind == "reference" else \
-           "numpy/BLAS + C oracle port"
+            "torch %d of %d threads%s, its own C++ index_max.forward_cpu"
+            % (threads, os.cpu_count() or 1, (" (fastest of a quarter-size step at %s)" % tried) if tried else "")) \
+        if kind == "reference" else "numpy/BLAS + C oracle port"
     return dict(value=2.0 / t, unit="clouds/s", cores=int(threads), kind=kind,
                 sample="%d x (1 pair = 2 clouds, N=%d, M=%d) fwd+loss, %s; %.2f s per pair"
                        % (len(times), cfg["N"], cfg["M"], what, t)), t
